@@ -1,0 +1,200 @@
+/*
+ * re2nn_b200.h — C-ABI of the B200-native RE2NN-SEQ transducer hot path.
+ *
+ * The reference (jeffchy/RE2NN-SEQ) is pure Python/PyTorch and has NO FFI / plugin / custom-op
+ * interface.  Its boundary for this path is the nn.Module surface of
+ * src_seq/farnn/*.py and src_seq/baselines/crf.py.  Each entry point below replaces the torch-op
+ * sequence of one reference method (cited file:line, relative to /root/reference/src_seq/) and is
+ * what a ctypes binding added to those modules would call.
+ *
+ * Conventions
+ *   - plain C, no torch types.  Every pointer is a DEVICE pointer unless the name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - float = fp32, indices/lengths/labels = int64 exactly as the reference holds them
+ *     (data.py:205-207).  Row-major, innermost dimension contiguous.
+ *   - return value: 0 on success, non-zero on error; re2nn_last_error() gives the message.
+ *     Errors are reported, never abort()ed (reference raises Python exceptions).
+ *   - no hidden global state: scratch memory is caller-provided (`ws`, size from *_workspace()).
+ *
+ * Index semantics: for a sequence of n tokens, alpha[b,t,:] (t<n) is the forward
+ * state after consuming tokens 0..t; beta[b,t,:] is the backward state after consuming tokens
+ * n-1..t+1 (beta[b,n-1,:] = hT).  The i-FST score of position t uses exactly these two rows.
+ */
+#ifndef RE2NN_B200_H
+#define RE2NN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RE2NN_ABI_VERSION 1
+
+/* update_nonlinear / additional_nonlinear (model_decompose_single.py:184-191, model_decompose.py:228-237) */
+enum { RE2NN_NL_NONE = 0, RE2NN_NL_RELU = 1, RE2NN_NL_TANH = 2, RE2NN_NL_RELUTANH = 3, RE2NN_NL_SIGMOID = 4 };
+/* arithmetic used by the recurrence GEMMs */
+enum {
+  RE2NN_PREC_FP32 = 0,      /* fp32 FFMA on CUDA cores: bit-for-bit the reference's operand precision */
+  RE2NN_PREC_BF16 = 1,      /* tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM */
+  RE2NN_PREC_TF32X3 = 2     /* tcgen05 kind::tf32, 3-term split (hi*hi + hi*lo + lo*hi): fp32-grade */
+};
+/* how the per-step rank factor v_t is addressed */
+enum {
+  RE2NN_V_TOKEN = 0,        /* v_t = vtab[x[b,t]]           (FARNN_S_D_W_I_S, token ids)          */
+  RE2NN_V_DENSE = 1         /* v_t = vtab[b*Lpad + t]       (FARNN_S_SF, pre-computed B x L x R)  */
+};
+
+int re2nn_abi_version(void);
+const char* re2nn_last_error(void);
+/* 1 if the running device is sm_100 and the tcgen05 kernels were compiled in. */
+int re2nn_has_tcgen05(void);
+
+/* ---- in-library kernel timing (used by bench.py for the roofline line) --------------------------------
+ * When enabled, every step-GEMM launch of re2nn_decompose_recurrence is bracketed by CUDA events on
+ * its own stream.  re2nn_profile_read synchronises those events, returns the summed milliseconds and
+ * launch counts per kernel class (0 = gate GEMM, 1 = GEMM1 + Q epilogue, 2 = GEMM2 + state epilogue)
+ * and resets the counters. */
+int re2nn_profile_enable(int on);
+int re2nn_profile_read(double* ms_out_host, int64_t* count_out_host);
+
+/* ---- generalised token factor table ------------------------------------------------------------
+ * table[r, :] = V_embed[r,:]*beta_vec + phi_add(E[r,:] @ G) * (1 - beta_vec)   for r in [0, rows)
+ * replaces get_generalized_v_embed_vec (farnn/model_decompose.py:222-241) evaluated per token id;
+ * hoisted out of the time loop because it only depends on the token. */
+int re2nn_token_table(const float* V_embed, const float* E, const float* G, const float* beta_vec,
+                      int rows, int D, int R, int additional_nonlinear, float* table, void* stream);
+
+/* ---- gate addend table --------------------------------------------------------------------------
+ * gate[r, 0:S]  = vtab[r,:] @ Wrs1 + bs1 ;  gate[r, S:2S] = vtab[r,:] @ Wrs2 + bs2  (farnn==2)
+ * the token-only part of zt/rt (farnn/model_decompose_single.py:147-150). */
+int re2nn_gate_table(const float* vtab, int rows, int R, int S, int farnn,
+                     const float* Wrs1, const float* bs1, const float* Wrs2, const float* bs2,
+                     float* gate, void* stream);
+
+/* ---- output-vector sum ------------------------------------------------------------------------------
+ * o[s] = sum_c C_mat[c,s] (+ wildcard_vec[s] if wildcard_vec != NULL, i.e. local_loss_func != 'CE1');
+ * model_decompose_single.py:231-234, model_onehot.py:367-370.  Deterministic column sum. */
+int re2nn_output_vector_sum(const float* C_mat, int C, int S, const float* wildcard_vec, float* o,
+                            void* stream);
+
+/* ---- decompose i-FST recurrence, both directions ------------------------------------------------
+ * replaces the L-step loop of FARNN_S_D_W_I_S.forward_local / FARNN_S_SF.forward and
+ * get_forward_score (farnn/model_decompose_single.py:138-200, 236-261, 417-481, 511-534),
+ * including reverse()/cat()/reverse() (utils.py:183-189): beta is written at un-reversed indices. */
+typedef struct re2nn_recurrence_args {
+  int32_t B, Lpad, L;          /* batch, row stride of x (tokens per row), steps to run (= max length) */
+  int32_t S, R;                /* states (incl. additional_states), rank */
+  int32_t farnn;               /* 0 plain, 1 update gate, 2 update+reset gates */
+  int32_t update_nonlinear;    /* RE2NN_NL_* */
+  int32_t precision;           /* RE2NN_PREC_* */
+  int32_t v_mode;              /* RE2NN_V_* */
+  int32_t full_pad;            /* 1: also compute pad positions exactly like the reference does */
+  int32_t save_for_backward;   /* 1: keep per-step gate values (zt, rt) for re2nn_decompose_backward */
+  float sigmoid_exponent;
+  const int64_t* x;            /* B x Lpad token ids (RE2NN_V_TOKEN) or NULL */
+  const int64_t* lengths;      /* B */
+  const float* vtab;           /* rows x R  (token table or dense v) */
+  const float* gtab;           /* rows x (S*farnn) gate addends, NULL if farnn==0 */
+  const float* S1;             /* S x R */
+  const float* S2;             /* S x R */
+  const float* W;              /* S x S wildcard_mat */
+  const float* o;              /* S  output_vector_sum (model_decompose_single.py:231-234) */
+  const float* h0;             /* S */
+  const float* hT;             /* S */
+  const float* Wss1;           /* S x S (farnn>=1) */
+  const float* Wss2;           /* S x S (farnn==2) */
+  float* alpha;                /* B x L x S out */
+  float* beta;                 /* B x L x S out */
+  float* zsave;                /* 2 x L x B x S (farnn>=1 && save_for_backward) or NULL */
+  float* rsave;                /* 2 x L x B x S (farnn==2 && save_for_backward) or NULL */
+  void* ws;                    /* scratch, >= re2nn_decompose_recurrence_workspace() bytes */
+  size_t ws_bytes;
+} re2nn_recurrence_args;
+
+size_t re2nn_decompose_recurrence_workspace(const re2nn_recurrence_args* a);
+int re2nn_decompose_recurrence(const re2nn_recurrence_args* a, void* stream);
+
+/* ---- onehot i-FST recurrence, both directions ---------------------------------------------------
+ * replaces FARNN_S_O_I_S.forward_score's recurrence (farnn/model_onehot.py:358-415):
+ * T = language_tensor[x_t] + wildcard_mat is formed on the fly (no V x S x S temporary),
+ * fwd h <- phi((h (.) T) * o), bwd h <- phi((h*o) (.) T^T), (.) = sum- or max-product (utils.py:192-199). */
+typedef struct re2nn_onehot_args {
+  int32_t B, Lpad, L, S;
+  int32_t update_nonlinear;
+  int32_t max_semiring;        /* train_mode == 'max' */
+  int32_t full_pad;
+  const int64_t* x;
+  const int64_t* lengths;
+  const float* language;       /* (V+1) x S x S */
+  const float* W;              /* S x S */
+  const float* o;              /* S */
+  const float* h0;
+  const float* hT;
+  float* alpha;                /* B x L x S */
+  float* beta;                 /* B x L x S */
+} re2nn_onehot_args;
+int re2nn_onehot_recurrence(const re2nn_onehot_args* a, void* stream);
+
+/* ---- per-position label scores -------------------------------------------------------------------
+ * scores[b,t,c] = sum_s C[c,s] * alpha[b,t,s] * beta[b,t,s]  for t < lengths[b] (all t if full_pad);
+ * replaces get_final_score + its L-step loop (model_decompose_single.py:202-205,263-269;
+ * model_onehot.py:346-349,417-426).  Optional PriorityLayer (priority.py:20-30) is applied when
+ * priority_mat != NULL: scores <- scores @ priority_mat + priority_bias.  Rows past the length are
+ * written as 0. */
+int re2nn_label_scores(const float* alpha, const float* beta, const int64_t* lengths,
+                       int B, int L, int S, const float* C_mat, int C,
+                       const float* priority_mat, const float* priority_bias, int full_pad,
+                       float* scores /* B x L x C */, float* ws /* B*L*C floats if priority */,
+                       void* stream);
+
+/* ---- argmax decode --------------------------------------------------------------------------------
+ * replaces decode()'s non-CRF branch / local_decode / forward_RE (model_decompose.py:363-369,
+ * model_onehot.py:148-180): optional clamp of column clamp_col to `threshold`, first-max argmax,
+ * remap clamp_col -> o_idx.  clamp_col < 0 disables clamp+remap (local_loss_func != 'CE1').
+ * flat_pred (N = sum lengths, batch-major; offsets = exclusive prefix sum of lengths) and/or
+ * padded_pred (B x L, every position decoded) may be NULL. */
+int re2nn_argmax_decode(const float* scores, const int64_t* lengths, const int64_t* offsets,
+                        int B, int L, int C, int clamp_col, float threshold, int64_t o_idx,
+                        int64_t* flat_pred, int64_t* padded_pred, void* stream);
+
+/* ---- CRF Viterbi ------------------------------------------------------------------------------------
+ * replaces CRF._viterbi_decode (baselines/crf.py:102-195) plus decode()'s CRF branch
+ * (model_decompose.py:349-359).  feats B x L x T (T = tagset+2), transitions T x T.
+ * padded_path reproduces the reference's B x L output bit for bit (pads 0, last column = final
+ * pointer); flat_pred additionally applies the clamp_col -> o_idx remap.  Either may be NULL.
+ * bp_ws: B*L*T uint16 scratch. */
+int re2nn_crf_viterbi(const float* feats, const float* transitions, const int64_t* lengths,
+                      const int64_t* offsets, int B, int L, int T, int clamp_col, float threshold,
+                      int64_t o_idx, int64_t* padded_path, int64_t* flat_pred, uint16_t* bp_ws,
+                      void* stream);
+
+/* ---- CRF negative log-likelihood ---------------------------------------------------------------------
+ * replaces CRF.neg_log_likelihood_loss = _calculate_PZ - _score_sentence (baselines/crf.py:48-99,
+ * 202-260).  per_seq[b] = logZ_b - gold_b ; *loss = sum_b per_seq[b] (deterministic reduction).
+ * part_save (B x L x T, may be NULL) keeps the forward partitions for re2nn_crf_nll_backward. */
+int re2nn_crf_nll(const float* feats, const float* transitions, const int64_t* lengths,
+                  const int64_t* tags, int B, int L, int Ltags, int T, float* per_seq, float* loss,
+                  float* part_save, void* stream);
+
+/* d loss / d feats (B x L x T, zero at pads) and d loss / d transitions (T x T), scaled by *gscale
+ * (device scalar, the upstream gradient). */
+int re2nn_crf_nll_backward(const float* feats, const float* transitions, const int64_t* lengths,
+                           const int64_t* tags, const float* part_save, const float* gscale,
+                           int B, int L, int Ltags, int T, float* dfeats, float* dtrans, void* stream);
+
+/* ---- cross entropy over valid positions -----------------------------------------------------------------
+ * nn.CrossEntropyLoss() mean over the N valid tokens (model_decompose.py:80, :289).
+ * n_total: number of tokens the mean divides by (global count under data parallelism). */
+int re2nn_ce_loss(const float* scores, const int64_t* lengths, const int64_t* labels, int B, int L,
+                  int Llab, int C, int64_t n_total, float* per_pos /* B*L scratch */, float* loss,
+                  void* stream);
+int re2nn_ce_loss_backward(const float* scores, const int64_t* lengths, const int64_t* labels,
+                           const float* gscale, int B, int L, int Llab, int C, int64_t n_total,
+                           float* dscores, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RE2NN_B200_H */

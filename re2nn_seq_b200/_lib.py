@@ -1,0 +1,82 @@
+"""ctypes binding of libre2nn_b200.so (the C-ABI declared in include/re2nn_b200.h).
+
+The library is built in-tree by re2nn_seq_b200/build.py (nvcc, sm_100a).  There is no CPU or
+PyTorch fallback: if the shared object is missing, import fails; if a kernel fails, a
+RuntimeError carrying re2nn_last_error() is raised.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libre2nn_b200.so')
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "re2nn_seq_b200: %s not found. Build it with `python -m re2nn_seq_b200.build` "
+        "(or __graft_entry__.build()); there is no fallback path." % LIB_PATH)
+
+lib = C.CDLL(LIB_PATH)
+
+vp, i32, i64, f32, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+
+NL = {'none': 0, 'relu': 1, 'tanh': 2, 'relutanh': 3, 'sigmoid': 4}
+PREC = {'fp32': 0, 'bf16': 1, 'tf32x3': 2}
+V_TOKEN, V_DENSE = 0, 1
+
+
+class RecurrenceArgs(C.Structure):
+    _fields_ = [
+        ('B', i32), ('Lpad', i32), ('L', i32), ('S', i32), ('R', i32), ('farnn', i32),
+        ('update_nonlinear', i32), ('precision', i32), ('v_mode', i32), ('full_pad', i32),
+        ('save_for_backward', i32), ('sigmoid_exponent', f32),
+        ('x', vp), ('lengths', vp), ('vtab', vp), ('gtab', vp), ('S1', vp), ('S2', vp), ('W', vp),
+        ('o', vp), ('h0', vp), ('hT', vp), ('Wss1', vp), ('Wss2', vp), ('alpha', vp), ('beta', vp),
+        ('zsave', vp), ('rsave', vp), ('ws', vp), ('ws_bytes', sz),
+    ]
+
+
+class OnehotArgs(C.Structure):
+    _fields_ = [
+        ('B', i32), ('Lpad', i32), ('L', i32), ('S', i32), ('update_nonlinear', i32),
+        ('max_semiring', i32), ('full_pad', i32),
+        ('x', vp), ('lengths', vp), ('language', vp), ('W', vp), ('o', vp), ('h0', vp), ('hT', vp),
+        ('alpha', vp), ('beta', vp),
+    ]
+
+
+def _sig(name, restype, argtypes):
+    fn = getattr(lib, name)
+    fn.restype = restype
+    fn.argtypes = argtypes
+    return fn
+
+
+# every symbol declared in include/re2nn_b200.h (tests/test_abi.py checks this list against the header)
+SYMBOLS = {
+    're2nn_abi_version': (C.c_int, []),
+    're2nn_last_error': (C.c_char_p, []),
+    're2nn_has_tcgen05': (C.c_int, []),
+    're2nn_profile_enable': (C.c_int, [C.c_int]),
+    're2nn_profile_read': (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    're2nn_token_table': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
+    're2nn_gate_table': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
+    're2nn_output_vector_sum': (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),
+    're2nn_decompose_recurrence_workspace': (sz, [C.POINTER(RecurrenceArgs)]),
+    're2nn_decompose_recurrence': (C.c_int, [C.POINTER(RecurrenceArgs), vp]),
+    're2nn_onehot_recurrence': (C.c_int, [C.POINTER(OnehotArgs), vp]),
+    're2nn_label_scores': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp]),
+    're2nn_argmax_decode': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, i64, vp, vp, vp]),
+    're2nn_crf_viterbi': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, i64, vp, vp, vp, vp]),
+    're2nn_crf_nll': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
+    're2nn_crf_nll_backward': (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    're2nn_ce_loss': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, i64, vp, vp, vp]),
+    're2nn_ce_loss_backward': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, i64, vp, vp]),
+}
+
+fn = {name: _sig(name, r, a) for name, (r, a) in SYMBOLS.items()}
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = fn['re2nn_last_error']()
+        raise RuntimeError("re2nn_b200 %s failed: %s" % (what, msg.decode() if msg else '?'))

@@ -1,0 +1,102 @@
+// Shared helpers for the re2nn_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/re2nn_b200.h"
+
+namespace re2nn {
+
+// ---- error reporting (C-ABI never aborts) -----------------------------------------------------
+extern thread_local char g_err[512];
+int set_error(const char* fmt, ...);
+
+#define RE2NN_CHECK(cond, ...)                         \
+  do {                                                 \
+    if (!(cond)) return ::re2nn::set_error(__VA_ARGS__); \
+  } while (0)
+
+#define RE2NN_CUDA(expr)                                                                       \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return ::re2nn::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define RE2NN_LAUNCH_CHECK() RE2NN_CUDA(cudaGetLastError())
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- nonlinearities ---------------------------------------------------------------------------
+__device__ __forceinline__ float apply_nl(float x, int kind) {
+  switch (kind) {
+    case RE2NN_NL_RELU: return fmaxf(x, 0.f);
+    case RE2NN_NL_TANH: return tanhf(x);
+    case RE2NN_NL_RELUTANH: return tanhf(fmaxf(x, 0.f));
+    case RE2NN_NL_SIGMOID: return 1.f / (1.f + expf(-x));
+    default: return x;
+  }
+}
+// derivative expressed through the OUTPUT y = phi(x) (and x only where needed for relu masks)
+__device__ __forceinline__ float nl_grad_from_out(float y, int kind) {
+  switch (kind) {
+    case RE2NN_NL_RELU: return y > 0.f ? 1.f : 0.f;
+    case RE2NN_NL_TANH: return 1.f - y * y;
+    case RE2NN_NL_RELUTANH: return y > 0.f ? 1.f - y * y : 0.f;
+    case RE2NN_NL_SIGMOID: return y * (1.f - y);
+    default: return 1.f;
+  }
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ---- step <-> position mapping ----------------------------------------------------------------
+// The reference runs the backward direction on reverse(input, lengths) and un-reverses the states
+// afterwards (model_decompose_single.py:222,257-261).  We keep its step order but address tokens
+// and outputs directly:
+//   dir 0 (forward):  step k consumes token k, produces alpha[.,k]
+//   dir 1 (backward): step k<n consumes token n-1-k, produces beta[., n-2-k] (k==n-1 -> beta_0, unused);
+//                     step k>=n consumes pad token k, produces the reference's pad row k.
+// `alive` = the row's state still matters at this step; `orow` = output row or -1.
+__device__ __forceinline__ void step_pos(int dir, int k, int n, int full_pad, int& tpos, int& orow, bool& alive) {
+  if (dir == 0) {
+    tpos = k;
+    alive = full_pad || (k < n);
+    orow = alive ? k : -1;
+  } else {
+    if (k < n) {
+      tpos = n - 1 - k;
+      orow = n - 2 - k;               // -1 when k == n-1
+      alive = full_pad || (k < n - 1);
+    } else {
+      tpos = k;
+      alive = full_pad != 0;
+      orow = alive ? k : -1;
+    }
+  }
+}
+
+// warp reductions
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// (value, index) arg-max with FIRST-index tie-break, as torch.max(dim) does
+__device__ __forceinline__ void warp_argmax_first(float& v, int& i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+}
+
+}  // namespace re2nn

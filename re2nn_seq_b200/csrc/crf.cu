@@ -1,0 +1,467 @@
+// CRF forward algorithm / Viterbi / gold score, argmax decode and cross-entropy kernels.
+// Reference: /root/reference/src_seq/baselines/crf.py:16-260, farnn/model_decompose.py:339-371,
+//            farnn/model_onehot.py:148-180.
+// One warp owns one sequence: the tag dimension (T = tagset+2, 75 for SNIPS) is spread over the
+// lanes, the T x T transition matrix sits in shared memory (fp32, read conflict-free along "to"),
+// the running partition is exchanged through a per-warp shared buffer.  Arithmetic order follows the
+// reference exactly where it decides an argmax: cur = (feat_j + trans_ij) + part_i, strict ">" keeps
+// the first maximal index like torch.max(dim).
+#include "common.cuh"
+
+namespace re2nn {
+
+constexpr int kCrfWarps = 8;
+
+__device__ __forceinline__ float clamped_feat(const float* f, int j, int clamp_col, float thr) {
+  float v = __ldg(f + j);
+  return (j == clamp_col) ? fminf(v, thr) : v;
+}
+
+// dynamic smem: [TS ? T*T : 0] transitions, then kCrfWarps * 2 * Tp partitions
+template <bool TS>
+__global__ void __launch_bounds__(kCrfWarps * 32) crf_viterbi_kernel(
+    const float* __restrict__ feats, const float* __restrict__ trans_g, const int64_t* __restrict__ len,
+    const int64_t* __restrict__ offsets, int B, int L, int T, int clamp_col, float thr, int64_t o_idx,
+    int64_t* __restrict__ padded, int64_t* __restrict__ flat, uint16_t* __restrict__ bp) {
+  extern __shared__ float smem[];
+  const int Tp = (T + 31) & ~31;
+  float* s_trans = smem;
+  float* s_part = smem + (TS ? T * T : 0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (TS) {
+    for (int i = threadIdx.x; i < T * T; i += blockDim.x) s_trans[i] = trans_g[i];
+    __syncthreads();
+  }
+  const float* tr = TS ? s_trans : trans_g;
+  const int b = blockIdx.x * kCrfWarps + warp;
+  if (b >= B) return;
+  const int n = (int)len[b];
+  float* pa = s_part + warp * 2 * Tp;
+  float* pb = pa + Tp;
+  const float* fb = feats + (size_t)b * L * T;
+  uint16_t* bpb = bp + (size_t)b * L * T;
+
+  for (int j = lane; j < T; j += 32) pa[j] = clamped_feat(fb, j, clamp_col, thr) + tr[(T - 2) * T + j];
+  __syncwarp();
+  for (int t = 1; t < n; ++t) {
+    const float* ft = fb + (size_t)t * T;
+    for (int j = lane; j < T; j += 32) {
+      const float f = clamped_feat(ft, j, clamp_col, thr);
+      float best = -INFINITY;
+      int bi = 0;
+      for (int i = 0; i < T; ++i) {
+        float v = (f + tr[i * T + j]) + pa[i];
+        if (v > best) { best = v; bi = i; }
+      }
+      pb[j] = best;
+      bpb[(size_t)t * T + j] = (uint16_t)bi;
+    }
+    __syncwarp();
+    float* tmp = pa; pa = pb; pb = tmp;
+  }
+  // transition into STOP: pointer = argmax_i (part_i + trans[i][STOP])
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = lane; i < T; i += 32) {
+    float v = pa[i] + tr[i * T + (T - 1)];
+    if (v > best) { best = v; bi = i; }
+  }
+  if (bi == 0x7fffffff) bi = lane;   // all -inf in this lane: keep order so lane 0 / index 0 wins ties
+  warp_argmax_first(best, bi);
+  if (best == -INFINITY) bi = 0;
+  __syncwarp();
+  if (lane == 0) {
+    int ptr = bi;
+    const int64_t off = offsets ? offsets[b] : 0;
+    auto emit = [&](int t, int tag) {
+      if (padded) padded[(size_t)b * L + t] = tag;
+      if (flat) flat[off + t] = (tag == clamp_col) ? o_idx : (int64_t)tag;
+    };
+    if (padded) {   // reference leaves pads at 0 and the final pointer in the last column
+      for (int t = n; t < L - 1; ++t) padded[(size_t)b * L + t] = 0;
+      if (n < L) padded[(size_t)b * L + (L - 1)] = ptr;
+    }
+    emit(n - 1, ptr);
+    for (int t = n - 1; t >= 1; --t) {
+      ptr = bpb[(size_t)t * T + ptr];
+      emit(t - 1, ptr);
+    }
+  }
+}
+
+// log-partition + gold score.  per_seq[b] = logZ_b - gold_b.   (crf.py:48-99, 202-251)
+template <bool TS>
+__global__ void __launch_bounds__(kCrfWarps * 32) crf_nll_kernel(
+    const float* __restrict__ feats, const float* __restrict__ trans_g, const int64_t* __restrict__ len,
+    const int64_t* __restrict__ tags, int B, int L, int Ltags, int T, float* __restrict__ per_seq,
+    float* __restrict__ part_save) {
+  extern __shared__ float smem[];
+  const int Tp = (T + 31) & ~31;
+  float* s_trans = smem;
+  float* s_part = smem + (TS ? T * T : 0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (TS) {
+    for (int i = threadIdx.x; i < T * T; i += blockDim.x) s_trans[i] = trans_g[i];
+    __syncthreads();
+  }
+  const float* tr = TS ? s_trans : trans_g;
+  const int b = blockIdx.x * kCrfWarps + warp;
+  if (b >= B) return;
+  const int n = (int)len[b];
+  float* pa = s_part + warp * 2 * Tp;
+  float* pb = pa + Tp;
+  const float* fb = feats + (size_t)b * L * T;
+  float* ps = part_save ? part_save + (size_t)b * L * T : nullptr;
+
+  for (int j = lane; j < T; j += 32) {
+    float v = __ldg(fb + j) + tr[(T - 2) * T + j];
+    pa[j] = v;
+    if (ps) ps[j] = v;
+  }
+  __syncwarp();
+  for (int t = 1; t < n; ++t) {
+    const float* ft = fb + (size_t)t * T;
+    for (int j = lane; j < T; j += 32) {
+      const float f = __ldg(ft + j);
+      float m = -INFINITY;
+      for (int i = 0; i < T; ++i) m = fmaxf(m, (f + tr[i * T + j]) + pa[i]);
+      float s = 0.f;
+      for (int i = 0; i < T; ++i) s += expf(((f + tr[i * T + j]) + pa[i]) - m);
+      float v = m + logf(s);
+      pb[j] = v;
+      if (ps) ps[(size_t)t * T + j] = v;
+    }
+    __syncwarp();
+    float* tmp = pa; pa = pb; pb = tmp;
+  }
+  // logZ = LSE_i(trans[i][STOP] + part_i)
+  float m = -INFINITY;
+  for (int i = lane; i < T; i += 32) m = fmaxf(m, tr[i * T + (T - 1)] + pa[i]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int i = lane; i < T; i += 32) s += expf((tr[i * T + (T - 1)] + pa[i]) - m);
+  s = warp_sum(s);
+  const float logZ = m + logf(s);
+  // gold path
+  const int64_t* tg = tags + (size_t)b * Ltags;
+  float g = 0.f;
+  for (int t = lane; t < n; t += 32) {
+    int cur = (int)tg[t];
+    int prev = t == 0 ? T - 2 : (int)tg[t - 1];
+    g += __ldg(fb + (size_t)t * T + cur) + tr[prev * T + cur];
+  }
+  g = warp_sum(g);
+  if (lane == 0) {
+    g += tr[(int)tg[n - 1] * T + (T - 1)];
+    per_seq[b] = logZ - g;
+  }
+}
+
+// CRF backward: marginals by the backward recursion, reusing the saved forward partitions.
+//   dfeats[b,t,j] = gs * (P(y_t=j) - [tag_t=j]);  dtrans[i,j] += gs * (sum_t P(y_{t-1}=i,y_t=j) - gold counts)
+template <bool TS>
+__global__ void __launch_bounds__(kCrfWarps * 32) crf_nll_backward_kernel(
+    const float* __restrict__ feats, const float* __restrict__ trans_g, const int64_t* __restrict__ len,
+    const int64_t* __restrict__ tags, const float* __restrict__ part_save, const float* __restrict__ gscale, int B,
+    int L, int Ltags, int T, float* __restrict__ dfeats, float* __restrict__ dtrans) {
+  extern __shared__ float smem[];
+  const int Tp = (T + 31) & ~31;
+  float* s_trans = smem;                        // T*T (if TS)
+  float* s_dtr = smem + (TS ? T * T : 0);       // T*T accumulator for this CTA
+  float* s_beta = s_dtr + T * T;                // kCrfWarps * 2 * Tp
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
+    if (TS) s_trans[i] = trans_g[i];
+    s_dtr[i] = 0.f;
+  }
+  __syncthreads();
+  const float* tr = TS ? s_trans : trans_g;
+  const float gs = gscale ? *gscale : 1.f;
+  const int b = blockIdx.x * kCrfWarps + warp;
+  if (b < B) {
+    const int n = (int)len[b];
+    float* ba = s_beta + warp * 2 * Tp;   // beta_t
+    float* bb = ba + Tp;                  // beta_{t-1}
+    const float* fb = feats + (size_t)b * L * T;
+    const float* ps = part_save + (size_t)b * L * T;
+    float* df = dfeats + (size_t)b * L * T;
+    const int64_t* tg = tags + (size_t)b * Ltags;
+    // logZ from the last saved partition
+    const float* pl = ps + (size_t)(n - 1) * T;
+    float m = -INFINITY;
+    for (int i = lane; i < T; i += 32) m = fmaxf(m, tr[i * T + (T - 1)] + pl[i]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int i = lane; i < T; i += 32) s += expf((tr[i * T + (T - 1)] + pl[i]) - m);
+    s = warp_sum(s);
+    const float logZ = m + logf(s);
+    for (int i = lane; i < T; i += 32) ba[i] = tr[i * T + (T - 1)];   // beta_{n-1}[i] = trans[i][STOP]
+    __syncwarp();
+    for (int t = n - 1; t >= 0; --t) {
+      const float* pt = ps + (size_t)t * T;
+      const int gold = (int)tg[t];
+      // unary marginal at t  (+ STOP column / START row of dtrans)
+      for (int j = lane; j < T; j += 32) {
+        float mg = expf(pt[j] + ba[j] - logZ);
+        df[(size_t)t * T + j] = gs * (mg - (j == gold ? 1.f : 0.f));
+        if (t == n - 1) atomicAdd(&s_dtr[j * T + (T - 1)], gs * (mg - (j == gold ? 1.f : 0.f)));
+        if (t == 0) atomicAdd(&s_dtr[(T - 2) * T + j], gs * (mg - (j == gold ? 1.f : 0.f)));
+      }
+      if (t == 0) break;
+      // pairwise marginals (t-1 -> t) and beta_{t-1}
+      const float* pp = ps + (size_t)(t - 1) * T;
+      const float* ft = fb + (size_t)t * T;
+      const int gprev = (int)tg[t - 1];
+      for (int i = lane; i < T; i += 32) {
+        float mx = -INFINITY;
+        for (int j = 0; j < T; ++j) mx = fmaxf(mx, (tr[i * T + j] + __ldg(ft + j)) + ba[j]);
+        float sm = 0.f;
+        const float pi = pp[i];
+        for (int j = 0; j < T; ++j) {
+          float e = (tr[i * T + j] + __ldg(ft + j)) + ba[j];
+          sm += expf(e - mx);
+          float pw = expf(pi + e - logZ);
+          float d = pw - ((i == gprev && j == gold) ? 1.f : 0.f);
+          if (d != 0.f) atomicAdd(&s_dtr[i * T + j], gs * d);
+        }
+        bb[i] = mx + logf(sm);
+      }
+      __syncwarp();
+      float* tmp = ba; ba = bb; bb = tmp;
+    }
+    // zero the pad rows of dfeats
+    for (int i = n * T + lane; i < L * T; i += 32) df[i] = 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
+    float v = s_dtr[i];
+    if (v != 0.f) atomicAdd(dtrans + i, v);
+  }
+}
+
+// deterministic sum of n floats (double accumulation), scaled
+__global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restrict__ v, size_t n, double scale,
+                                                          float* __restrict__ out) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) acc += (double)v[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) *out = (float)(acc * scale);
+  }
+}
+
+// one warp per (b,t): clamp, first-max argmax, remap
+__global__ void __launch_bounds__(256) argmax_decode_kernel(const float* __restrict__ scores,
+                                                            const int64_t* __restrict__ len,
+                                                            const int64_t* __restrict__ offsets, int B, int L, int C,
+                                                            int clamp_col, float thr, int64_t o_idx,
+                                                            int64_t* __restrict__ flat, int64_t* __restrict__ padded) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= B * L) return;
+  const int b = gw / L, t = gw - b * L;
+  const bool valid = t < (int)len[b];
+  if (!valid && !padded) return;
+  const float* s = scores + (size_t)gw * C;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = lane; c < C; c += 32) {
+    float v = clamped_feat(s, c, clamp_col, thr);
+    if (v > best) { best = v; bi = c; }
+  }
+  if (bi == 0x7fffffff) bi = lane;
+  warp_argmax_first(best, bi);
+  if (best == -INFINITY) bi = 0;
+  if (lane == 0) {
+    int64_t tag = (bi == clamp_col) ? o_idx : (int64_t)bi;
+    if (padded) padded[gw] = tag;
+    if (flat && valid) flat[offsets[b] + t] = tag;
+  }
+}
+
+// per-position cross entropy: lse(scores) - scores[label]; 0 at pads
+__global__ void __launch_bounds__(256) ce_pos_kernel(const float* __restrict__ scores, const int64_t* __restrict__ len,
+                                                     const int64_t* __restrict__ labels, int B, int L, int Llab, int C,
+                                                     float* __restrict__ per_pos) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= B * L) return;
+  const int b = gw / L, t = gw - b * L;
+  if (t >= (int)len[b]) {
+    if (lane == 0) per_pos[gw] = 0.f;
+    return;
+  }
+  const float* s = scores + (size_t)gw * C;
+  float m = -INFINITY;
+  for (int c = lane; c < C; c += 32) m = fmaxf(m, __ldg(s + c));
+  m = warp_max(m);
+  float e = 0.f;
+  for (int c = lane; c < C; c += 32) e += expf(__ldg(s + c) - m);
+  e = warp_sum(e);
+  if (lane == 0) per_pos[gw] = (m + logf(e)) - __ldg(s + (int)labels[(size_t)b * Llab + t]);
+}
+
+__global__ void __launch_bounds__(256) ce_backward_kernel(const float* __restrict__ scores,
+                                                          const int64_t* __restrict__ len,
+                                                          const int64_t* __restrict__ labels,
+                                                          const float* __restrict__ gscale, int B, int L, int Llab,
+                                                          int C, float inv_n, float* __restrict__ dscores) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= B * L) return;
+  const int b = gw / L, t = gw - b * L;
+  float* d = dscores + (size_t)gw * C;
+  if (t >= (int)len[b]) {
+    for (int c = lane; c < C; c += 32) d[c] = 0.f;
+    return;
+  }
+  const float* s = scores + (size_t)gw * C;
+  float m = -INFINITY;
+  for (int c = lane; c < C; c += 32) m = fmaxf(m, __ldg(s + c));
+  m = warp_max(m);
+  float e = 0.f;
+  for (int c = lane; c < C; c += 32) e += expf(__ldg(s + c) - m);
+  e = warp_sum(e);
+  const float g = (gscale ? *gscale : 1.f) * inv_n;
+  const int lab = (int)labels[(size_t)b * Llab + t];
+  for (int c = lane; c < C; c += 32) d[c] = g * (expf(__ldg(s + c) - m) / e - (c == lab ? 1.f : 0.f));
+}
+
+__global__ void colsum_kernel(const float* __restrict__ Cm, int C, int S, const float* __restrict__ wv,
+                              float* __restrict__ o) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  float acc = 0.f;
+  for (int c = 0; c < C; ++c) acc += Cm[(size_t)c * S + s];   // same order as torch's sum over dim 0
+  o[s] = wv ? acc + wv[s] : acc;
+}
+
+static const size_t kSmemLimit = 200 * 1024;
+
+}  // namespace re2nn
+
+using namespace re2nn;
+
+extern "C" {
+
+int re2nn_output_vector_sum(const float* C_mat, int C, int S, const float* wildcard_vec, float* o, void* stream) {
+  RE2NN_CHECK(C_mat && o && C > 0 && S > 0, "output_vector_sum: bad arguments");
+  colsum_kernel<<<cdiv(S, 128), 128, 0, (cudaStream_t)stream>>>(C_mat, C, S, wildcard_vec, o);
+  RE2NN_LAUNCH_CHECK();
+  return 0;
+}
+
+int re2nn_crf_viterbi(const float* feats, const float* transitions, const int64_t* lengths, const int64_t* offsets,
+                      int B, int L, int T, int clamp_col, float threshold, int64_t o_idx, int64_t* padded_path,
+                      int64_t* flat_pred, uint16_t* bp_ws, void* stream) {
+  RE2NN_CHECK(feats && transitions && lengths && bp_ws, "crf_viterbi: null tensor");
+  RE2NN_CHECK(B > 0 && L > 0 && T >= 3 && T <= 65535, "crf_viterbi: bad dims B=%d L=%d T=%d", B, L, T);
+  RE2NN_CHECK(!flat_pred || offsets, "crf_viterbi: flat output needs offsets");
+  const int Tp = (T + 31) & ~31;
+  const size_t part = (size_t)kCrfWarps * 2 * Tp * 4;
+  const size_t with_tr = part + (size_t)T * T * 4;
+  const int grid = cdiv(B, kCrfWarps);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (with_tr <= kSmemLimit) {
+    RE2NN_CUDA(cudaFuncSetAttribute(crf_viterbi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_tr));
+    crf_viterbi_kernel<true><<<grid, kCrfWarps * 32, with_tr, st>>>(feats, transitions, lengths, offsets, B, L, T,
+                                                                    clamp_col, threshold, o_idx, padded_path,
+                                                                    flat_pred, bp_ws);
+  } else {
+    crf_viterbi_kernel<false><<<grid, kCrfWarps * 32, part, st>>>(feats, transitions, lengths, offsets, B, L, T,
+                                                                  clamp_col, threshold, o_idx, padded_path, flat_pred,
+                                                                  bp_ws);
+  }
+  RE2NN_LAUNCH_CHECK();
+  return 0;
+}
+
+int re2nn_crf_nll(const float* feats, const float* transitions, const int64_t* lengths, const int64_t* tags, int B,
+                  int L, int Ltags, int T, float* per_seq, float* loss, float* part_save, void* stream) {
+  RE2NN_CHECK(feats && transitions && lengths && tags && per_seq, "crf_nll: null tensor");
+  RE2NN_CHECK(B > 0 && L > 0 && T >= 3, "crf_nll: bad dims");
+  const int Tp = (T + 31) & ~31;
+  const size_t part = (size_t)kCrfWarps * 2 * Tp * 4;
+  const size_t with_tr = part + (size_t)T * T * 4;
+  const int grid = cdiv(B, kCrfWarps);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (with_tr <= kSmemLimit) {
+    RE2NN_CUDA(cudaFuncSetAttribute(crf_nll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_tr));
+    crf_nll_kernel<true><<<grid, kCrfWarps * 32, with_tr, st>>>(feats, transitions, lengths, tags, B, L, Ltags, T,
+                                                                per_seq, part_save);
+  } else {
+    crf_nll_kernel<false><<<grid, kCrfWarps * 32, part, st>>>(feats, transitions, lengths, tags, B, L, Ltags, T,
+                                                              per_seq, part_save);
+  }
+  RE2NN_LAUNCH_CHECK();
+  if (loss) {
+    reduce_sum_kernel<<<1, 1024, 0, st>>>(per_seq, (size_t)B, 1.0, loss);
+    RE2NN_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int re2nn_crf_nll_backward(const float* feats, const float* transitions, const int64_t* lengths, const int64_t* tags,
+                           const float* part_save, const float* gscale, int B, int L, int Ltags, int T, float* dfeats,
+                           float* dtrans, void* stream) {
+  RE2NN_CHECK(feats && transitions && lengths && tags && part_save && dfeats && dtrans, "crf_nll_backward: null tensor");
+  const int Tp = (T + 31) & ~31;
+  const size_t base = (size_t)kCrfWarps * 2 * Tp * 4 + (size_t)T * T * 4;
+  const size_t with_tr = base + (size_t)T * T * 4;
+  const int grid = cdiv(B, kCrfWarps);
+  cudaStream_t st = (cudaStream_t)stream;
+  RE2NN_CUDA(cudaMemsetAsync(dtrans, 0, (size_t)T * T * 4, st));
+  if (with_tr <= kSmemLimit) {
+    RE2NN_CUDA(cudaFuncSetAttribute(crf_nll_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_tr));
+    crf_nll_backward_kernel<true><<<grid, kCrfWarps * 32, with_tr, st>>>(feats, transitions, lengths, tags, part_save,
+                                                                         gscale, B, L, Ltags, T, dfeats, dtrans);
+  } else {
+    RE2NN_CHECK(base <= kSmemLimit, "crf_nll_backward: tag set too large (T=%d)", T);
+    RE2NN_CUDA(cudaFuncSetAttribute(crf_nll_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base));
+    crf_nll_backward_kernel<false><<<grid, kCrfWarps * 32, base, st>>>(feats, transitions, lengths, tags, part_save,
+                                                                       gscale, B, L, Ltags, T, dfeats, dtrans);
+  }
+  RE2NN_LAUNCH_CHECK();
+  return 0;
+}
+
+int re2nn_argmax_decode(const float* scores, const int64_t* lengths, const int64_t* offsets, int B, int L, int C,
+                        int clamp_col, float threshold, int64_t o_idx, int64_t* flat_pred, int64_t* padded_pred,
+                        void* stream) {
+  RE2NN_CHECK(scores && lengths, "argmax_decode: null tensor");
+  RE2NN_CHECK(!flat_pred || offsets, "argmax_decode: flat output needs offsets");
+  const long long threads = (long long)B * L * 32;
+  argmax_decode_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      scores, lengths, offsets, B, L, C, clamp_col, threshold, o_idx, flat_pred, padded_pred);
+  RE2NN_LAUNCH_CHECK();
+  return 0;
+}
+
+int re2nn_ce_loss(const float* scores, const int64_t* lengths, const int64_t* labels, int B, int L, int Llab, int C,
+                  int64_t n_total, float* per_pos, float* loss, void* stream) {
+  RE2NN_CHECK(scores && lengths && labels && per_pos && loss, "ce_loss: null tensor");
+  RE2NN_CHECK(n_total > 0, "ce_loss: n_total must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long threads = (long long)B * L * 32;
+  ce_pos_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(scores, lengths, labels, B, L, Llab, C, per_pos);
+  RE2NN_LAUNCH_CHECK();
+  reduce_sum_kernel<<<1, 1024, 0, st>>>(per_pos, (size_t)B * L, 1.0 / (double)n_total, loss);
+  RE2NN_LAUNCH_CHECK();
+  return 0;
+}
+
+int re2nn_ce_loss_backward(const float* scores, const int64_t* lengths, const int64_t* labels, const float* gscale,
+                           int B, int L, int Llab, int C, int64_t n_total, float* dscores, void* stream) {
+  RE2NN_CHECK(scores && lengths && labels && dscores, "ce_loss_backward: null tensor");
+  const long long threads = (long long)B * L * 32;
+  ce_backward_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      scores, lengths, labels, gscale, B, L, Llab, C, 1.f / (float)n_total, dscores);
+  RE2NN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,196 @@
+// Problem description shared by the CUDA-core (fp32) and tcgen05 GEMM mainloops, plus the fused
+// epilogue functors of the decompose recurrence.  One "step GEMM" computes, for both directions z,
+//     C_z[M x N] = sum_seg A_{z,seg}[M x K_seg] * B_{z,seg}[K_seg x N]
+// and hands every accumulator element to an epilogue functor instead of writing C.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace re2nn {
+
+constexpr int kMaxSeg = 3;
+
+struct GemmSeg {
+  const void* A;   // M x K operand, row-major, leading dimension lda (elements)
+  const void* B;   // b_nk ? N x K (K contiguous) : K x N (N contiguous); leading dimension ldb
+  int lda, ldb, K, b_nk;
+  size_t a_plane, b_plane;   // TF32X3 only: element offset of the "lo" plane
+};
+struct GemmProblem {
+  int M, N, nseg, ndir;
+  GemmSeg seg[2][kMaxSeg];
+};
+
+// ---- operand formats ---------------------------------------------------------------------------
+// FP32: float, ld = K.   BF16: __nv_bfloat16, ld = roundup(K, 8).   TF32X3: two float planes (hi, lo).
+template <int PREC> struct OperandFmt;
+template <> struct OperandFmt<RE2NN_PREC_FP32> {
+  static constexpr int kElemBytes = 4, kPlanes = 1, kLdAlign = 1;
+  __device__ static __forceinline__ void store(void* base, size_t idx, size_t, float v) { ((float*)base)[idx] = v; }
+};
+template <> struct OperandFmt<RE2NN_PREC_BF16> {
+  static constexpr int kElemBytes = 2, kPlanes = 1, kLdAlign = 8;
+  __device__ static __forceinline__ void store(void* base, size_t idx, size_t, float v) {
+    ((__nv_bfloat16*)base)[idx] = __float2bfloat16_rn(v);
+  }
+};
+__device__ __forceinline__ float tf32_hi(float v) {   // round-to-nearest onto the 10-bit tf32 mantissa
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+template <> struct OperandFmt<RE2NN_PREC_TF32X3> {
+  static constexpr int kElemBytes = 4, kPlanes = 2, kLdAlign = 4;
+  __device__ static __forceinline__ void store(void* base, size_t idx, size_t plane, float v) {
+    float hi = tf32_hi(v);
+    ((float*)base)[idx] = hi;
+    ((float*)base)[idx + plane] = tf32_hi(v - hi);
+  }
+};
+inline int operand_ld(int prec, int K) {
+  int a = prec == RE2NN_PREC_BF16 ? 8 : (prec == RE2NN_PREC_TF32X3 ? 4 : 1);
+  return (K + a - 1) / a * a;
+}
+inline size_t operand_bytes(int prec, size_t rows, int K) {
+  size_t ld = operand_ld(prec, K);
+  size_t eb = prec == RE2NN_PREC_BF16 ? 2 : 4;
+  size_t planes = prec == RE2NN_PREC_TF32X3 ? 2 : 1;
+  return align_up(rows * ld * eb * planes, 256);
+}
+
+// ---- per-step parameters of the decompose recurrence -----------------------------------------
+struct StepParams {
+  int B, Lpad, L, S, R, k;
+  int farnn, nl, v_mode, full_pad;
+  float sig_k;
+  const int64_t* x;
+  const int64_t* len;
+  const float* vtab;
+  const float* gtab;
+  int ldg;
+  const float* o;
+  const float* hinit[2];
+  void* Q[2];        int ldq;  size_t q_plane;    // operand format, B x R
+  void* Hbar_next[2]; int ldh; size_t h_plane;    // operand format, B x S : A operand of the NEXT step (farnn<=1)
+  void* Hbar_cur[2];                              // operand format: written by the gate epilogue (farnn==2)
+  void* Hst[2];                                   // operand format: post-update state, A operand of the gate GEMM
+  float* H[2];                                    // fp32 state B x S (farnn>=1)
+  float* Z[2];                                    // fp32 update gate B x S (farnn>=1)
+  float* Rg[2];                                   // optional save of reset gate
+  float* out[2];                                  // alpha / beta : B x L x S
+};
+
+struct RowCtx {
+  int vrow, orow;
+  bool alive;
+};
+
+__device__ __forceinline__ RowCtx make_row(const StepParams& p, int z, int m) {
+  RowCtx r;
+  int n = (int)p.len[m];
+  int tpos;
+  step_pos(z, p.k, n, p.full_pad, tpos, r.orow, r.alive);
+  r.vrow = p.v_mode == RE2NN_V_TOKEN ? (int)p.x[(size_t)m * p.Lpad + tpos] : m * p.Lpad + tpos;
+  return r;
+}
+
+// is any row of [m0, m0+rows) still alive at this step?  (block-uniform; all threads must call)
+__device__ __forceinline__ bool tile_alive(const StepParams& p, int z, int m0, int rows) {
+  bool a = false;
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+    int tpos, orow;
+    bool alive;
+    step_pos(z, p.k, (int)p.len[m0 + i], p.full_pad, tpos, orow, alive);
+    a |= alive;
+  }
+  return __syncthreads_or(a) != 0;
+}
+
+// E1: Q = (Hbar @ S1|S2) * v_t            (model_decompose_single.py:170-171 / 175-176)
+template <int PREC> struct EpiQ {
+  StepParams p;
+  __device__ __forceinline__ bool tile_alive(int z, int m0, int rows) const { return re2nn::tile_alive(p, z, m0, rows); }
+  __device__ __forceinline__ RowCtx row(int z, int m) const { return make_row(p, z, m); }
+  __device__ __forceinline__ void apply(const RowCtx& r, int z, int m, int n, float acc) const {
+    float v = __ldg(p.vtab + (size_t)r.vrow * p.R + n);
+    OperandFmt<PREC>::store(p.Q[z], (size_t)m * p.ldq + n, p.q_plane, acc * v);
+  }
+};
+
+// E2: h_next = phi((Q @ S2^T + Hbar @ W) [* o]) ; gate blend ; write alpha/beta + next operands
+// (model_decompose_single.py:172-173,177-199)
+template <int PREC> struct EpiH {
+  StepParams p;
+  __device__ __forceinline__ bool tile_alive(int z, int m0, int rows) const { return re2nn::tile_alive(p, z, m0, rows); }
+  __device__ __forceinline__ RowCtx row(int z, int m) const { return make_row(p, z, m); }
+  __device__ __forceinline__ void apply(const RowCtx& r, int z, int m, int n, float acc) const {
+    const float on = __ldg(p.o + n);
+    float hn = z == 0 ? acc * on : acc;
+    hn = apply_nl(hn, p.nl);
+    float hnew = hn;
+    const size_t si = (size_t)m * p.S + n;
+    if (p.farnn >= 1) {
+      float zt = p.Z[z][si];
+      float hp = p.H[z][si];
+      hnew = (1.f - zt) * hp + zt * hn;
+      p.H[z][si] = hnew;
+      OperandFmt<PREC>::store(p.Hst[z], (size_t)m * p.ldh + n, p.h_plane, hnew);
+    }
+    if (p.farnn <= 1) {
+      OperandFmt<PREC>::store(p.Hbar_next[z], (size_t)m * p.ldh + n, p.h_plane, z == 1 ? hnew * on : hnew);
+    }
+    if (r.orow >= 0) p.out[z][((size_t)m * p.L + r.orow) * p.S + n] = hnew;
+  }
+};
+
+// EG: zt / rt gates and the reset-blended operand (model_decompose_single.py:147-157)
+// columns [0,S) = update gate pre-activation, [S,2S) = reset gate pre-activation (farnn==2)
+template <int PREC> struct EpiGate {
+  StepParams p;
+  __device__ __forceinline__ bool tile_alive(int z, int m0, int rows) const { return re2nn::tile_alive(p, z, m0, rows); }
+  __device__ __forceinline__ RowCtx row(int z, int m) const { return make_row(p, z, m); }
+  __device__ __forceinline__ void apply(const RowCtx& r, int z, int m, int n, float acc) const {
+    float pre = acc + __ldg(p.gtab + (size_t)r.vrow * p.ldg + n);
+    float g = sigmoidf_(pre * p.sig_k);
+    if (n < p.S) {
+      p.Z[z][(size_t)m * p.S + n] = g;
+    } else {
+      int s = n - p.S;
+      size_t si = (size_t)m * p.S + s;
+      float hb = (1.f - g) * __ldg(p.hinit[z] + s) + g * p.H[z][si];
+      if (z == 1) hb *= __ldg(p.o + s);
+      OperandFmt<PREC>::store(p.Hbar_cur[z], (size_t)m * p.ldh + s, p.h_plane, hb);
+      if (p.Rg[z]) p.Rg[z][si] = g;
+    }
+  }
+};
+
+// plain store epilogue (token table, gate table, generic C = A*B [+ bias] [phi]); used off the step loop
+struct EpiStore {
+  float* C;
+  int ldc;
+  const float* bias;      // per-column or NULL
+  __device__ __forceinline__ bool tile_alive(int, int, int) const { return true; }
+  __device__ __forceinline__ RowCtx row(int, int) const { return RowCtx{0, 0, true}; }
+  __device__ __forceinline__ void apply(const RowCtx&, int, int m, int n, float acc) const {
+    C[(size_t)m * ldc + n] = bias ? acc + __ldg(bias + n) : acc;
+  }
+};
+
+// token table epilogue: table = V_embed*beta + phi(acc)*(1-beta)     (model_decompose.py:226-239)
+struct EpiTokenTable {
+  float* table;
+  const float* V_embed;
+  const float* beta_vec;
+  int R, nl;
+  __device__ __forceinline__ bool tile_alive(int, int, int) const { return true; }
+  __device__ __forceinline__ RowCtx row(int, int) const { return RowCtx{0, 0, true}; }
+  __device__ __forceinline__ void apply(const RowCtx&, int, int m, int n, float acc) const {
+    float b = __ldg(beta_vec + n);
+    float g = apply_nl(acc, nl);
+    table[(size_t)m * R + n] = __ldg(V_embed + (size_t)m * R + n) * b + g * (1.f - b);
+  }
+};
+
+}  // namespace re2nn

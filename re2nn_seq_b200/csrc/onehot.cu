@@ -1,0 +1,141 @@
+// Onehot i-FST recurrence: h <- phi((h (.) T[x_t]) * o) / h <- phi((h*o) (.) T[x_t]^T), T = language[x_t] + W.
+// Reference: /root/reference/src_seq/farnn/model_onehot.py:358-415 (FARNN_S_O_I_S.forward_score),
+//            utils.py:192-199 (_matmul / _maxmul).
+// HBM-bound: every (sequence, direction, step) streams one S x S fp32 slice of the language tensor
+// exactly once.  One CTA owns one (sequence, direction) for all its steps and keeps the state vector
+// in shared memory; rows of the slice are read as full 128-byte lines (lanes along the contiguous
+// "to-state" index), W comes from L2.  language + W is formed on the fly in the reference's own
+// rounding order, so no V x S x S temporary is ever written (K1 in SURVEY.md §2.2).
+#include "common.cuh"
+
+namespace re2nn {
+
+constexpr int kOhThreads = 512;
+constexpr int kOhWarps = kOhThreads / 32;
+
+template <bool MAXP>
+__device__ __forceinline__ float comb(float acc, float h, float t) {
+  return MAXP ? fmaxf(acc, h * t) : fmaf(h, t, acc);
+}
+
+template <bool MAXP>
+__global__ void __launch_bounds__(kOhThreads) onehot_recurrence_kernel(const re2nn_onehot_args a) {
+  extern __shared__ float smem[];
+  const int S = a.S;
+  float* h = smem;                 // S   current state (bwd: already multiplied by o)
+  float* part = smem + S;          // kOhWarps * S partial results (fwd)
+  const int b = blockIdx.x, z = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = (int)a.lengths[b];
+  const float* __restrict__ W = a.W;
+  const float* __restrict__ o = a.o;
+  float* out = z == 0 ? a.alpha : a.beta;
+  const float init = MAXP ? -INFINITY : 0.f;
+
+  for (int s = tid; s < S; s += kOhThreads) {
+    float v = z == 0 ? a.h0[s] : a.hT[s];
+    if (z == 1) {
+      if (n >= 1 && n <= a.L) out[((size_t)b * a.L + (n - 1)) * S + s] = v;   // beta_n = hT
+      v *= o[s];
+    }
+    h[s] = v;
+  }
+  __syncthreads();
+
+  for (int k = 0; k < a.L; ++k) {
+    int tpos, orow;
+    bool alive;
+    step_pos(z, k, n, a.full_pad, tpos, orow, alive);
+    if (!alive) break;   // block-uniform
+    const int64_t tok = a.x[(size_t)b * a.Lpad + tpos];
+    const float* __restrict__ T = a.language + (size_t)tok * S * S;
+    if (z == 0) {
+      // out[j] = (+|max)_s h[s] * (T[s][j] + W[s][j]); warps stride over rows s, lanes over columns j
+      for (int jb = 0; jb < S; jb += 32) {
+        const int j = jb + lane;
+        float acc = init;
+        if (j < S) {
+          int s = warp;
+          for (; s + 3 * kOhWarps < S; s += 4 * kOhWarps) {
+            float t0 = __ldg(T + (size_t)s * S + j) + __ldg(W + (size_t)s * S + j);
+            float t1 = __ldg(T + (size_t)(s + kOhWarps) * S + j) + __ldg(W + (size_t)(s + kOhWarps) * S + j);
+            float t2 = __ldg(T + (size_t)(s + 2 * kOhWarps) * S + j) + __ldg(W + (size_t)(s + 2 * kOhWarps) * S + j);
+            float t3 = __ldg(T + (size_t)(s + 3 * kOhWarps) * S + j) + __ldg(W + (size_t)(s + 3 * kOhWarps) * S + j);
+            acc = comb<MAXP>(acc, h[s], t0);
+            acc = comb<MAXP>(acc, h[s + kOhWarps], t1);
+            acc = comb<MAXP>(acc, h[s + 2 * kOhWarps], t2);
+            acc = comb<MAXP>(acc, h[s + 3 * kOhWarps], t3);
+          }
+          for (; s < S; s += kOhWarps)
+            acc = comb<MAXP>(acc, h[s], __ldg(T + (size_t)s * S + j) + __ldg(W + (size_t)s * S + j));
+          part[warp * S + j] = acc;
+        }
+      }
+      __syncthreads();
+      for (int j = tid; j < S; j += kOhThreads) {
+        float acc = init;
+#pragma unroll
+        for (int w = 0; w < kOhWarps; ++w) acc = MAXP ? fmaxf(acc, part[w * S + j]) : acc + part[w * S + j];
+        float v = apply_nl(acc * o[j], a.update_nonlinear);
+        h[j] = v;
+        if (orow >= 0) out[((size_t)b * a.L + orow) * S + j] = v;
+      }
+      __syncthreads();
+    } else {
+      // out[s] = (+|max)_j h[j] * (T[s][j] + W[s][j]); one warp per row s, lanes along j
+      float* hn = part;   // S
+      for (int s = warp; s < S; s += kOhWarps) {
+        const float* __restrict__ Tr = T + (size_t)s * S;
+        const float* __restrict__ Wr = W + (size_t)s * S;
+        float acc = init;
+        int j = lane;
+        for (; j + 96 < S; j += 128) {
+          float t0 = __ldg(Tr + j) + __ldg(Wr + j);
+          float t1 = __ldg(Tr + j + 32) + __ldg(Wr + j + 32);
+          float t2 = __ldg(Tr + j + 64) + __ldg(Wr + j + 64);
+          float t3 = __ldg(Tr + j + 96) + __ldg(Wr + j + 96);
+          acc = comb<MAXP>(acc, h[j], t0);
+          acc = comb<MAXP>(acc, h[j + 32], t1);
+          acc = comb<MAXP>(acc, h[j + 64], t2);
+          acc = comb<MAXP>(acc, h[j + 96], t3);
+        }
+        for (; j < S; j += 32) acc = comb<MAXP>(acc, h[j], __ldg(Tr + j) + __ldg(Wr + j));
+        acc = MAXP ? warp_max(acc) : warp_sum(acc);
+        if (lane == 0) hn[s] = acc;
+      }
+      __syncthreads();
+      for (int s = tid; s < S; s += kOhThreads) {
+        float v = apply_nl(hn[s], a.update_nonlinear);
+        if (orow >= 0) out[((size_t)b * a.L + orow) * S + s] = v;
+        h[s] = v * o[s];
+      }
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace re2nn
+
+using namespace re2nn;
+
+extern "C" int re2nn_onehot_recurrence(const re2nn_onehot_args* a, void* stream) {
+  RE2NN_CHECK(a != nullptr, "onehot_recurrence: null args");
+  RE2NN_CHECK(a->B > 0 && a->L > 0 && a->S > 0 && a->L <= a->Lpad, "onehot_recurrence: bad dims");
+  RE2NN_CHECK(a->x && a->lengths && a->language && a->W && a->o && a->h0 && a->hT && a->alpha && a->beta,
+              "onehot_recurrence: null tensor");
+  RE2NN_CHECK(a->update_nonlinear >= RE2NN_NL_NONE && a->update_nonlinear <= RE2NN_NL_RELUTANH,
+              "onehot_recurrence: unsupported update_nonlinear %d", a->update_nonlinear);
+  const size_t smem = (size_t)(1 + kOhWarps) * a->S * sizeof(float);
+  RE2NN_CHECK(smem <= 220 * 1024, "onehot_recurrence: S=%d too large for the shared-memory state", a->S);
+  dim3 grid(a->B, 2);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->max_semiring) {
+    RE2NN_CUDA(cudaFuncSetAttribute(onehot_recurrence_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    onehot_recurrence_kernel<true><<<grid, kOhThreads, smem, st>>>(*a);
+  } else {
+    RE2NN_CUDA(cudaFuncSetAttribute(onehot_recurrence_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    onehot_recurrence_kernel<false><<<grid, kOhThreads, smem, st>>>(*a);
+  }
+  RE2NN_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,311 @@
+// Decompose i-FST recurrence driver, token/gate tables and label scores (C-ABI entry points).
+// Reference: /root/reference/src_seq/farnn/model_decompose_single.py:138-269, model_decompose.py:222-241.
+#include <stdarg.h>
+
+#include <mutex>
+#include <vector>
+
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+
+namespace re2nn {
+
+thread_local char g_err[512] = "";
+int set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+// ---- workspace ----------------------------------------------------------------------------------
+struct RecWs {
+  void* Q[2];
+  void* Hbar[2][2];   // [parity][dir]
+  void* Hst[2];
+  float* H[2];
+  float* Z[2];
+  void* wprep;        // prepared (converted / concatenated) weights
+  WeightPrep wp;
+};
+
+static size_t carve(const re2nn_recurrence_args& a, char* base, RecWs* ws) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> void* {
+    void* p = base ? base + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  const int prec = a.precision;
+  RecWs w;
+  memset(&w, 0, sizeof(w));
+  for (int z = 0; z < 2; ++z) {
+    w.Q[z] = take(operand_bytes(prec, a.B, a.R));
+    w.Hbar[0][z] = take(operand_bytes(prec, a.B, a.S));
+    w.Hbar[1][z] = take(operand_bytes(prec, a.B, a.S));
+    if (a.farnn >= 1) {
+      w.Hst[z] = take(operand_bytes(prec, a.B, a.S));
+      w.H[z] = (float*)take((size_t)a.B * a.S * 4);
+      w.Z[z] = (float*)take((size_t)a.B * a.S * 4);
+    }
+  }
+  off += weight_prep_carve(prec, a.S, a.R, a.farnn, base ? base + off : nullptr, &w.wp);
+  if (ws) *ws = w;
+  return off;
+}
+
+// ---- init: step "-1" ------------------------------------------------------------------------------
+template <int PREC>
+__global__ void rec_init_kernel(int B, int L, int S, int farnn, const int64_t* len, const float* h0, const float* hT,
+                                const float* o, RecWs w, int ldh, size_t h_plane, float* beta) {
+  const size_t total = (size_t)2 * B * S;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int s = (int)(i % S);
+    size_t r = i / S;
+    int m = (int)(r % B), z = (int)(r / B);
+    float h = z == 0 ? h0[s] : hT[s];
+    if (farnn >= 1) {
+      w.H[z][(size_t)m * S + s] = h;
+      OperandFmt<PREC>::store(w.Hst[z], (size_t)m * ldh + s, h_plane, h);
+    }
+    if (farnn <= 1) OperandFmt<PREC>::store(w.Hbar[0][z], (size_t)m * ldh + s, h_plane, z == 1 ? h * o[s] : h);
+    if (z == 1) {
+      int n = (int)len[m];
+      if (n >= 1 && n <= L) beta[((size_t)m * L + (n - 1)) * S + s] = h;   // beta_n = hT
+    }
+  }
+}
+
+// ---- optional per-launch timing ------------------------------------------------------------------------
+struct ProfPair { cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfPair> g_prof_pool;        // all event pairs ever created
+static std::vector<int> g_prof_used[3];          // indices into the pool, per kernel class
+static size_t g_prof_next = 0;
+static std::mutex g_prof_mu;
+
+static int prof_begin(int cls, cudaStream_t st) {
+  if (!g_prof_on) return -1;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (g_prof_next == g_prof_pool.size()) {
+    ProfPair p;
+    if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return -1;
+    g_prof_pool.push_back(p);
+  }
+  int idx = (int)g_prof_next++;
+  g_prof_used[cls].push_back(idx);
+  cudaEventRecord(g_prof_pool[idx].a, st);
+  return idx;
+}
+static void prof_end(int idx, cudaStream_t st) {
+  if (idx >= 0) cudaEventRecord(g_prof_pool[idx].b, st);
+}
+
+template <int PREC, class Epi>
+static cudaError_t launch_gemm(int cls, const GemmProblem& prob, const Epi& epi, const TcStepMaps* maps,
+                               cudaStream_t st) {
+  const int pi = prof_begin(cls, st);
+  cudaError_t e;
+  if (PREC == RE2NN_PREC_FP32) e = launch_simt_gemm(prob, epi, ALoadPlain{}, st);
+  else e = launch_tc_gemm<PREC>(prob, epi, maps, st);
+  prof_end(pi, st);
+  return e;
+}
+
+template <int PREC>
+static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
+  RecWs w;
+  size_t need = carve(a, (char*)a.ws, &w);
+  RE2NN_CHECK(a.ws && a.ws_bytes >= need, "decompose_recurrence: workspace too small (%zu < %zu)", a.ws_bytes, need);
+  const int B = a.B, S = a.S, R = a.R, L = a.L;
+  const int ldh = operand_ld(PREC, S), ldq = operand_ld(PREC, R);
+  const size_t h_plane = (size_t)B * ldh, q_plane = (size_t)B * ldq;
+
+  if (int rc = weight_prep_run<PREC>(a, w.wp, st)) return rc;
+  {
+    size_t total = (size_t)2 * B * S;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    rec_init_kernel<PREC><<<blocks, 256, 0, st>>>(B, L, S, a.farnn, a.lengths, a.h0, a.hT, a.o, w, ldh, h_plane, a.beta);
+    RE2NN_LAUNCH_CHECK();
+  }
+
+  TcRecurrenceMaps tmaps;
+  if (PREC != RE2NN_PREC_FP32) {
+    if (int rc = tc_build_maps<PREC>(a, w.Q, w.Hbar, w.Hst, w.wp, &tmaps)) return rc;
+  }
+
+  StepParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.Lpad = a.Lpad; p.L = L; p.S = S; p.R = R;
+  p.farnn = a.farnn; p.nl = a.update_nonlinear; p.v_mode = a.v_mode; p.full_pad = a.full_pad;
+  p.sig_k = a.sigmoid_exponent;
+  p.x = a.x; p.len = a.lengths; p.vtab = a.vtab; p.gtab = a.gtab; p.ldg = S * a.farnn;
+  p.o = a.o; p.hinit[0] = a.h0; p.hinit[1] = a.hT;
+  p.ldq = ldq; p.q_plane = q_plane; p.ldh = ldh; p.h_plane = h_plane;
+  p.out[0] = a.alpha; p.out[1] = a.beta;
+  for (int z = 0; z < 2; ++z) { p.Q[z] = w.Q[z]; p.Hst[z] = w.Hst[z]; p.H[z] = w.H[z]; }
+
+  for (int k = 0; k < L; ++k) {
+    p.k = k;
+    const int par = k & 1;
+    for (int z = 0; z < 2; ++z) {
+      p.Hbar_cur[z] = w.Hbar[par][z];
+      p.Hbar_next[z] = w.Hbar[par ^ 1][z];
+      const size_t slab = ((size_t)z * L + k) * B * S;
+      p.Z[z] = (a.save_for_backward && a.zsave) ? a.zsave + slab : w.Z[z];
+      p.Rg[z] = (a.save_for_backward && a.rsave) ? a.rsave + slab : nullptr;
+    }
+    GemmProblem g;
+    if (a.farnn >= 1) {   // gates: [Z | R]pre = Hst @ [Wss1 | Wss2]
+      memset(&g, 0, sizeof(g));
+      g.M = B; g.N = S * a.farnn; g.nseg = 1; g.ndir = 2;
+      for (int z = 0; z < 2; ++z) g.seg[z][0] = w.wp.seg_gate(w.Hst[z], ldh, h_plane);
+      RE2NN_CUDA((launch_gemm<PREC>(0, g, EpiGate<PREC>{p}, PREC != RE2NN_PREC_FP32 ? &tmaps.gate : nullptr, st)));
+    }
+    // GEMM1: P = Hbar @ S1 (fwd) | Hbar @ S2 (bwd) ; Q = P * v_t
+    memset(&g, 0, sizeof(g));
+    g.M = B; g.N = R; g.nseg = 1; g.ndir = 2;
+    for (int z = 0; z < 2; ++z) g.seg[z][0] = w.wp.seg_g1(z, w.Hbar[par][z], ldh, h_plane);
+    RE2NN_CUDA((launch_gemm<PREC>(1, g, EpiQ<PREC>{p}, PREC != RE2NN_PREC_FP32 ? &tmaps.g1[par] : nullptr, st)));
+    // GEMM2: Hn = Q @ S2^T + Hbar @ W (fwd) | Q @ S1^T + Hbar @ W^T (bwd)
+    memset(&g, 0, sizeof(g));
+    g.M = B; g.N = S; g.nseg = 2; g.ndir = 2;
+    for (int z = 0; z < 2; ++z) {
+      g.seg[z][0] = w.wp.seg_g2q(z, w.Q[z], ldq, q_plane);
+      g.seg[z][1] = w.wp.seg_g2w(z, w.Hbar[par][z], ldh, h_plane);
+    }
+    RE2NN_CUDA((launch_gemm<PREC>(2, g, EpiH<PREC>{p}, PREC != RE2NN_PREC_FP32 ? &tmaps.g2[par] : nullptr, st)));
+  }
+  return 0;
+}
+
+}  // namespace re2nn
+
+using namespace re2nn;
+
+extern "C" {
+
+int re2nn_abi_version(void) { return RE2NN_ABI_VERSION; }
+
+int re2nn_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+  return 0;
+}
+
+int re2nn_profile_read(double* ms_out_host, int64_t* count_out_host) {
+  RE2NN_CHECK(ms_out_host && count_out_host, "profile_read: null output");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int c = 0; c < 3; ++c) {
+    double tot = 0.0;
+    for (int idx : g_prof_used[c]) {
+      float ms = 0.f;
+      RE2NN_CUDA(cudaEventSynchronize(g_prof_pool[idx].b));
+      RE2NN_CUDA(cudaEventElapsedTime(&ms, g_prof_pool[idx].a, g_prof_pool[idx].b));
+      tot += ms;
+    }
+    ms_out_host[c] = tot;
+    count_out_host[c] = (int64_t)g_prof_used[c].size();
+    g_prof_used[c].clear();
+  }
+  g_prof_next = 0;
+  return 0;
+}
+const char* re2nn_last_error(void) { return re2nn::g_err; }
+
+size_t re2nn_decompose_recurrence_workspace(const re2nn_recurrence_args* a) {
+  if (!a) return 0;
+  return carve(*a, nullptr, nullptr);
+}
+
+int re2nn_decompose_recurrence(const re2nn_recurrence_args* a, void* stream) {
+  RE2NN_CHECK(a != nullptr, "decompose_recurrence: null args");
+  RE2NN_CHECK(a->B > 0 && a->L > 0 && a->S > 0 && a->R > 0, "decompose_recurrence: bad dims B=%d L=%d S=%d R=%d", a->B,
+              a->L, a->S, a->R);
+  RE2NN_CHECK(a->L <= a->Lpad, "decompose_recurrence: L (%d) > Lpad (%d)", a->L, a->Lpad);
+  RE2NN_CHECK(a->farnn >= 0 && a->farnn <= 2, "decompose_recurrence: farnn must be 0, 1 or 2 (got %d)", a->farnn);
+  RE2NN_CHECK(a->update_nonlinear >= RE2NN_NL_NONE && a->update_nonlinear <= RE2NN_NL_RELUTANH,
+              "decompose_recurrence: unsupported update_nonlinear %d", a->update_nonlinear);
+  RE2NN_CHECK(a->v_mode == RE2NN_V_DENSE || a->x != nullptr, "decompose_recurrence: token mode needs x");
+  RE2NN_CHECK(a->lengths && a->vtab && a->S1 && a->S2 && a->W && a->o && a->h0 && a->hT && a->alpha && a->beta,
+              "decompose_recurrence: null tensor");
+  RE2NN_CHECK(a->farnn == 0 || (a->gtab && a->Wss1), "decompose_recurrence: farnn>=1 needs gtab and Wss1");
+  RE2NN_CHECK(a->farnn < 2 || a->Wss2, "decompose_recurrence: farnn==2 needs Wss2");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (a->precision) {
+    case RE2NN_PREC_FP32: return run_recurrence<RE2NN_PREC_FP32>(*a, st);
+    case RE2NN_PREC_BF16:
+      RE2NN_CHECK(re2nn_has_tcgen05(), "decompose_recurrence: tcgen05 path needs an sm_100 device");
+      return run_recurrence<RE2NN_PREC_BF16>(*a, st);
+    case RE2NN_PREC_TF32X3:
+      RE2NN_CHECK(re2nn_has_tcgen05(), "decompose_recurrence: tcgen05 path needs an sm_100 device");
+      return run_recurrence<RE2NN_PREC_TF32X3>(*a, st);
+    default: return set_error("decompose_recurrence: unknown precision %d", a->precision);
+  }
+}
+
+int re2nn_token_table(const float* V_embed, const float* E, const float* G, const float* beta_vec, int rows, int D,
+                      int R, int additional_nonlinear, float* table, void* stream) {
+  RE2NN_CHECK(V_embed && E && G && beta_vec && table, "token_table: null tensor");
+  RE2NN_CHECK(rows > 0 && D > 0 && R > 0, "token_table: bad dims");
+  GemmProblem g;
+  memset(&g, 0, sizeof(g));
+  g.M = rows; g.N = R; g.nseg = 1; g.ndir = 1;
+  g.seg[0][0] = GemmSeg{E, G, D, R, D, 0, 0, 0};
+  EpiTokenTable epi{table, V_embed, beta_vec, R, additional_nonlinear};
+  RE2NN_CUDA(launch_simt_gemm(g, epi, ALoadPlain{}, (cudaStream_t)stream));
+  return 0;
+}
+
+int re2nn_gate_table(const float* vtab, int rows, int R, int S, int farnn, const float* Wrs1, const float* bs1,
+                     const float* Wrs2, const float* bs2, float* gate, void* stream) {
+  RE2NN_CHECK(farnn == 1 || farnn == 2, "gate_table: farnn must be 1 or 2");
+  RE2NN_CHECK(vtab && Wrs1 && bs1 && gate && (farnn == 1 || (Wrs2 && bs2)), "gate_table: null tensor");
+  const int ldg = S * farnn;
+  for (int gi = 0; gi < farnn; ++gi) {
+    GemmProblem g;
+    memset(&g, 0, sizeof(g));
+    g.M = rows; g.N = S; g.nseg = 1; g.ndir = 1;
+    g.seg[0][0] = GemmSeg{vtab, gi == 0 ? Wrs1 : Wrs2, R, S, R, 0, 0, 0};
+    EpiStore epi{gate + (size_t)gi * S, ldg, gi == 0 ? bs1 : bs2};
+    RE2NN_CUDA(launch_simt_gemm(g, epi, ALoadPlain{}, (cudaStream_t)stream));
+  }
+  return 0;
+}
+
+int re2nn_label_scores(const float* alpha, const float* beta, const int64_t* lengths, int B, int L, int S,
+                       const float* C_mat, int C, const float* priority_mat, const float* priority_bias, int full_pad,
+                       float* scores, float* ws, void* stream) {
+  RE2NN_CHECK(alpha && beta && lengths && C_mat && scores, "label_scores: null tensor");
+  RE2NN_CHECK(!priority_mat || ws, "label_scores: priority needs a B*L*C workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmProblem g;
+  memset(&g, 0, sizeof(g));
+  g.M = B * L; g.N = C; g.nseg = 1; g.ndir = 1;
+  g.seg[0][0] = GemmSeg{alpha, C_mat, S, S, S, 1, 0, 0};
+  EpiStore e1{priority_mat ? ws : scores, C, nullptr};
+  RE2NN_CUDA(launch_simt_gemm(g, e1, ALoadAlphaBeta{alpha, beta, lengths, L, full_pad}, st));
+  if (priority_mat) {
+    memset(&g, 0, sizeof(g));
+    g.M = B * L; g.N = C; g.nseg = 1; g.ndir = 1;
+    g.seg[0][0] = GemmSeg{ws, priority_mat, C, C, C, 0, 0, 0};
+    EpiStore e2{scores, C, priority_bias};
+    RE2NN_CUDA(launch_simt_gemm(g, e2, ALoadPlain{}, st));
+  }
+  return 0;
+}
+
+}  // extern "C"
+
+extern "C" int re2nn_has_tcgen05(void) {
+#ifdef RE2NN_HAVE_TC
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10;
+#else
+  return 0;
+#endif
+}

@@ -1,0 +1,18 @@
+"""Teacher-mixing losses used when marryup_type is 'kd' or 'pr' (src_seq/baselines/KD.py:3-18).
+Out of the hot-path scope: plain torch on the op's all_scores output."""
+import torch
+import torch.nn.functional as F
+
+
+def KD_loss(scores, re_scores, args):
+    temp = args.c1_kdpr
+    student = torch.log_softmax(scores / temp, 2)
+    teacher = torch.softmax(re_scores / temp, 2)
+    return F.kl_div(student, teacher, reduction='mean') * temp * temp
+
+
+def PR_loss(scores, re_scores, args):
+    log_student = torch.log_softmax(scores, 2)
+    student = torch.softmax(scores, 2)
+    teacher = torch.softmax(student * (torch.exp(re_scores - 1) * args.c1_kdpr), 2)
+    return F.kl_div(log_student, teacher, reduction='mean')

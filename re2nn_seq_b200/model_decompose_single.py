@@ -1,0 +1,320 @@
+"""Drop-in i-FST decompose modules: FARNN_S_D_W_I_S and FARNN_S_SF.
+
+Same class names, constructor signatures, parameter names / shapes / requires_grad flags,
+state_dict keys and forward_local / forward contracts as
+/root/reference/src_seq/farnn/model_decompose_single.py:12-304 (FARNN_S_D_W_I_S) and :307-580
+(FARNN_S_SF); shared helpers follow farnn/model_decompose.py:69-102,191-241,339-371.
+All arithmetic of the hot path runs in the CUDA kernels behind re2nn_seq_b200.ops; this file
+only owns parameters, picks launch-time constants from ``args`` and wires autograd.
+
+Constructor RNG: torch random draws are made in the same order and with the same calls as the
+reference constructor, so a module built after torch.manual_seed(s) is bit-identical to the
+reference module built after the same seed (tests/test_host_modules.py).
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from . import autograd_fns, ops
+from .crf import CRF
+from .priority import PriorityLayer
+from .utils import exclusive_offsets, flatten, get_length_mask
+
+_UPDATE_NL = ('none', 'relu', 'tanh', 'relutanh')
+_ADD_NL = ('none', 'relu', 'tanh', 'sigmoid', 'relutanh')
+
+
+def _nl_name(name, allowed):
+    return name if name in allowed else 'none'     # the reference falls through to "pass" (identity)
+
+
+class _DecomposeBase(nn.Module):
+    """Shared pieces of the rank-R i-FST modules."""
+
+    # ---- construction helpers (model_decompose.py:191-220) ------------------------------------
+    def get_random(self, sizes):
+        kind = self.args.random_pad_func
+        if kind == 'uniform':
+            return torch.rand(sizes)
+        if kind == 'normal':
+            return torch.randn(sizes)
+        t = torch.randn(sizes)
+        nn.init.xavier_normal_(t)
+        return t
+
+    def pad_additional_states(self, obj):
+        """Grow every dimension equal to S by additional_states; 1-D pads with zeros, higher ranks
+        with rand_constant-scaled noise (the noise tensor is drawn even when nothing grows)."""
+        shape = tuple(obj.shape)
+        grown = tuple(d + self.additional_states if d == self.S else d for d in shape)
+        if len(shape) == 1:
+            out = torch.zeros(grown)
+        elif len(shape) in (2, 3, 4):
+            out = self.get_random(grown) * self.args.rand_constant
+        else:
+            raise NotImplementedError()
+        out[tuple(slice(0, d) for d in shape)] = obj
+        return out
+
+    def initialize(self):
+        a = self.args
+        self.additional_nonlinear = a.additional_nonlinear
+        if a.train_mode not in ('sum', 'max'):
+            raise NotImplementedError()
+        if a.local_loss_func not in ('CE', 'CE1'):
+            raise NotImplementedError("re2nn_b200: only the cross-entropy local losses are built (CE, CE1)")
+        if a.sigmoid_exponent <= 0 and a.farnn:
+            raise AssertionError("sigmoid_exponent must be positive")
+        self.precision = getattr(a, 'precision', 'fp32')
+        self._cache = {}
+
+    def _gate_params(self, S_full):
+        a = self.args
+        if a.farnn not in (0, 1, 2):
+            raise NotImplementedError()
+        if a.farnn >= 1:
+            self.Wss1 = nn.Parameter(torch.randn((S_full, S_full)).float(), requires_grad=True)
+            self.Wrs1 = nn.Parameter(torch.randn((self.R, S_full)).float(), requires_grad=True)
+            self.bs1 = nn.Parameter(torch.ones((1, S_full)).float() * a.bias_init, requires_grad=True)
+        if a.farnn == 1 and a.xavier:
+            nn.init.xavier_normal_(self.Wss1)
+            nn.init.xavier_normal_(self.Wrs1)
+            nn.init.xavier_normal_(self.bs1)
+        if a.farnn == 2:
+            self.Wss2 = nn.Parameter(torch.randn((S_full, S_full)).float(), requires_grad=True)
+            self.Wrs2 = nn.Parameter(torch.randn((self.R, S_full)).float(), requires_grad=True)
+            self.bs2 = nn.Parameter(torch.ones((1, S_full)).float() * a.bias_init, requires_grad=True)
+            if a.xavier:
+                for w in (self.Wss1, self.Wrs1, self.Wss2, self.Wrs2):
+                    nn.init.xavier_normal_(w)
+
+    # ---- launch-time constants -----------------------------------------------------------------
+    @property
+    def _S_full(self):
+        return self.S + self.additional_states
+
+    def _device(self):
+        ops.require_cuda()
+        dev = self.S1.device
+        if dev.type != 'cuda':
+            raise RuntimeError("re2nn_b200: %s must live on a CUDA device (call .cuda()); there is no CPU path"
+                               % type(self).__name__)
+        return dev
+
+    def _host_shape(self, lengths):
+        """(L, N) = (max length, total valid tokens) with a single device->host sync."""
+        if lengths.is_cuda:
+            L, N = torch.stack([lengths.max(), lengths.sum()]).tolist()
+        else:
+            L, N = int(lengths.max()), int(lengths.sum())
+        return int(L), int(N)
+
+    def _params_for_fn(self):
+        """Ordered (name, tensor) list handed to the autograd function."""
+        names = ['h0', 'hT', 'S1', 'S2', 'C_output_mat', 'wildcard_mat', 'wildcard_output_vector']
+        if self.args.farnn >= 1:
+            names += ['Wss1', 'Wrs1', 'bs1']
+        if self.args.farnn == 2:
+            names += ['Wss2', 'Wrs2', 'bs2']
+        return names
+
+    # ---- decode (model_decompose.py:339-371) ------------------------------------------------------
+    def decode(self, all_scores, flattened_all_scores, mask, lengths, _shape=None):
+        """all_scores B x L x C -> flat predictions N (int64).  `flattened_all_scores` and `mask`
+        are accepted for signature compatibility; the kernels address valid positions directly."""
+        with torch.no_grad():
+            dev = all_scores.device
+            lengths = lengths.to(dev).contiguous()
+            N = _shape[1] if _shape is not None else int(lengths.sum())
+            offsets = exclusive_offsets(lengths)
+            ce1 = self.args.local_loss_func == 'CE1'
+            sc = all_scores.detach().contiguous()
+            if self.use_crf:
+                flat, _ = ops.crf_viterbi(sc, self.crf.transitions.detach(), lengths, offsets, N,
+                                          clamp_col=self.C - 3 if ce1 else -1, threshold=self.args.threshold,
+                                          o_idx=self.o_idx, want_flat=True, want_padded=False)
+            else:
+                flat, _ = ops.argmax_decode(sc, lengths, offsets, N, clamp_col=self.C - 1 if ce1 else -1,
+                                            threshold=self.args.threshold, o_idx=self.o_idx)
+        return flat
+
+    # ---- loss + decode tail shared by forward_local / forward (model_decompose_single.py:271-304) ---
+    def _finish(self, all_scores, label, lengths, train, re_tags, shape):
+        L, N = shape
+        dev = all_scores.device
+        label = label.to(dev)
+        flattened_true_labels = flatten(label[:, :L], lengths)
+        loss = None
+        if train:
+            lab = label.contiguous()
+            if self.use_crf:
+                loss = self.crf.neg_log_likelihood_loss(all_scores, None, lab, lengths=lengths)
+            else:
+                loss = autograd_fns.ce_loss(all_scores, lengths, lab, N)
+            mt = self.args.marryup_type
+            if mt in ('kd', 'pr'):
+                from .kd import KD_loss, PR_loss
+                B, Lr, _ = re_tags.size()
+                extra = 3 if self.args.use_crf else 1
+                re_tags = torch.cat([re_tags.to(dev), torch.zeros(B, Lr, extra, device=dev)], dim=2)
+                if mt == 'kd':
+                    kl = KD_loss(all_scores, re_tags[:, :L, :], self.args)
+                    loss = self.args.c2_kdpr * loss + (1 - self.args.c2_kdpr) * kl
+                else:
+                    kl = PR_loss(all_scores, re_tags[:, :L, :], self.args)
+                    pi = max(self.args.c2_kdpr, self.args.c3_pr ** self.t)
+                    loss = pi * loss + (1 - pi) * kl
+        pred = self.decode(all_scores, None, None, lengths, _shape=shape)
+        return loss, pred, flattened_true_labels
+
+    def _recurrence_consts(self):
+        a = self.args
+        if a.train_mode == 'max':
+            raise NotImplementedError("re2nn_b200: train_mode='max' is not built for the decompose path yet")
+        return dict(farnn=a.farnn, update_nonlinear=_nl_name(a.update_nonlinear, _UPDATE_NL),
+                    sigmoid_exponent=float(a.sigmoid_exponent), precision=self.precision,
+                    ce1=(a.local_loss_func == 'CE1'), use_priority=bool(a.use_priority),
+                    additional_nonlinear=_nl_name(a.additional_nonlinear, _ADD_NL),
+                    full_pad=bool(getattr(self, 'full_pad', False)) or a.marryup_type in ('kd', 'pr'))
+
+
+class FARNN_S_D_W_I_S(_DecomposeBase):
+    def __init__(self, V=None, S1=None, S2=None, C_output_mat=None, wildcard_mat=None,
+                 wildcard_output_vector=None, final_vector=None, start_vector=None,
+                 pretrained_word_embed=None, priority_mat=None, args=None, o_idx=0, is_cuda=True):
+        super().__init__()
+        self.is_cuda = torch.cuda.is_available() if is_cuda else False
+        self.additional_states = args.additional_states
+        self.args = args
+        self.embedding = nn.Embedding.from_pretrained(torch.from_numpy(pretrained_word_embed).float(),
+                                                      freeze=(not args.train_word_embed))
+        self.C, _ = C_output_mat.shape
+        self.S, self.R = S1.shape
+        self.t = 1
+        self.use_crf = bool(args.use_crf)
+        if self.use_crf:
+            self.crf = CRF(self.C, self.is_cuda)
+            self.C += 2
+        self.priority_layer = PriorityLayer(self.C, priority_mat)
+        self.random = bool(args.random)
+        self.h0 = nn.Parameter(self.pad_additional_states(torch.from_numpy(start_vector).float()),
+                               requires_grad=bool(args.train_h0))
+        self.hT = nn.Parameter(self.pad_additional_states(torch.from_numpy(final_vector).float()),
+                               requires_grad=bool(args.train_hT))
+        self.init_forward_parameters(S1, S2, V, C_output_mat, wildcard_mat, wildcard_output_vector)
+        self.beta = args.beta
+        self.beta_vec = nn.Parameter(torch.tensor([self.beta] * self.R).float(),
+                                     requires_grad=bool(args.train_beta))
+        self.o_idx = o_idx
+        self.not_o_idxs = [i for i in range(self.C) if i != self.o_idx]
+        self.initialize()
+
+    def init_forward_parameters(self, S1, S2, V, C_o, W, W_o):
+        a = self.args
+        self.S1 = nn.Parameter(self.pad_additional_states(torch.from_numpy(S1).float()), requires_grad=True)
+        self.S2 = nn.Parameter(self.pad_additional_states(torch.from_numpy(S2).float()), requires_grad=True)
+        self.V_embed = nn.Parameter(torch.from_numpy(V).float(), requires_grad=bool(a.train_V_embed))
+        # least-squares map from word-embedding space to rank space: G = pinv(E) @ V_embed   (D x R)
+        G = torch.matmul(self.embedding.weight.data.pinverse(), self.V_embed.data)
+        self.embed_r_generalized = nn.Parameter(G, requires_grad=True)
+        if a.use_crf == 1:   # two extra label rows (START/STOP) of small noise
+            C_o = np.concatenate((C_o, self.get_random((2, self.S)).numpy() * a.rand_constant), axis=0)
+        self.C_output_mat = nn.Parameter(self.pad_additional_states(torch.from_numpy(C_o).float()),
+                                         requires_grad=bool(a.train_c_output))
+        self.wildcard_mat = nn.Parameter(self.pad_additional_states(torch.from_numpy(W).float()),
+                                         requires_grad=bool(a.train_wildcard))
+        self.wildcard_output_vector = nn.Parameter(self.pad_additional_states(torch.from_numpy(W_o).float()),
+                                                   requires_grad=bool(a.train_wildcard_wildcard))
+        self._gate_params(self.S + self.additional_states)
+        if self.random:
+            for w in (self.S1, self.S2, self.V_embed, self.C_output_mat, self.embed_r_generalized,
+                      self.wildcard_mat):
+                nn.init.xavier_normal_(w)
+            nn.init.normal_(self.h0)
+            nn.init.normal_(self.hT)
+
+    def _fn_params(self):
+        names = self._params_for_fn() + ['V_embed', 'embed_r_generalized', 'beta_vec']
+        tensors = [getattr(self, n) for n in names] + [self.embedding.weight]
+        return names + ['embedding'], tensors
+
+    def forward_scores(self, input, lengths, shape=None):
+        """all_scores B x L x C (L = max length); differentiable w.r.t. the module parameters."""
+        dev = self._device()
+        x = input.to(dev).contiguous()
+        lengths = lengths.to(dev).contiguous()
+        shape = shape or self._host_shape(lengths)
+        names, tensors = self._fn_params()
+        pr = (self.priority_layer.priority_mat, self.priority_layer.priority_bias)
+        return autograd_fns.decompose_scores(self._recurrence_consts(), names, tensors, pr, x, None, lengths, shape[0],
+                                             cache=self._cache)
+
+    def forward_local(self, input, label, lengths, train=True, re_tags=None):
+        dev = self._device()
+        lengths = lengths.to(dev).contiguous()
+        shape = self._host_shape(lengths)
+        all_scores = self.forward_scores(input, lengths, shape)
+        return self._finish(all_scores, label, lengths, train, re_tags, shape)
+
+
+class FARNN_S_SF(_DecomposeBase):
+    def __init__(self, S1=None, S2=None, C_output_mat=None, wildcard_mat=None, wildcard_output_vector=None,
+                 final_vector=None, start_vector=None, priority_mat=None, args=None, o_idx=0, is_cuda=True):
+        super().__init__()
+        self.is_cuda = torch.cuda.is_available() if is_cuda else False
+        self.additional_states = args.additional_states
+        self.args = args
+        self.C, _ = C_output_mat.shape
+        self.S, self.R = S1.shape
+        self.t = 1
+        self.use_crf = bool(args.use_crf)
+        if self.use_crf:
+            self.crf = CRF(self.C, self.is_cuda)
+            self.C += 2
+        self.priority_layer = PriorityLayer(self.C, priority_mat)
+        self.random = bool(args.random)
+        self.h0 = nn.Parameter(self.pad_additional_states(torch.from_numpy(start_vector).float()),
+                               requires_grad=bool(args.train_h0))
+        self.hT = nn.Parameter(self.pad_additional_states(torch.from_numpy(final_vector).float()),
+                               requires_grad=bool(args.train_hT))
+        self.init_forward_parameters(S1, S2, C_output_mat, wildcard_mat, wildcard_output_vector)
+        self.o_idx = o_idx
+        self.not_o_idxs = [i for i in range(self.C) if i != self.o_idx]
+        self.initialize()
+
+    def init_forward_parameters(self, S1, S2, C_o, W, W_o):
+        a = self.args
+        self.S1 = nn.Parameter(self.pad_additional_states(torch.from_numpy(S1).float()), requires_grad=True)
+        self.S2 = nn.Parameter(self.pad_additional_states(torch.from_numpy(S2).float()), requires_grad=True)
+        if a.use_crf == 1:
+            C_o = np.concatenate((C_o, self.get_random((2, self.S)).numpy() * a.rand_constant), axis=0)
+        self.C_output_mat = nn.Parameter(self.pad_additional_states(torch.from_numpy(C_o).float()),
+                                         requires_grad=bool(a.train_c_output))
+        self.wildcard_mat = nn.Parameter(self.pad_additional_states(torch.from_numpy(W).float()),
+                                         requires_grad=bool(a.train_wildcard))
+        self.wildcard_output_vector = nn.Parameter(self.pad_additional_states(torch.from_numpy(W_o).float()),
+                                                   requires_grad=bool(a.train_wildcard_wildcard))
+        self._gate_params(self.S + self.additional_states)
+        if self.random:
+            for w in (self.S1, self.S2, self.C_output_mat, self.wildcard_mat):
+                nn.init.xavier_normal_(w)
+            nn.init.normal_(self.h0)
+            nn.init.normal_(self.hT)
+
+    def forward_scores(self, input, lengths, shape=None):
+        dev = self._device()
+        v = input.to(dev).float().contiguous()
+        lengths = lengths.to(dev).contiguous()
+        shape = shape or self._host_shape(lengths)
+        names = self._params_for_fn()
+        tensors = [getattr(self, n) for n in names]
+        pr = (self.priority_layer.priority_mat, self.priority_layer.priority_bias)
+        return autograd_fns.decompose_scores(self._recurrence_consts(), names, tensors, pr, None, v, lengths, shape[0])
+
+    def forward(self, input, label, lengths, train=True, re_tags=None):
+        """input: pre-computed rank factors B x L x R (model_decompose_single.py:483-580)."""
+        dev = self._device()
+        lengths = lengths.to(dev).contiguous()
+        shape = self._host_shape(lengths)
+        all_scores = self.forward_scores(input, lengths, shape)
+        return self._finish(all_scores, label, lengths, train, re_tags, shape)

@@ -1,0 +1,232 @@
+"""Thin Python wrappers over the C-ABI: torch owns device memory and streams, the kernels do the work.
+
+Every function takes contiguous CUDA tensors (fp32 / int64), allocates outputs with torch and
+calls one entry point of libre2nn_b200.so on the current stream.  No computation happens in torch.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import NL, PREC, V_DENSE, V_TOKEN, OnehotArgs, RecurrenceArgs, check, fn
+
+_LAUNCHES = {'n': 0}   # launch counter read by bench.py ("gpu_launches")
+
+
+def launches():
+    return _LAUNCHES['n']
+
+
+def _count(k):
+    _LAUNCHES['n'] += k
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("re2nn_b200: expected a CUDA tensor (there is no CPU path)")
+    if not t.is_contiguous():
+        raise RuntimeError("re2nn_b200: expected a contiguous tensor")
+    return C.c_void_p(t.data_ptr())
+
+
+def _f32(t):
+    if t.dtype != torch.float32:
+        raise RuntimeError("re2nn_b200: expected float32, got %s" % t.dtype)
+    return _p(t)
+
+
+def _i64(t):
+    if t.dtype != torch.int64:
+        raise RuntimeError("re2nn_b200: expected int64, got %s" % t.dtype)
+    return _p(t)
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("re2nn_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def token_table(V_embed, E, G, beta_vec, additional_nonlinear):
+    rows, R = V_embed.shape
+    D = E.shape[1]
+    out = torch.empty((rows, R), dtype=torch.float32, device=V_embed.device)
+    check(fn['re2nn_token_table'](_f32(V_embed), _f32(E), _f32(G), _f32(beta_vec), rows, D, R,
+                                  NL[additional_nonlinear], _f32(out), _stream()), 'token_table')
+    _count(1)
+    return out
+
+
+def gate_table(vtab, Wrs1, bs1, Wrs2, bs2, farnn):
+    rows, R = vtab.shape
+    S = Wrs1.shape[1]
+    out = torch.empty((rows, S * farnn), dtype=torch.float32, device=vtab.device)
+    check(fn['re2nn_gate_table'](_f32(vtab), rows, R, S, farnn, _f32(Wrs1), _f32(bs1),
+                                 _f32(Wrs2) if farnn == 2 else None, _f32(bs2) if farnn == 2 else None,
+                                 _f32(out), _stream()), 'gate_table')
+    _count(farnn)
+    return out
+
+
+def output_vector_sum(C_mat, wildcard_vec=None):
+    Cn, S = C_mat.shape
+    o = torch.empty((S,), dtype=torch.float32, device=C_mat.device)
+    check(fn['re2nn_output_vector_sum'](_f32(C_mat), Cn, S, _f32(wildcard_vec) if wildcard_vec is not None else None,
+                                        _f32(o), _stream()), 'output_vector_sum')
+    _count(1)
+    return o
+
+
+def decompose_recurrence(x, lengths, L, vtab, gtab, S1, S2, W, o, h0, hT, Wss1, Wss2, farnn,
+                         update_nonlinear, sigmoid_exponent, precision='fp32', v_mode=V_TOKEN,
+                         full_pad=False, save_for_backward=False, Lpad=None):
+    """Returns (alpha, beta[, zsave, rsave]) — B x L x S each; pad rows are left at 0."""
+    B = lengths.shape[0]
+    S, R = S1.shape
+    dev = S1.device
+    a = RecurrenceArgs()
+    a.B, a.L, a.S, a.R = B, L, S, R
+    a.Lpad = Lpad if Lpad is not None else (x.shape[1] if x is not None else L)
+    a.farnn, a.update_nonlinear, a.precision = farnn, NL[update_nonlinear], PREC[precision]
+    a.v_mode, a.full_pad, a.save_for_backward = v_mode, int(full_pad), int(save_for_backward)
+    a.sigmoid_exponent = float(sigmoid_exponent)
+    alpha = torch.zeros((B, L, S), dtype=torch.float32, device=dev)
+    beta = torch.zeros((B, L, S), dtype=torch.float32, device=dev)
+    zsave = rsave = None
+    if save_for_backward and farnn >= 1:
+        zsave = torch.empty((2, L, B, S), dtype=torch.float32, device=dev)
+        if farnn == 2:
+            rsave = torch.empty((2, L, B, S), dtype=torch.float32, device=dev)
+    a.x = _i64(x) if x is not None else None
+    a.lengths = _i64(lengths)
+    a.vtab, a.gtab = _f32(vtab), (_f32(gtab) if gtab is not None else None)
+    a.S1, a.S2, a.W, a.o, a.h0, a.hT = _f32(S1), _f32(S2), _f32(W), _f32(o), _f32(h0), _f32(hT)
+    a.Wss1 = _f32(Wss1) if Wss1 is not None else None
+    a.Wss2 = _f32(Wss2) if Wss2 is not None else None
+    a.alpha, a.beta = _f32(alpha), _f32(beta)
+    a.zsave = _f32(zsave) if zsave is not None else None
+    a.rsave = _f32(rsave) if rsave is not None else None
+    need = fn['re2nn_decompose_recurrence_workspace'](C.byref(a))
+    ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+    a.ws, a.ws_bytes = C.c_void_p(ws.data_ptr()), need
+    check(fn['re2nn_decompose_recurrence'](C.byref(a), _stream()), 'decompose_recurrence')
+    _count(1 + (1 if farnn == 2 or precision != 'fp32' else 0) + L * (2 + (1 if farnn else 0)))
+    return alpha, beta, zsave, rsave
+
+
+def onehot_recurrence(x, lengths, L, language, W, o, h0, hT, update_nonlinear, max_semiring=False, full_pad=False):
+    B, Lpad = x.shape
+    S = W.shape[0]
+    a = OnehotArgs()
+    a.B, a.Lpad, a.L, a.S = B, Lpad, L, S
+    a.update_nonlinear, a.max_semiring, a.full_pad = NL[update_nonlinear], int(max_semiring), int(full_pad)
+    alpha = torch.zeros((B, L, S), dtype=torch.float32, device=W.device)
+    beta = torch.zeros((B, L, S), dtype=torch.float32, device=W.device)
+    a.x, a.lengths = _i64(x), _i64(lengths)
+    a.language, a.W, a.o, a.h0, a.hT = _f32(language), _f32(W), _f32(o), _f32(h0), _f32(hT)
+    a.alpha, a.beta = _f32(alpha), _f32(beta)
+    check(fn['re2nn_onehot_recurrence'](C.byref(a), _stream()), 'onehot_recurrence')
+    _count(1)
+    return alpha, beta
+
+
+def label_scores(alpha, beta, lengths, C_mat, priority_mat=None, priority_bias=None, full_pad=False):
+    B, L, S = alpha.shape
+    Cn = C_mat.shape[0]
+    scores = torch.empty((B, L, Cn), dtype=torch.float32, device=alpha.device)
+    ws = torch.empty((B, L, Cn), dtype=torch.float32, device=alpha.device) if priority_mat is not None else None
+    check(fn['re2nn_label_scores'](_f32(alpha), _f32(beta), _i64(lengths), B, L, S, _f32(C_mat), Cn,
+                                   _f32(priority_mat) if priority_mat is not None else None,
+                                   _f32(priority_bias) if priority_bias is not None else None,
+                                   int(full_pad), _f32(scores), _f32(ws) if ws is not None else None, _stream()),
+          'label_scores')
+    _count(2 if priority_mat is not None else 1)
+    return scores
+
+
+def argmax_decode(scores, lengths, offsets, n_flat, clamp_col, threshold, o_idx, want_flat=True, want_padded=False):
+    B, L, Cn = scores.shape
+    flat = torch.empty((n_flat,), dtype=torch.int64, device=scores.device) if want_flat else None
+    padded = torch.empty((B, L), dtype=torch.int64, device=scores.device) if want_padded else None
+    check(fn['re2nn_argmax_decode'](_f32(scores), _i64(lengths), _i64(offsets) if offsets is not None else None,
+                                    B, L, Cn, clamp_col, float(threshold), int(o_idx),
+                                    _i64(flat) if flat is not None else None,
+                                    _i64(padded) if padded is not None else None, _stream()), 'argmax_decode')
+    _count(1)
+    return flat, padded
+
+
+def crf_viterbi(feats, transitions, lengths, offsets=None, n_flat=0, clamp_col=-1, threshold=0.0, o_idx=0,
+                want_flat=False, want_padded=True):
+    B, L, T = feats.shape
+    dev = feats.device
+    flat = torch.empty((n_flat,), dtype=torch.int64, device=dev) if want_flat else None
+    padded = torch.empty((B, L), dtype=torch.int64, device=dev) if want_padded else None
+    bp = torch.empty((B * L * T,), dtype=torch.int16, device=dev)
+    check(fn['re2nn_crf_viterbi'](_f32(feats), _f32(transitions), _i64(lengths),
+                                  _i64(offsets) if offsets is not None else None, B, L, T, clamp_col,
+                                  float(threshold), int(o_idx), _i64(padded) if padded is not None else None,
+                                  _i64(flat) if flat is not None else None, C.c_void_p(bp.data_ptr()), _stream()),
+          'crf_viterbi')
+    _count(1)
+    return flat, padded
+
+
+def crf_nll(feats, transitions, lengths, tags, save=False):
+    B, L, T = feats.shape
+    dev = feats.device
+    per_seq = torch.empty((B,), dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    part = torch.empty((B, L, T), dtype=torch.float32, device=dev) if save else None
+    check(fn['re2nn_crf_nll'](_f32(feats), _f32(transitions), _i64(lengths), _i64(tags), B, L, tags.shape[1], T,
+                              _f32(per_seq), _f32(loss), _f32(part) if part is not None else None, _stream()),
+          'crf_nll')
+    _count(2)
+    return loss, per_seq, part
+
+
+def crf_nll_backward(feats, transitions, lengths, tags, part, gscale):
+    B, L, T = feats.shape
+    dfeats = torch.empty_like(feats)
+    dtrans = torch.empty((T, T), dtype=torch.float32, device=feats.device)
+    check(fn['re2nn_crf_nll_backward'](_f32(feats), _f32(transitions), _i64(lengths), _i64(tags), _f32(part),
+                                       _f32(gscale), B, L, tags.shape[1], T, _f32(dfeats), _f32(dtrans), _stream()),
+          'crf_nll_backward')
+    _count(1)
+    return dfeats, dtrans
+
+
+def ce_loss(scores, lengths, labels, n_total):
+    B, L, Cn = scores.shape
+    per_pos = torch.empty((B * L,), dtype=torch.float32, device=scores.device)
+    loss = torch.empty((), dtype=torch.float32, device=scores.device)
+    check(fn['re2nn_ce_loss'](_f32(scores), _i64(lengths), _i64(labels), B, L, labels.shape[1], Cn, int(n_total),
+                              _f32(per_pos), _f32(loss), _stream()), 'ce_loss')
+    _count(2)
+    return loss
+
+
+def ce_loss_backward(scores, lengths, labels, n_total, gscale):
+    B, L, Cn = scores.shape
+    d = torch.empty_like(scores)
+    check(fn['re2nn_ce_loss_backward'](_f32(scores), _i64(lengths), _i64(labels), _f32(gscale), B, L,
+                                       labels.shape[1], Cn, int(n_total), _f32(d), _stream()), 'ce_loss_backward')
+    _count(1)
+    return d
+
+
+def profile_enable(on):
+    check(fn['re2nn_profile_enable'](int(on)), 'profile_enable')
+
+
+def profile_read():
+    """-> ([ms_gate, ms_gemm1, ms_gemm2], [n_gate, n_gemm1, n_gemm2]) summed since the last read."""
+    ms = (C.c_double * 3)()
+    cnt = (C.c_int64 * 3)()
+    check(fn['re2nn_profile_read'](ms, cnt), 'profile_read')
+    return list(ms), list(cnt)

@@ -1,0 +1,132 @@
+"""GPU: CUDA path (through the C-ABI) vs the reference's golden fixtures and the oracle.
+
+Tolerances (north_star): decoded tags / Viterbi paths bit-exact; scores, losses, gradients within
+1e-5 relative in fp32 (rel = max|a-b| / max|b| over the tensor)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_files
+from helpers import args_of, build_module, golden_grads, load_golden, oracle_params, rel_err
+from oracle import re2nn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+GRAD_TOL = 2e-5
+
+
+def _t(a, dev='cuda'):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+DEC = [n for n in golden_files('dec_') + golden_files('sf_')]
+
+
+@pytest.mark.parametrize('name', DEC)
+def test_decompose_golden(name):
+    z, meta = load_golden(name)
+    if meta['flags'].get('train_mode') == 'max':
+        pytest.skip("train_mode='max' decompose path not built yet")
+    m = build_module(name, z, meta).cuda()
+    x, lab, lens = _t(z['x']), _t(z['labels']), _t(z['lengths'])
+    inp = _t(z['dense_v']) if meta['kind'] == 'sf' else x
+    with torch.no_grad():
+        scores = m.forward_scores(inp, lens)
+        if meta['kind'] == 'sf':
+            loss, pred, true = m(inp, lab, lens, True)
+        else:
+            loss, pred, true = m.forward_local(inp, lab, lens, train=True)
+    L = int(z['lengths'].max())
+    mask = orc.length_mask(z['lengths'], L)
+    got = scores.cpu().numpy()
+    ref = z['all_scores']
+    assert rel_err(got[mask], ref[mask]) < TOL
+    assert rel_err(loss.item(), z['loss']) < TOL
+    np.testing.assert_array_equal(pred.cpu().numpy(), z['pred'])
+    np.testing.assert_array_equal(true.cpu().numpy(), z['true'])
+
+
+@pytest.mark.parametrize('name', golden_files('one_'))
+def test_onehot_golden(name):
+    z, meta = load_golden(name)
+    m = build_module(name, z, meta)
+    x, lab, lens = torch.from_numpy(z['x']), torch.from_numpy(z['labels']), torch.from_numpy(z['lengths'])   # CPU in
+    with torch.no_grad():
+        scores = m.forward_score(x, lab, lens)
+        loss, pred, true = m.forward_local(x, lab, lens, train=True)
+        re_pred, re_scores = m.forward_RE(x, lab, lens)
+    assert scores.device.type == 'cpu' and pred.device.type == 'cpu'          # results return on the caller's device
+    if meta['flags']['rand_constant'] == 0:
+        np.testing.assert_array_equal(scores.numpy(), z['all_scores'])          # exact path counts, pads included
+    assert rel_err(scores.numpy(), z['all_scores']) < TOL                       # pad positions included
+    assert rel_err(loss.item(), z['loss']) < TOL
+    np.testing.assert_array_equal(pred.numpy(), z['pred'])
+    np.testing.assert_array_equal(true.numpy(), z['true'])
+    np.testing.assert_array_equal(re_pred.numpy(), z['re_pred'])
+    assert rel_err(re_scores.numpy(), z['re_scores']) < TOL
+    flat = orc.flatten_rows(z['all_scores'], z['lengths'])
+    np.testing.assert_array_equal(m.local_decode(torch.from_numpy(flat)).numpy(), z['pred'])
+
+
+@pytest.mark.parametrize('name', golden_files('crf_'))
+def test_crf_golden(name):
+    import re2nn_seq_b200 as r
+    z, meta = load_golden(name)
+    crf = r.CRF(meta['tagset'], True).cuda()
+    with torch.no_grad():
+        crf.transitions.copy_(_t(z['transitions']))
+    feats = _t(z['feats']).requires_grad_(True)
+    lens = z['lengths']
+    mask = _t(orc.length_mask(lens, z['feats'].shape[1]))
+    loss = crf.neg_log_likelihood_loss(feats, mask, _t(z['tags']))
+    assert rel_err(loss.item(), z['loss']) < TOL
+    _, path = crf._viterbi_decode(feats.detach(), mask)
+    np.testing.assert_array_equal(path.cpu().numpy(), z['path'])                # pad quirks included
+    loss.backward()
+    assert rel_err(feats.grad.cpu().numpy(), z['g_feats']) < GRAD_TOL
+    assert rel_err(crf.transitions.grad.cpu().numpy(), z['g_transitions']) < GRAD_TOL
+
+
+def _random_decompose(seed, V, S, R, C, D, B, Lmax, **flags):
+    from re2nn_seq_b200 import synth
+    import re2nn_seq_b200 as r
+    args = synth.make_args(**flags)
+    f = synth.make_decompose_factors(seed, V, S, R, C, D, dtype=np.float32)
+    x, lens, lab = synth.make_batch(seed + 1, B, Lmax, V, C)
+    torch.manual_seed(seed)
+    m = r.FARNN_S_D_W_I_S(args=args, o_idx=0, **f)
+    with torch.no_grad():
+        if args.use_crf:
+            m.crf.transitions.copy_(torch.from_numpy(synth.crf_transitions(seed, m.C)))
+        if args.farnn:
+            for n in ('Wss1', 'Wrs1', 'Wss2', 'Wrs2'):
+                if hasattr(m, n):
+                    getattr(m, n).mul_(0.05)
+            m.bs1.fill_(0.3)
+    return m.cuda(), args, x, lens, lab
+
+
+@pytest.mark.parametrize('farnn,crf', [(0, 1), (2, 1), (1, 0)])
+def test_decompose_cfg2_shapes_vs_oracle(farnn, crf):
+    """SNIPS-shaped factors (S=300, R=200, C=72, D=100) on a batch the oracle finishes in seconds."""
+    m, args, x, lens, lab = _random_decompose(5, 2000, 300, 200, 72, 100, 96, 35, farnn=farnn, use_crf=crf,
+                                              update_nonlinear='tanh', beta=0.1)
+    with torch.no_grad():
+        scores = m.forward_scores(_t(x), _t(lens)).cpu().numpy()
+        loss, pred, true = m.forward_local(_t(x), _t(lab), _t(lens), train=True)
+    sd = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    z = {'p.' + k: v for k, v in sd.items()}
+
+    class _Z(dict):
+        files = property(lambda self: list(self.keys()))
+    p32 = oracle_params(_Z(z), np.float32)
+    p64 = oracle_params(_Z(z), np.float64)
+    o_loss, o_pred, o_true, o_scores = orc.decompose_forward_local(p32, x, lab, lens, args, 0, True)
+    t_scores, _, _ = orc.decompose_scores(p64, x, lens, args)
+    mask = orc.length_mask(lens, 35)
+    assert rel_err(scores[mask], t_scores[mask]) < TOL                # vs the float64 truth
+    assert rel_err(scores[mask], o_scores[mask]) < TOL                # vs the fp32 restatement
+    assert rel_err(loss.item(), o_loss) < TOL
+    np.testing.assert_array_equal(true.cpu().numpy(), o_true)
+    mism = int((pred.cpu().numpy() != o_pred).sum())
+    assert mism == 0, 'decoded tags differ at %d of %d positions' % (mism, len(o_pred))

@@ -1,0 +1,53 @@
+"""CPU: the drop-in modules expose the reference's parameter surface and reproduce its initialisation."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_files
+from helpers import build_module, load_golden
+
+# parameters make_golden.py perturbs after construction
+_PERTURBED = ('crf.transitions', 'beta_vec', 'wildcard_output_vector', 'output_wildcard_vector', 'bs1', 'bs2')
+_SCALED = ('Wss1', 'Wrs1', 'Wss2', 'Wrs2')
+
+
+@pytest.mark.parametrize('name', golden_files('dec_') + golden_files('sf_') + golden_files('one_'))
+def test_state_dict_surface_and_init(name):
+    z, meta = load_golden(name)
+    m = build_module(name, z, meta, load_state=False).cpu()
+    sd = m.state_dict()
+    gold = {k[2:]: z[k] for k in z.files if k.startswith('p.')}
+    assert sorted(sd.keys()) == sorted(gold.keys())                  # same state_dict keys
+    for k, g in gold.items():
+        assert tuple(sd[k].shape) == g.shape, k
+        if k in _PERTURBED:
+            continue
+        mine = sd[k].numpy() * np.float32(0.3) if k in _SCALED else sd[k].numpy()
+        np.testing.assert_array_equal(mine, g, err_msg=k)            # same RNG draws, same values
+    grads = {k[2:] for k in z.files if k.startswith('g.')}
+    trainable = {k for k, v in m.named_parameters() if v.requires_grad}
+    assert grads <= trainable
+
+
+def test_forward_without_gpu_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    z, meta = load_golden('dec_f0_tanh_crf')
+    m = build_module('dec_f0_tanh_crf', z, meta)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        m.forward_local(torch.from_numpy(z['x']), torch.from_numpy(z['labels']), torch.from_numpy(z['lengths']),
+                        train=False)
+
+
+def test_utils_match_oracle():
+    from oracle import re2nn_oracle as orc
+    from re2nn_seq_b200 import utils
+    rs = np.random.RandomState(0)
+    a = rs.randn(5, 7, 3).astype(np.float32)
+    lens = np.array([7, 1, 3, 5, 2])
+    np.testing.assert_array_equal(utils.reverse(torch.from_numpy(a), torch.from_numpy(lens)).numpy(),
+                                  orc.reverse_rows(a, lens))
+    np.testing.assert_array_equal(utils.flatten(torch.from_numpy(a), torch.from_numpy(lens)).numpy(),
+                                  orc.flatten_rows(a, lens))
+    np.testing.assert_array_equal(utils.get_length_mask(torch.from_numpy(lens)).numpy(), orc.length_mask(lens))
+    np.testing.assert_array_equal(utils.exclusive_offsets(torch.from_numpy(lens)).numpy(), [0, 7, 8, 11, 16])
