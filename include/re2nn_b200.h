@@ -59,6 +59,15 @@ int re2nn_has_tcgen05(void);
 int re2nn_profile_enable(int on);
 int re2nn_profile_read(double* ms_out_host, int64_t* count_out_host);
 
+/* ---- stand-alone GEMM through the step-GEMM mainloops (unit-test / calibration entry) -------------------
+ * C[M x N] = A[M x K] @ B[N x K]^T, A/B/C fp32 row-major.  precision selects the mainloop:
+ * RE2NN_PREC_FP32 (CUDA cores), RE2NN_PREC_BF16 / RE2NN_PREC_TF32X3 (tcgen05; operands are first
+ * converted into `ws`).  Not on the reference's path; it exists so the tensor-core mainloop can be
+ * checked in isolation against a known product. */
+size_t re2nn_gemm_nt_workspace(int precision, int M, int N, int K);
+int re2nn_gemm_nt(int precision, const float* A, const float* B, int M, int N, int K, float* C, void* ws,
+                  size_t ws_bytes, void* stream);
+
 /* ---- generalised token factor table ------------------------------------------------------------
  * table[r, :] = V_embed[r,:]*beta_vec + phi_add(E[r,:] @ G) * (1 - beta_vec)   for r in [0, rows)
  * replaces get_generalized_v_embed_vec (farnn/model_decompose.py:222-241) evaluated per token id;

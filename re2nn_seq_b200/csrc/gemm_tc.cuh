@@ -131,18 +131,6 @@ inline int weight_prep_run(const re2nn_recurrence_args& a, WeightPrep& w, cudaSt
   return 0;
 }
 
-// ---- tcgen05 mainloop: filled in by gemm_tc_impl (phase 2) ---------------------------------------------
-struct TcStepMaps { int dummy; };
-struct TcRecurrenceMaps { TcStepMaps gate, g1[2], g2[2]; };
-
-template <int PREC>
-inline int tc_build_maps(const re2nn_recurrence_args&, void* const*, void* const (*)[2], void* const*,
-                         const WeightPrep&, TcRecurrenceMaps*) {
-  return set_error("tcgen05 path not built");
-}
-template <int PREC, class Epi>
-inline cudaError_t launch_tc_gemm(const GemmProblem&, const Epi&, const TcStepMaps*, cudaStream_t) {
-  return cudaErrorNotSupported;
-}
-
 }  // namespace re2nn
+
+#include "gemm_tc_impl.cuh"

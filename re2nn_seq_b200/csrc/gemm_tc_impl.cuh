@@ -1,0 +1,331 @@
+// tcgen05 step GEMM (sm_100a): TMA -> 128B-swizzled shared memory -> tcgen05.mma (accumulator in TMEM)
+// -> tcgen05.ld -> fused epilogue functor.  One 128 x BN output tile per CTA, warp-specialised:
+//   warp 0      TMA producer (one elected lane), STAGES-deep mbarrier ring
+//   warp 1      TMEM allocator + MMA issuer (one elected lane)
+//   warps 2..5  epilogue: each warp owns the 32 TMEM lanes (rows) its warp-id quarter may access
+// Both operands are K-major (A: M x K, B: N x K, K contiguous), bf16 (kind::f16) or tf32 (kind::tf32);
+// TF32X3 runs three (A_hi,B_hi) / (A_lo,B_hi) / (A_hi,B_lo) segment passes into the same accumulator.
+#pragma once
+#include <cuda.h>
+
+#include "gemm_common.cuh"
+
+#define RE2NN_HAVE_TC 1
+
+namespace re2nn {
+
+constexpr int kTcMaxMaps = 16;
+constexpr int kTcMaxSeg = 6;
+
+struct TcSeg { int a_map, b_map, kblocks; };
+struct __align__(64) TcLaunch {
+  CUtensorMap maps[kTcMaxMaps];
+  TcSeg seg[2][kTcMaxSeg];
+  int nseg, nmaps, M, N, BN, ndir;
+};
+typedef TcLaunch TcStepMaps;
+struct TcRecurrenceMaps { TcLaunch gate, g1[2], g2[2]; };
+
+// ---- host: tensor maps ---------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline PFN_tmapEncodeTiled tmap_encoder() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_tmapEncodeTiled)p;
+  }
+  return fn;
+}
+
+// rows x K operand (K contiguous, leading dimension ld elements); box = box_rows x (128 bytes of K)
+template <int PREC>
+inline int make_operand_map(CUtensorMap* m, const void* base, size_t elem_off, int rows, int K, int ld, int box_rows) {
+  PFN_tmapEncodeTiled enc = tmap_encoder();
+  RE2NN_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  constexpr int eb = OperandFmt<PREC>::kElemBytes;
+  const char* addr = (const char*)base + elem_off * eb;
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * eb};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / eb), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  RE2NN_CHECK(((uintptr_t)addr & 15) == 0 && (gstride[0] & 15) == 0, "tensor map: operand not 16-byte aligned");
+  CUresult r = enc(m, PREC == RE2NN_PREC_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   (void*)addr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RE2NN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%d box_rows=%d", (int)r, rows, K,
+              ld, box_rows);
+  return 0;
+}
+
+inline int tc_pick_bn(int M, int N, int ndir) {
+  const long mt = (long)cdiv(M, 128) * ndir;
+  if (mt * cdiv(N, 256) >= 148 && N >= 192) return 256;
+  if (mt * cdiv(N, 128) >= 296 && N >= 96) return 128;
+  return 64;
+}
+
+// Expand a GemmProblem (operands already in the PREC operand format, all B operands K-major) into maps.
+template <int PREC>
+inline int tc_make_launch(const GemmProblem& g, TcLaunch* out) {
+  memset(out, 0, sizeof(*out));
+  out->M = g.M; out->N = g.N; out->ndir = g.ndir;
+  out->BN = tc_pick_bn(g.M, g.N, g.ndir);
+  constexpr int kpb = 128 / OperandFmt<PREC>::kElemBytes;   // K elements per 128-byte block
+  int nm = 0;
+  for (int z = 0; z < g.ndir; ++z) {
+    int ns = 0;
+    for (int s = 0; s < g.nseg; ++s) {
+      const GemmSeg& sg = g.seg[z][s];
+      RE2NN_CHECK(sg.b_nk == 1, "tcgen05 path needs K-major B operands");
+      const int kb = cdiv(sg.K, kpb);
+      RE2NN_CHECK(nm + 2 * OperandFmt<PREC>::kPlanes <= kTcMaxMaps, "too many tensor maps");
+      const int a_hi = nm++;
+      if (int rc = make_operand_map<PREC>(&out->maps[a_hi], sg.A, 0, g.M, sg.K, sg.lda, 128)) return rc;
+      const int b_hi = nm++;
+      if (int rc = make_operand_map<PREC>(&out->maps[b_hi], sg.B, 0, g.N, sg.K, sg.ldb, out->BN)) return rc;
+      out->seg[z][ns++] = TcSeg{a_hi, b_hi, kb};
+      if (PREC == RE2NN_PREC_TF32X3) {
+        const int a_lo = nm++;
+        if (int rc = make_operand_map<PREC>(&out->maps[a_lo], sg.A, sg.a_plane, g.M, sg.K, sg.lda, 128)) return rc;
+        const int b_lo = nm++;
+        if (int rc = make_operand_map<PREC>(&out->maps[b_lo], sg.B, sg.b_plane, g.N, sg.K, sg.ldb, out->BN)) return rc;
+        out->seg[z][ns++] = TcSeg{a_lo, b_hi, kb};
+        out->seg[z][ns++] = TcSeg{a_hi, b_lo, kb};
+      }
+    }
+    out->nseg = ns;
+  }
+  out->nmaps = nm;
+  return 0;
+}
+
+// ---- device: PTX wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  if (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+  }
+}
+// K-major, 128-byte swizzled tile: rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address
+  d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN> struct TcCfg {
+  static constexpr int kStages = BN == 64 ? 3 : (BN == 128 ? 3 : 4);
+  static constexpr int kABytes = 128 * 128;
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+constexpr int kTcThreads = 192;
+
+template <int PREC, int BN, class Epi>
+__global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(const __grid_constant__ TcLaunch L, const Epi epi) {
+  using Cfg = TcCfg<BN>;
+  constexpr bool TF32 = PREC == RE2NN_PREC_TF32X3;
+  const int z = blockIdx.z;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+  const int rows = min(128, L.M - m0);
+  if (!epi.tile_alive(z, m0, rows)) return;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + Cfg::kStages * Cfg::kStageBytes;     // full[S], empty[S], tmem_full, tmem_ptr
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (Cfg::kStages + s); };
+  const uint32_t tmem_full = bars + 8u * (2 * Cfg::kStages);
+  const uint32_t tmem_slot = tmem_full + 8u;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_p = (volatile uint32_t*)(gen_base + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nseg = L.nseg;
+  int total_kb = 0;
+  for (int s = 0; s < nseg; ++s) total_kb += L.seg[z][s].kblocks;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < nseg; ++s) {
+      tma_prefetch_desc(&L.maps[L.seg[z][s].a_map]);
+      tma_prefetch_desc(&L.maps[L.seg[z][s].b_map]);
+    }
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot_p;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int s = 0; s < nseg; ++s) {
+        const TcSeg sg = L.seg[z][s];
+        const CUtensorMap* ma = &L.maps[sg.a_map];
+        const CUtensorMap* mb = &L.maps[sg.b_map];
+        constexpr int kpb = 128 / OperandFmt<PREC>::kElemBytes;
+        for (int kb = 0; kb < sg.kblocks; ++kb, ++it) {
+          const int st = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait(empty_bar(st), ph ^ 1);
+          const uint32_t sa = base + st * Cfg::kStageBytes;
+          mbar_expect_tx(full_bar(st), Cfg::kStageBytes);
+          tma_load_2d(sa, ma, full_bar(st), kb * kpb, m0);
+          tma_load_2d(sa + Cfg::kABytes, mb, full_bar(st), kb * kpb, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A/B = bf16 (1) or tf32 (2), both K-major, N>>3, M>>4
+      const uint32_t fmt = TF32 ? 2u : 1u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+      for (int it = 0; it < total_kb; ++it) {
+        const int st = it % Cfg::kStages;
+        const uint32_t ph = (it / Cfg::kStages) & 1;
+        mbar_wait(full_bar(st), ph);
+        tc_fence_after();
+        const uint32_t sa = base + st * Cfg::kStageBytes;
+        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + Cfg::kABytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // 4 x 32-byte K steps per 128-byte block (16 bf16 / 8 tf32 each)
+          tc_mma<TF32>(tmem_acc, da + 2u * k, db + 2u * k, idesc, (it | k) != 0 ? 1u : 0u);
+        tc_commit(empty_bar(st));     // frees the smem slot once these MMAs have read it
+      }
+      tc_commit(tmem_full);           // accumulator complete
+    }
+  } else {
+    // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const bool row_ok = m < L.M;
+    RowCtx rc{0, -1, false};
+    if (row_ok) rc = epi.row(z, m);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= L.N) break;     // warp-uniform
+      uint32_t r[32];
+      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + c0 + j;
+          if (n < L.N) epi.apply(rc, z, m, n, __uint_as_float(r[j]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)BN));
+  }
+}
+
+template <int PREC, int BN, class Epi>
+inline cudaError_t launch_tc_bn(const TcLaunch& L, const Epi& epi, cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<PREC, BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid(cdiv(L.M, 128), cdiv(L.N, BN), L.ndir);
+  tc_gemm_kernel<PREC, BN, Epi><<<grid, kTcThreads, Cfg::kSmem, st>>>(L, epi);
+  return cudaGetLastError();
+}
+
+template <int PREC, class Epi>
+inline cudaError_t launch_tc_gemm(const GemmProblem&, const Epi& epi, const TcStepMaps* L, cudaStream_t st) {
+  if constexpr (PREC == RE2NN_PREC_FP32) {
+    return cudaErrorNotSupported;
+  } else {
+    if (L == nullptr) return cudaErrorInvalidValue;
+    switch (L->BN) {
+      case 64: return launch_tc_bn<PREC, 64>(*L, epi, st);
+      case 128: return launch_tc_bn<PREC, 128>(*L, epi, st);
+      default: return launch_tc_bn<PREC, 256>(*L, epi, st);
+    }
+  }
+}
+
+}  // namespace re2nn

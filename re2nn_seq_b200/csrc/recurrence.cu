@@ -2,6 +2,7 @@
 // Reference: /root/reference/src_seq/farnn/model_decompose_single.py:138-269, model_decompose.py:222-241.
 #include <stdarg.h>
 
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -131,9 +132,34 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
     RE2NN_LAUNCH_CHECK();
   }
 
-  TcRecurrenceMaps tmaps;
-  if (PREC != RE2NN_PREC_FP32) {
-    if (int rc = tc_build_maps<PREC>(a, w.Q, w.Hbar, w.Hst, w.wp, &tmaps)) return rc;
+  // the three step GEMMs, per ping-pong parity of the Hbar operand
+  GemmProblem g_gate, g_1[2], g_2[2];
+  memset(&g_gate, 0, sizeof(g_gate));
+  g_gate.M = B; g_gate.N = S * a.farnn; g_gate.nseg = 1; g_gate.ndir = 2;
+  if (a.farnn >= 1)
+    for (int z = 0; z < 2; ++z) g_gate.seg[z][0] = w.wp.seg_gate(w.Hst[z], ldh, h_plane);
+  for (int par = 0; par < 2; ++par) {
+    memset(&g_1[par], 0, sizeof(GemmProblem));
+    memset(&g_2[par], 0, sizeof(GemmProblem));
+    g_1[par].M = B; g_1[par].N = R; g_1[par].nseg = 1; g_1[par].ndir = 2;   // P = Hbar @ S1 | Hbar @ S2
+    g_2[par].M = B; g_2[par].N = S; g_2[par].nseg = 2; g_2[par].ndir = 2;   // Q @ S2^T + Hbar @ W | Q @ S1^T + Hbar @ W^T
+    for (int z = 0; z < 2; ++z) {
+      g_1[par].seg[z][0] = w.wp.seg_g1(z, w.Hbar[par][z], ldh, h_plane);
+      g_2[par].seg[z][0] = w.wp.seg_g2q(z, w.Q[z], ldq, q_plane);
+      g_2[par].seg[z][1] = w.wp.seg_g2w(z, w.Hbar[par][z], ldh, h_plane);
+    }
+  }
+  TcRecurrenceMaps* tm = nullptr;
+  std::unique_ptr<TcRecurrenceMaps> tm_hold;
+  if constexpr (PREC != RE2NN_PREC_FP32) {
+    tm_hold.reset(new TcRecurrenceMaps);
+    tm = tm_hold.get();
+    if (a.farnn >= 1)
+      if (int rc = tc_make_launch<PREC>(g_gate, &tm->gate)) return rc;
+    for (int par = 0; par < 2; ++par) {
+      if (int rc = tc_make_launch<PREC>(g_1[par], &tm->g1[par])) return rc;
+      if (int rc = tc_make_launch<PREC>(g_2[par], &tm->g2[par])) return rc;
+    }
   }
 
   StepParams p;
@@ -157,26 +183,10 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
       p.Z[z] = (a.save_for_backward && a.zsave) ? a.zsave + slab : w.Z[z];
       p.Rg[z] = (a.save_for_backward && a.rsave) ? a.rsave + slab : nullptr;
     }
-    GemmProblem g;
-    if (a.farnn >= 1) {   // gates: [Z | R]pre = Hst @ [Wss1 | Wss2]
-      memset(&g, 0, sizeof(g));
-      g.M = B; g.N = S * a.farnn; g.nseg = 1; g.ndir = 2;
-      for (int z = 0; z < 2; ++z) g.seg[z][0] = w.wp.seg_gate(w.Hst[z], ldh, h_plane);
-      RE2NN_CUDA((launch_gemm<PREC>(0, g, EpiGate<PREC>{p}, PREC != RE2NN_PREC_FP32 ? &tmaps.gate : nullptr, st)));
-    }
-    // GEMM1: P = Hbar @ S1 (fwd) | Hbar @ S2 (bwd) ; Q = P * v_t
-    memset(&g, 0, sizeof(g));
-    g.M = B; g.N = R; g.nseg = 1; g.ndir = 2;
-    for (int z = 0; z < 2; ++z) g.seg[z][0] = w.wp.seg_g1(z, w.Hbar[par][z], ldh, h_plane);
-    RE2NN_CUDA((launch_gemm<PREC>(1, g, EpiQ<PREC>{p}, PREC != RE2NN_PREC_FP32 ? &tmaps.g1[par] : nullptr, st)));
-    // GEMM2: Hn = Q @ S2^T + Hbar @ W (fwd) | Q @ S1^T + Hbar @ W^T (bwd)
-    memset(&g, 0, sizeof(g));
-    g.M = B; g.N = S; g.nseg = 2; g.ndir = 2;
-    for (int z = 0; z < 2; ++z) {
-      g.seg[z][0] = w.wp.seg_g2q(z, w.Q[z], ldq, q_plane);
-      g.seg[z][1] = w.wp.seg_g2w(z, w.Hbar[par][z], ldh, h_plane);
-    }
-    RE2NN_CUDA((launch_gemm<PREC>(2, g, EpiH<PREC>{p}, PREC != RE2NN_PREC_FP32 ? &tmaps.g2[par] : nullptr, st)));
+    if (a.farnn >= 1)
+      RE2NN_CUDA((launch_gemm<PREC>(0, g_gate, EpiGate<PREC>{p}, tm ? &tm->gate : nullptr, st)));
+    RE2NN_CUDA((launch_gemm<PREC>(1, g_1[par], EpiQ<PREC>{p}, tm ? &tm->g1[par] : nullptr, st)));
+    RE2NN_CUDA((launch_gemm<PREC>(2, g_2[par], EpiH<PREC>{p}, tm ? &tm->g2[par] : nullptr, st)));
   }
   return 0;
 }
@@ -184,6 +194,28 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
 }  // namespace re2nn
 
 using namespace re2nn;
+
+extern "C" int re2nn_has_tcgen05(void);
+
+template <int PREC>
+static int gemm_nt_tc(const float* A, const float* B, int M, int N, int K, float* C, void* ws, cudaStream_t st) {
+  const int ld = operand_ld(PREC, K);
+  void* Ao = ws;
+  void* Bo = (char*)ws + operand_bytes(PREC, M, K);
+  const size_t pa = (size_t)M * ld, pb = (size_t)N * ld;
+  convert_weight_kernel<PREC><<<(unsigned)(((size_t)M * ld + 255) / 256), 256, 0, st>>>(A, M, K, K, 0, Ao, ld, pa, 0);
+  RE2NN_LAUNCH_CHECK();
+  convert_weight_kernel<PREC><<<(unsigned)(((size_t)N * ld + 255) / 256), 256, 0, st>>>(B, N, K, K, 0, Bo, ld, pb, 0);
+  RE2NN_LAUNCH_CHECK();
+  GemmProblem g;
+  memset(&g, 0, sizeof(g));
+  g.M = M; g.N = N; g.nseg = 1; g.ndir = 1;
+  g.seg[0][0] = GemmSeg{Ao, Bo, ld, ld, K, 1, pa, pb};
+  TcLaunch L;
+  if (int rc = tc_make_launch<PREC>(g, &L)) return rc;
+  RE2NN_CUDA((launch_tc_gemm<PREC>(g, EpiStore{C, N, nullptr}, &L, st)));
+  return 0;
+}
 
 extern "C" {
 
@@ -244,6 +276,30 @@ int re2nn_decompose_recurrence(const re2nn_recurrence_args* a, void* stream) {
       return run_recurrence<RE2NN_PREC_TF32X3>(*a, st);
     default: return set_error("decompose_recurrence: unknown precision %d", a->precision);
   }
+}
+
+size_t re2nn_gemm_nt_workspace(int precision, int M, int N, int K) {
+  if (precision == RE2NN_PREC_FP32) return 256;
+  return operand_bytes(precision, M, K) + operand_bytes(precision, N, K) + 256;
+}
+
+int re2nn_gemm_nt(int precision, const float* A, const float* B, int M, int N, int K, float* C, void* ws,
+                  size_t ws_bytes, void* stream) {
+  RE2NN_CHECK(A && B && C && M > 0 && N > 0 && K > 0, "gemm_nt: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == RE2NN_PREC_FP32) {
+    GemmProblem g;
+    memset(&g, 0, sizeof(g));
+    g.M = M; g.N = N; g.nseg = 1; g.ndir = 1;
+    g.seg[0][0] = GemmSeg{A, B, K, K, K, 1, 0, 0};
+    RE2NN_CUDA(launch_simt_gemm(g, EpiStore{C, N, nullptr}, ALoadPlain{}, st));
+    return 0;
+  }
+  RE2NN_CHECK(re2nn_has_tcgen05(), "gemm_nt: tcgen05 path needs an sm_100 device");
+  RE2NN_CHECK(ws && ws_bytes >= re2nn_gemm_nt_workspace(precision, M, N, K), "gemm_nt: workspace too small");
+  if (precision == RE2NN_PREC_BF16) return gemm_nt_tc<RE2NN_PREC_BF16>(A, B, M, N, K, C, ws, st);
+  if (precision == RE2NN_PREC_TF32X3) return gemm_nt_tc<RE2NN_PREC_TF32X3>(A, B, M, N, K, C, ws, st);
+  return set_error("gemm_nt: unknown precision %d", precision);
 }
 
 int re2nn_token_table(const float* V_embed, const float* E, const float* G, const float* beta_vec, int rows, int D,

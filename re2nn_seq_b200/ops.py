@@ -230,3 +230,20 @@ def profile_read():
     cnt = (C.c_int64 * 3)()
     check(fn['re2nn_profile_read'](ms, cnt), 'profile_read')
     return list(ms), list(cnt)
+
+
+def has_tcgen05():
+    return bool(fn['re2nn_has_tcgen05']())
+
+
+def gemm_nt(A, B, precision='fp32'):
+    """C = A @ B^T through the selected step-GEMM mainloop (test / calibration entry)."""
+    M, K = A.shape
+    N = B.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    need = fn['re2nn_gemm_nt_workspace'](PREC[precision], M, N, K)
+    ws = torch.empty((need,), dtype=torch.uint8, device=A.device)
+    check(fn['re2nn_gemm_nt'](PREC[precision], _f32(A), _f32(B), M, N, K, _f32(out), C.c_void_p(ws.data_ptr()), need,
+                              _stream()), 'gemm_nt')
+    _count(1 if precision == 'fp32' else 3)
+    return out
