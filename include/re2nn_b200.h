@@ -151,12 +151,13 @@ int re2nn_onehot_recurrence(const re2nn_onehot_args* a, void* stream);
  * replaces get_final_score + its L-step loop (model_decompose_single.py:202-205,263-269;
  * model_onehot.py:346-349,417-426).  Optional PriorityLayer (priority.py:20-30) is applied when
  * priority_mat != NULL: scores <- scores @ priority_mat + priority_bias.  Rows past the length are
- * written as 0. */
+ * written as 0.  ws: re2nn_label_scores_workspace() bytes. */
+size_t re2nn_label_scores_workspace(int B, int L, int S, int C, int precision, int has_priority);
 int re2nn_label_scores(const float* alpha, const float* beta, const int64_t* lengths,
                        int B, int L, int S, const float* C_mat, int C,
                        const float* priority_mat, const float* priority_bias, int full_pad,
-                       float* scores /* B x L x C */, float* ws /* B*L*C floats if priority */,
-                       void* stream);
+                       int precision /* RE2NN_PREC_*: fp32 = CUDA cores, else tcgen05 */,
+                       float* scores /* B x L x C */, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- argmax decode --------------------------------------------------------------------------------
  * replaces decode()'s non-CRF branch / local_decode / forward_RE (model_decompose.py:363-369,

@@ -66,7 +66,9 @@ SYMBOLS = {
     're2nn_decompose_recurrence_workspace': (sz, [C.POINTER(RecurrenceArgs)]),
     're2nn_decompose_recurrence': (C.c_int, [C.POINTER(RecurrenceArgs), vp]),
     're2nn_onehot_recurrence': (C.c_int, [C.POINTER(OnehotArgs), vp]),
-    're2nn_label_scores': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp]),
+    're2nn_label_scores_workspace': (sz, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    're2nn_label_scores': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, sz,
+                                     vp]),
     're2nn_argmax_decode': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, i64, vp, vp, vp]),
     're2nn_crf_viterbi': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, i64, vp, vp, vp, vp]),
     're2nn_crf_nll': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),

@@ -39,7 +39,8 @@ class _DecomposeScores(torch.autograd.Function):
     @staticmethod
     def forward(ctx, consts, names, pr, x, dense_v, lengths, L, cache, *tensors):
         p = {n: t.detach().contiguous() for n, t in zip(names, tensors)}
-        need_grad = any(ctx.needs_input_grad[8:]) or (dense_v is not None and ctx.needs_input_grad[4])
+        need_grad = consts['grad_on'] and (any(ctx.needs_input_grad[8:]) or
+                                           (dense_v is not None and ctx.needs_input_grad[4]))
         vtab, gtab, o = _prepare(consts, p, dense_v, None if need_grad else cache)
         Lpad = x.shape[1] if dense_v is None else dense_v.shape[1]
         alpha, beta, zs, rs = ops.decompose_recurrence(
@@ -48,7 +49,8 @@ class _DecomposeScores(torch.autograd.Function):
             precision=consts['precision'], v_mode=V_TOKEN if dense_v is None else V_DENSE,
             full_pad=consts['full_pad'], save_for_backward=need_grad, Lpad=Lpad)
         pm, pb = (pr if consts['use_priority'] else (None, None))
-        scores = ops.label_scores(alpha, beta, lengths, p['C_output_mat'], pm, pb, full_pad=consts['full_pad'])
+        scores = ops.label_scores(alpha, beta, lengths, p['C_output_mat'], pm, pb, full_pad=consts['full_pad'],
+                                  precision=consts['precision'])
         if need_grad:
             ctx.consts, ctx.names, ctx.pr, ctx.L = consts, names, pr, L
             ctx.saved = (p, x, dense_v, lengths, vtab, gtab, o, alpha, beta, zs, rs)
@@ -66,6 +68,7 @@ class _DecomposeScores(torch.autograd.Function):
 
 
 def decompose_scores(consts, names, tensors, pr, x, dense_v, lengths, L, cache=None):
+    consts = dict(consts, grad_on=torch.is_grad_enabled())     # Function.forward itself always runs under no_grad
     return _DecomposeScores.apply(consts, names, pr, x, dense_v, lengths, L, cache, *tensors)
 
 
@@ -91,7 +94,7 @@ def ce_loss(scores, lengths, labels, n_total):
 class _OnehotScores(torch.autograd.Function):
     @staticmethod
     def forward(ctx, consts, pr, x, lengths, L, h0, hT, language, W, output_mat, out_wild):
-        need_grad = any(ctx.needs_input_grad[5:])
+        need_grad = consts['grad_on'] and any(ctx.needs_input_grad[5:])
         o = ops.output_vector_sum(output_mat, None if consts['ce1'] else out_wild)
         alpha, beta = ops.onehot_recurrence(x, lengths, L, language, W, o, h0, hT, consts['update_nonlinear'],
                                             consts['max_semiring'], consts['full_pad'])
@@ -111,4 +114,5 @@ class _OnehotScores(torch.autograd.Function):
 
 def onehot_scores(consts, tensors, pr, x, lengths, L):
     t = [v.detach() if not v.requires_grad else v for v in tensors]
+    consts = dict(consts, grad_on=torch.is_grad_enabled())
     return _OnehotScores.apply(consts, pr, x, lengths, L, *t)

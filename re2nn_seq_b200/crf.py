@@ -11,8 +11,8 @@ STOP_TAG = -1
 
 class _CrfNll(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feats, transitions, lengths, tags):
-        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+    def forward(ctx, feats, transitions, lengths, tags, grad_on):
+        need = grad_on and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         loss, _, part = ops.crf_nll(feats, transitions, lengths, tags, save=need)
         if need:
             ctx.save_for_backward(feats, transitions, lengths, tags, part)
@@ -22,7 +22,7 @@ class _CrfNll(torch.autograd.Function):
     def backward(ctx, g):
         feats, transitions, lengths, tags, part = ctx.saved_tensors
         dfeats, dtrans = ops.crf_nll_backward(feats, transitions, lengths, tags, part, g.contiguous().float())
-        return dfeats, dtrans, None, None
+        return dfeats, dtrans, None, None, None
 
 
 class CRF(nn.Module):
@@ -53,7 +53,7 @@ class CRF(nn.Module):
         dev = feats.device
         lengths = (self._lengths(mask) if lengths is None else lengths).to(dev).contiguous()
         tags = tags.to(dev).contiguous()
-        return _CrfNll.apply(feats, self.transitions, lengths, tags)
+        return _CrfNll.apply(feats, self.transitions, lengths, tags, torch.is_grad_enabled())
 
     def _viterbi_decode(self, feats, mask, lengths=None):
         assert feats.size(2) == self.tagset_size + 2          # crf.py:114

@@ -52,6 +52,28 @@ __device__ __forceinline__ float nl_grad_from_out(float y, int kind) {
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
+// hardware approximations (MUFU): ~2^-11 relative error, used only where operands are bf16 anyway
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <bool FAST>
+__device__ __forceinline__ float apply_nl_t(float x, int kind) {
+  if (!FAST) return apply_nl(x, kind);
+  switch (kind) {
+    case RE2NN_NL_RELU: return fmaxf(x, 0.f);
+    case RE2NN_NL_TANH: return tanh_fast(x);
+    case RE2NN_NL_RELUTANH: return tanh_fast(fmaxf(x, 0.f));
+    case RE2NN_NL_SIGMOID: return 0.5f * tanh_fast(0.5f * x) + 0.5f;
+    default: return x;
+  }
+}
+template <bool FAST>
+__device__ __forceinline__ float sigmoid_t(float x) {
+  return FAST ? 0.5f * tanh_fast(0.5f * x) + 0.5f : sigmoidf_(x);
+}
+
 // ---- step <-> position mapping ----------------------------------------------------------------
 // The reference runs the backward direction on reverse(input, lengths) and un-reverses the states
 // afterwards (model_decompose_single.py:222,257-261).  We keep its step order but address tokens

@@ -107,74 +107,100 @@ __device__ __forceinline__ bool tile_alive(const StepParams& p, int z, int m0, i
   return __syncthreads_or(a) != 0;
 }
 
+// Every epilogue functor is split so the mainloops can (a) hoist per-column constants, (b) put all of a
+// tile's dependent global loads in flight at once (on the tcgen05 path before the accumulator is ready):
+//   Col  col(z, n)                              per-column constants (o[n], bias[n], ...)
+//   Pre  prefetch(row, z, m, n)                 loads only
+//   void apply(col, row, z, m, n, acc, pre)     arithmetic + stores
+// Index math is 32-bit wherever the host guarantees rows*ld < 2^31 (checked in run_recurrence).
+struct Pre { float a, b; };
+struct Col { float a, b; };
+
 // E1: Q = (Hbar @ S1|S2) * v_t            (model_decompose_single.py:170-171 / 175-176)
 template <int PREC> struct EpiQ {
   StepParams p;
   __device__ __forceinline__ bool tile_alive(int z, int m0, int rows) const { return re2nn::tile_alive(p, z, m0, rows); }
   __device__ __forceinline__ RowCtx row(int z, int m) const { return make_row(p, z, m); }
-  __device__ __forceinline__ void apply(const RowCtx& r, int z, int m, int n, float acc) const {
-    float v = __ldg(p.vtab + (size_t)r.vrow * p.R + n);
-    OperandFmt<PREC>::store(p.Q[z], (size_t)m * p.ldq + n, p.q_plane, acc * v);
+  __device__ __forceinline__ Col col(int, int) const { return Col{0.f, 0.f}; }
+  __device__ __forceinline__ Pre prefetch(const RowCtx& r, int, int, int n) const {
+    return Pre{__ldg(p.vtab + (size_t)r.vrow * p.R + n), 0.f};
+  }
+  __device__ __forceinline__ void apply(const Col&, const RowCtx&, int z, int m, int n, float acc, const Pre& pre) const {
+    OperandFmt<PREC>::store(p.Q[z], (uint32_t)m * (uint32_t)p.ldq + (uint32_t)n, p.q_plane, acc * pre.a);
   }
 };
 
 // E2: h_next = phi((Q @ S2^T + Hbar @ W) [* o]) ; gate blend ; write alpha/beta + next operands
 // (model_decompose_single.py:172-173,177-199)
 template <int PREC> struct EpiH {
+  static constexpr bool kFast = PREC == RE2NN_PREC_BF16;
   StepParams p;
   __device__ __forceinline__ bool tile_alive(int z, int m0, int rows) const { return re2nn::tile_alive(p, z, m0, rows); }
   __device__ __forceinline__ RowCtx row(int z, int m) const { return make_row(p, z, m); }
-  __device__ __forceinline__ void apply(const RowCtx& r, int z, int m, int n, float acc) const {
-    const float on = __ldg(p.o + n);
-    float hn = z == 0 ? acc * on : acc;
-    hn = apply_nl(hn, p.nl);
-    float hnew = hn;
-    const size_t si = (size_t)m * p.S + n;
+  __device__ __forceinline__ Col col(int, int n) const { return Col{__ldg(p.o + n), 0.f}; }
+  __device__ __forceinline__ Pre prefetch(const RowCtx&, int z, int m, int n) const {
     if (p.farnn >= 1) {
-      float zt = p.Z[z][si];
-      float hp = p.H[z][si];
-      hnew = (1.f - zt) * hp + zt * hn;
-      p.H[z][si] = hnew;
-      OperandFmt<PREC>::store(p.Hst[z], (size_t)m * p.ldh + n, p.h_plane, hnew);
+      const uint32_t si = (uint32_t)m * (uint32_t)p.S + (uint32_t)n;
+      return Pre{p.Z[z][si], p.H[z][si]};
     }
-    if (p.farnn <= 1) {
-      OperandFmt<PREC>::store(p.Hbar_next[z], (size_t)m * p.ldh + n, p.h_plane, z == 1 ? hnew * on : hnew);
+    return Pre{0.f, 0.f};
+  }
+  __device__ __forceinline__ void apply(const Col& c, const RowCtx& r, int z, int m, int n, float acc, const Pre& pre) const {
+    float hn = z == 0 ? acc * c.a : acc;
+    hn = apply_nl_t<kFast>(hn, p.nl);
+    float hnew = hn;
+    const uint32_t hi = (uint32_t)m * (uint32_t)p.ldh + (uint32_t)n;
+    if (p.farnn >= 1) {
+      hnew = (1.f - pre.a) * pre.b + pre.a * hn;
+      p.H[z][(uint32_t)m * (uint32_t)p.S + (uint32_t)n] = hnew;
+      OperandFmt<PREC>::store(p.Hst[z], hi, p.h_plane, hnew);
     }
-    if (r.orow >= 0) p.out[z][((size_t)m * p.L + r.orow) * p.S + n] = hnew;
+    if (p.farnn <= 1) OperandFmt<PREC>::store(p.Hbar_next[z], hi, p.h_plane, z == 1 ? hnew * c.a : hnew);
+    if (r.orow >= 0) p.out[z][(size_t)((uint32_t)m * (uint32_t)p.L + (uint32_t)r.orow) * p.S + n] = hnew;
   }
 };
 
 // EG: zt / rt gates and the reset-blended operand (model_decompose_single.py:147-157)
 // columns [0,S) = update gate pre-activation, [S,2S) = reset gate pre-activation (farnn==2)
 template <int PREC> struct EpiGate {
+  static constexpr bool kFast = PREC == RE2NN_PREC_BF16;
   StepParams p;
   __device__ __forceinline__ bool tile_alive(int z, int m0, int rows) const { return re2nn::tile_alive(p, z, m0, rows); }
   __device__ __forceinline__ RowCtx row(int z, int m) const { return make_row(p, z, m); }
-  __device__ __forceinline__ void apply(const RowCtx& r, int z, int m, int n, float acc) const {
-    float pre = acc + __ldg(p.gtab + (size_t)r.vrow * p.ldg + n);
-    float g = sigmoidf_(pre * p.sig_k);
+  __device__ __forceinline__ Col col(int z, int n) const {
+    if (n < p.S) return Col{0.f, 0.f};
+    return Col{__ldg(p.hinit[z] + (n - p.S)), __ldg(p.o + (n - p.S))};
+  }
+  __device__ __forceinline__ Pre prefetch(const RowCtx& r, int z, int m, int n) const {
+    Pre q{__ldg(p.gtab + (size_t)r.vrow * p.ldg + n), 0.f};
+    if (n >= p.S) q.b = p.H[z][(uint32_t)m * (uint32_t)p.S + (uint32_t)(n - p.S)];
+    return q;
+  }
+  __device__ __forceinline__ void apply(const Col& c, const RowCtx&, int z, int m, int n, float acc, const Pre& pre) const {
+    float g = sigmoid_t<kFast>((acc + pre.a) * p.sig_k);
     if (n < p.S) {
-      p.Z[z][(size_t)m * p.S + n] = g;
+      p.Z[z][(uint32_t)m * (uint32_t)p.S + (uint32_t)n] = g;
     } else {
-      int s = n - p.S;
-      size_t si = (size_t)m * p.S + s;
-      float hb = (1.f - g) * __ldg(p.hinit[z] + s) + g * p.H[z][si];
-      if (z == 1) hb *= __ldg(p.o + s);
-      OperandFmt<PREC>::store(p.Hbar_cur[z], (size_t)m * p.ldh + s, p.h_plane, hb);
-      if (p.Rg[z]) p.Rg[z][si] = g;
+      const int s = n - p.S;
+      float hb = (1.f - g) * c.a + g * pre.b;
+      if (z == 1) hb *= c.b;
+      OperandFmt<PREC>::store(p.Hbar_cur[z], (uint32_t)m * (uint32_t)p.ldh + (uint32_t)s, p.h_plane, hb);
+      if (p.Rg[z]) p.Rg[z][(uint32_t)m * (uint32_t)p.S + (uint32_t)s] = g;
     }
   }
 };
 
-// plain store epilogue (token table, gate table, generic C = A*B [+ bias] [phi]); used off the step loop
+// plain store epilogue (gate table, label scores, generic C = A*B [+ bias]); used off the step loop
 struct EpiStore {
   float* C;
   int ldc;
   const float* bias;      // per-column or NULL
   __device__ __forceinline__ bool tile_alive(int, int, int) const { return true; }
   __device__ __forceinline__ RowCtx row(int, int) const { return RowCtx{0, 0, true}; }
-  __device__ __forceinline__ void apply(const RowCtx&, int, int m, int n, float acc) const {
-    C[(size_t)m * ldc + n] = bias ? acc + __ldg(bias + n) : acc;
+  __device__ __forceinline__ Col col(int, int n) const { return Col{bias ? __ldg(bias + n) : 0.f, 0.f}; }
+  __device__ __forceinline__ Pre prefetch(const RowCtx&, int, int, int) const { return Pre{0.f, 0.f}; }
+  __device__ __forceinline__ void apply(const Col& c, const RowCtx&, int, int m, int n, float acc, const Pre&) const {
+    C[(size_t)m * ldc + n] = acc + c.a;
   }
 };
 
@@ -186,10 +212,13 @@ struct EpiTokenTable {
   int R, nl;
   __device__ __forceinline__ bool tile_alive(int, int, int) const { return true; }
   __device__ __forceinline__ RowCtx row(int, int) const { return RowCtx{0, 0, true}; }
-  __device__ __forceinline__ void apply(const RowCtx&, int, int m, int n, float acc) const {
-    float b = __ldg(beta_vec + n);
+  __device__ __forceinline__ Col col(int, int n) const { return Col{__ldg(beta_vec + n), 0.f}; }
+  __device__ __forceinline__ Pre prefetch(const RowCtx&, int, int m, int n) const {
+    return Pre{__ldg(V_embed + (size_t)m * R + n), 0.f};
+  }
+  __device__ __forceinline__ void apply(const Col& c, const RowCtx&, int, int m, int n, float acc, const Pre& pre) const {
     float g = apply_nl(acc, nl);
-    table[(size_t)m * R + n] = __ldg(V_embed + (size_t)m * R + n) * b + g * (1.f - b);
+    table[(size_t)m * R + n] = pre.a * c.a + g * (1.f - c.a);
   }
 };
 

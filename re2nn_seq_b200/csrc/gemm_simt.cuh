@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const GemmProblem prob, 
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       const int n = n0 + tx * TN + j;
-      if (n < N) epi.apply(r, z, m, n, acc[i][j]);
+      if (n < N) epi.apply(epi.col(z, n), r, z, m, n, acc[i][j], epi.prefetch(r, z, m, n));
     }
   }
 }

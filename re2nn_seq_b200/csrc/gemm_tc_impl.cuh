@@ -65,7 +65,7 @@ inline int make_operand_map(CUtensorMap* m, const void* base, size_t elem_off, i
 inline int tc_pick_bn(int M, int N, int ndir) {
   const long mt = (long)cdiv(M, 128) * ndir;
   if (mt * cdiv(N, 256) >= 148 && N >= 192) return 256;
-  if (mt * cdiv(N, 128) >= 296 && N >= 96) return 128;
+  if (N > 64 && mt * cdiv(N, 128) >= 148) return 128;
   return 64;
 }
 
@@ -181,13 +181,14 @@ template <int BN> struct TcCfg {
   static constexpr int kABytes = 128 * 128;
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 128 /*barriers*/ + 2048 /*row ctx*/;
 };
 
-constexpr int kTcThreads = 192;
+constexpr int kTcEpiWarps = 8;                       // two warps per TMEM lane quarter
+constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;
 
 template <int PREC, int BN, class Epi>
-__global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(const __grid_constant__ TcLaunch L, const Epi epi) {
+__global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_constant__ TcLaunch L, const Epi epi) {
   using Cfg = TcCfg<BN>;
   constexpr bool TF32 = PREC == RE2NN_PREC_TF32X3;
   const int z = blockIdx.z;
@@ -270,26 +271,60 @@ __global__ void __launch_bounds__(kTcThreads) tc_gemm_kernel(const __grid_consta
       tc_commit(tmem_full);           // accumulator complete
     }
   } else {
-    // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
-    const int q = warp & 3;
-    const int m = m0 + q * 32 + lane;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const bool row_ok = m < L.M;
-    RowCtx rc{0, -1, false};
-    if (row_ok) rc = epi.row(z, m);
+    // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31.  tcgen05.ld hands lane i the 32 columns of
+    // row i; a 32x33 shared-memory transpose turns that into "lane = column" so that every global access
+    // of the epilogue functor is a full contiguous row segment (128 B fp32 / 64 B bf16 per warp request).
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int ew = warp - 2;                // epilogue warp index 0..7
+    const int half = ew >> 2;               // which interleaved set of 32-column chunks this warp takes
+    const int mrow0 = m0 + q * 32;
+    // all pipeline stages are drained once tmem_full fires: stage memory doubles as the transpose buffer;
+    // the row contexts live behind the barriers (never touched by TMA)
+    float* tbuf = reinterpret_cast<float*>(gen_base) + ew * (32 * 33);
+    int* ctx = reinterpret_cast<int*>(gen_base + Cfg::kStages * Cfg::kStageBytes + 128) + ew * 64;   // [vrow x32 | orow x32]
+    {
+      RowCtx mine{0, -1, false};
+      if (mrow0 + lane < L.M) mine = epi.row(z, mrow0 + lane);
+      ctx[lane] = mine.vrow;
+      ctx[32 + lane] = mine.orow;
+    }
+    __syncwarp();
+    const int nrows = min(32, L.M - mrow0);
+    bool acc_ready = false;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = half * 32; c0 < BN; c0 += 32 * (kTcEpiWarps / 4)) {
       if (n0 + c0 >= L.N) break;     // warp-uniform
+      const int n = n0 + c0 + lane;
+      const bool col_ok = n < L.N;
+      const Col cc = col_ok ? epi.col(z, n) : Col{0.f, 0.f};
+      // phase 1: every dependent global load of this 32x32 block in flight at once
+      Pre pre[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        pre[i] = Pre{0.f, 0.f};
+        if (col_ok && i < nrows) pre[i] = epi.prefetch(RowCtx{ctx[i], ctx[32 + i], true}, z, mrow0 + i, n);
+      }
+      if (!acc_ready) {
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        acc_ready = true;
+      }
       uint32_t r[32];
       tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      if (row_ok) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + c0 + j;
-          if (n < L.N) epi.apply(rc, z, m, n, __uint_as_float(r[j]));
-        }
+      for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
+      __syncwarp();
+      // phase 2: lane = column, loop over rows: every store is a contiguous row segment
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (col_ok && i < nrows)
+          epi.apply(cc, RowCtx{ctx[i], ctx[32 + i], true}, z, mrow0 + i, n, tbuf[i * 33 + lane], pre[i]);
       }
+      __syncwarp();
+    }
+    if (!acc_ready) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
     }
     tc_fence_before();
   }

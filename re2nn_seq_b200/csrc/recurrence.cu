@@ -2,6 +2,7 @@
 // Reference: /root/reference/src_seq/farnn/model_decompose_single.py:138-269, model_decompose.py:222-241.
 #include <stdarg.h>
 
+#include <algorithm>
 #include <memory>
 #include <mutex>
 #include <vector>
@@ -121,6 +122,8 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
   RE2NN_CHECK(a.ws && a.ws_bytes >= need, "decompose_recurrence: workspace too small (%zu < %zu)", a.ws_bytes, need);
   const int B = a.B, S = a.S, R = a.R, L = a.L;
   const int ldh = operand_ld(PREC, S), ldq = operand_ld(PREC, R);
+  RE2NN_CHECK((size_t)B * (size_t)std::max(ldh, ldq) < ((size_t)1 << 31) && (size_t)B * L < ((size_t)1 << 31),
+              "decompose_recurrence: batch too large for 32-bit row indexing (B=%d)", B);
   const size_t h_plane = (size_t)B * ldh, q_plane = (size_t)B * ldq;
 
   if (int rc = weight_prep_run<PREC>(a, w.wp, st)) return rc;
@@ -196,6 +199,48 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
 using namespace re2nn;
 
 extern "C" int re2nn_has_tcgen05(void);
+
+// (alpha * beta) in operand format for the tcgen05 score GEMM; rows past the length are zero
+template <int PREC>
+__global__ void ab_operand_kernel(const float* __restrict__ alpha, const float* __restrict__ beta,
+                                  const int64_t* __restrict__ len, int B, int L, int S, int ld, int full_pad,
+                                  void* __restrict__ dst, size_t plane) {
+  const size_t total = (size_t)B * L * ld;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t m = i / ld;
+    const int s = (int)(i - m * ld);
+    const int b = (int)(m / L), t = (int)(m - (size_t)b * L);
+    float v = 0.f;
+    if (s < S && (full_pad || t < (int)len[b])) v = __ldg(alpha + m * S + s) * __ldg(beta + m * S + s);
+    OperandFmt<PREC>::store(dst, i, plane, v);
+  }
+}
+
+template <int PREC>
+static int label_scores_tc(const float* alpha, const float* beta, const int64_t* lengths, int B, int L, int S,
+                           const float* C_mat, int C, int full_pad, float* out, char* ws, cudaStream_t st) {
+  const int ld = operand_ld(PREC, S);
+  const size_t M = (size_t)B * L;
+  void* Aop = ws;
+  void* Bop = ws + operand_bytes(PREC, M, S);
+  const size_t pa = M * ld, pb = (size_t)C * ld;
+  {
+    size_t total = M * ld;
+    int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 32);
+    ab_operand_kernel<PREC><<<blocks, 256, 0, st>>>(alpha, beta, lengths, B, L, S, ld, full_pad, Aop, pa);
+    RE2NN_LAUNCH_CHECK();
+    convert_weight_kernel<PREC><<<(unsigned)(((size_t)C * ld + 255) / 256), 256, 0, st>>>(C_mat, C, S, S, 0, Bop, ld, pb, 0);
+    RE2NN_LAUNCH_CHECK();
+  }
+  GemmProblem g;
+  memset(&g, 0, sizeof(g));
+  g.M = (int)M; g.N = C; g.nseg = 1; g.ndir = 1;
+  g.seg[0][0] = GemmSeg{Aop, Bop, ld, ld, S, 1, pa, pb};
+  TcLaunch Lc;
+  if (int rc = tc_make_launch<PREC>(g, &Lc)) return rc;
+  RE2NN_CUDA((launch_tc_gemm<PREC>(g, EpiStore{out, C, nullptr}, &Lc, st)));
+  return 0;
+}
 
 template <int PREC>
 static int gemm_nt_tc(const float* A, const float* B, int M, int N, int K, float* C, void* ws, cudaStream_t st) {
@@ -331,24 +376,45 @@ int re2nn_gate_table(const float* vtab, int rows, int R, int S, int farnn, const
   return 0;
 }
 
+size_t re2nn_label_scores_workspace(int B, int L, int S, int C, int precision, int has_priority) {
+  size_t need = 256;
+  if (has_priority) need += align_up((size_t)B * L * C * 4, 256);
+  if (precision != RE2NN_PREC_FP32) need += operand_bytes(precision, (size_t)B * L, S) + operand_bytes(precision, C, S);
+  return need;
+}
+
 int re2nn_label_scores(const float* alpha, const float* beta, const int64_t* lengths, int B, int L, int S,
                        const float* C_mat, int C, const float* priority_mat, const float* priority_bias, int full_pad,
-                       float* scores, float* ws, void* stream) {
+                       int precision, float* scores, void* ws, size_t ws_bytes, void* stream) {
   RE2NN_CHECK(alpha && beta && lengths && C_mat && scores, "label_scores: null tensor");
-  RE2NN_CHECK(!priority_mat || ws, "label_scores: priority needs a B*L*C workspace");
+  const size_t need = re2nn_label_scores_workspace(B, L, S, C, precision, priority_mat != nullptr);
+  RE2NN_CHECK(need <= 256 || (ws && ws_bytes >= need), "label_scores: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  GemmProblem g;
-  memset(&g, 0, sizeof(g));
-  g.M = B * L; g.N = C; g.nseg = 1; g.ndir = 1;
-  g.seg[0][0] = GemmSeg{alpha, C_mat, S, S, S, 1, 0, 0};
-  EpiStore e1{priority_mat ? ws : scores, C, nullptr};
-  RE2NN_CUDA(launch_simt_gemm(g, e1, ALoadAlphaBeta{alpha, beta, lengths, L, full_pad}, st));
+  char* wp = (char*)ws;
+  float* raw = scores;
   if (priority_mat) {
+    raw = (float*)wp;
+    wp += align_up((size_t)B * L * C * 4, 256);
+  }
+  if (precision == RE2NN_PREC_FP32) {
+    GemmProblem g;
     memset(&g, 0, sizeof(g));
     g.M = B * L; g.N = C; g.nseg = 1; g.ndir = 1;
-    g.seg[0][0] = GemmSeg{ws, priority_mat, C, C, C, 0, 0, 0};
-    EpiStore e2{scores, C, priority_bias};
-    RE2NN_CUDA(launch_simt_gemm(g, e2, ALoadPlain{}, st));
+    g.seg[0][0] = GemmSeg{alpha, C_mat, S, S, S, 1, 0, 0};
+    RE2NN_CUDA(launch_simt_gemm(g, EpiStore{raw, C, nullptr}, ALoadAlphaBeta{alpha, beta, lengths, L, full_pad}, st));
+  } else {
+    RE2NN_CHECK(re2nn_has_tcgen05(), "label_scores: tcgen05 path needs an sm_100 device");
+    int rc = precision == RE2NN_PREC_BF16
+                 ? label_scores_tc<RE2NN_PREC_BF16>(alpha, beta, lengths, B, L, S, C_mat, C, full_pad, raw, wp, st)
+                 : label_scores_tc<RE2NN_PREC_TF32X3>(alpha, beta, lengths, B, L, S, C_mat, C, full_pad, raw, wp, st);
+    if (rc) return rc;
+  }
+  if (priority_mat) {
+    GemmProblem g;
+    memset(&g, 0, sizeof(g));
+    g.M = B * L; g.N = C; g.nseg = 1; g.ndir = 1;
+    g.seg[0][0] = GemmSeg{raw, priority_mat, C, C, C, 0, 0, 0};
+    RE2NN_CUDA(launch_simt_gemm(g, EpiStore{scores, C, priority_bias}, ALoadPlain{}, st));
   }
   return 0;
 }

@@ -95,8 +95,9 @@ def decompose_recurrence(x, lengths, L, vtab, gtab, S1, S2, W, o, h0, hT, Wss1, 
     a.farnn, a.update_nonlinear, a.precision = farnn, NL[update_nonlinear], PREC[precision]
     a.v_mode, a.full_pad, a.save_for_backward = v_mode, int(full_pad), int(save_for_backward)
     a.sigmoid_exponent = float(sigmoid_exponent)
-    alpha = torch.zeros((B, L, S), dtype=torch.float32, device=dev)
-    beta = torch.zeros((B, L, S), dtype=torch.float32, device=dev)
+    # pad rows are never read downstream (label_scores masks them), so no zero-fill is needed
+    alpha = torch.empty((B, L, S), dtype=torch.float32, device=dev)
+    beta = torch.empty((B, L, S), dtype=torch.float32, device=dev)
     zsave = rsave = None
     if save_for_backward and farnn >= 1:
         zsave = torch.empty((2, L, B, S), dtype=torch.float32, device=dev)
@@ -135,17 +136,20 @@ def onehot_recurrence(x, lengths, L, language, W, o, h0, hT, update_nonlinear, m
     return alpha, beta
 
 
-def label_scores(alpha, beta, lengths, C_mat, priority_mat=None, priority_bias=None, full_pad=False):
+def label_scores(alpha, beta, lengths, C_mat, priority_mat=None, priority_bias=None, full_pad=False,
+                 precision='fp32'):
     B, L, S = alpha.shape
     Cn = C_mat.shape[0]
     scores = torch.empty((B, L, Cn), dtype=torch.float32, device=alpha.device)
-    ws = torch.empty((B, L, Cn), dtype=torch.float32, device=alpha.device) if priority_mat is not None else None
+    has_pr = priority_mat is not None
+    need = fn['re2nn_label_scores_workspace'](B, L, S, Cn, PREC[precision], int(has_pr))
+    ws = torch.empty((need,), dtype=torch.uint8, device=alpha.device)
     check(fn['re2nn_label_scores'](_f32(alpha), _f32(beta), _i64(lengths), B, L, S, _f32(C_mat), Cn,
-                                   _f32(priority_mat) if priority_mat is not None else None,
+                                   _f32(priority_mat) if has_pr else None,
                                    _f32(priority_bias) if priority_bias is not None else None,
-                                   int(full_pad), _f32(scores), _f32(ws) if ws is not None else None, _stream()),
-          'label_scores')
-    _count(2 if priority_mat is not None else 1)
+                                   int(full_pad), PREC[precision], _f32(scores), C.c_void_p(ws.data_ptr()), need,
+                                   _stream()), 'label_scores')
+    _count((1 if precision == 'fp32' else 3) + (1 if has_pr else 0))
     return scores
 
 
