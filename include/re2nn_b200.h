@@ -57,6 +57,10 @@ int re2nn_has_tcgen05(void);
  * launch counts per kernel class (0 = gate GEMM, 1 = GEMM1 + Q epilogue, 2 = GEMM2 + state epilogue)
  * and resets the counters. */
 int re2nn_profile_enable(int on);
+/* debug: install (or clear with NULL) a device buffer receiving 8 clock64 stamps per CTA of every
+ * tcgen05 step-GEMM launch (entry, alive-check, setup, MMAs issued, prefetch issued, accumulator ready,
+ * epilogue done, exit); slot = 8 * linear CTA id, overwritten by every launch. */
+int re2nn_debug_set_tc_trace(unsigned long long* device_buf);
 int re2nn_profile_read(double* ms_out_host, int64_t* count_out_host);
 
 /* ---- stand-alone GEMM through the step-GEMM mainloops (unit-test / calibration entry) -------------------

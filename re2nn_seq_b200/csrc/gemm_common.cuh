@@ -79,6 +79,14 @@ struct StepParams {
   float* Z[2];                                    // fp32 update gate B x S (farnn>=1)
   float* Rg[2];                                   // optional save of reset gate
   float* out[2];                                  // alpha / beta : B x L x S
+  int dir;                                        // set by bind(): the direction this CTA works on
+  // Move direction z into slot 0 so the epilogue addresses plain members (registers after inlining)
+  // instead of indexing the constant bank with a run-time z for every element.
+  __device__ __forceinline__ void bind(int z) {
+    dir = z;
+    hinit[0] = hinit[z]; Q[0] = Q[z]; Hbar_next[0] = Hbar_next[z]; Hbar_cur[0] = Hbar_cur[z];
+    Hst[0] = Hst[z]; H[0] = H[z]; Z[0] = Z[z]; Rg[0] = Rg[z]; out[0] = out[z];
+  }
 };
 
 struct RowCtx {
@@ -119,44 +127,49 @@ struct Col { float a, b; };
 // E1: Q = (Hbar @ S1|S2) * v_t            (model_decompose_single.py:170-171 / 175-176)
 template <int PREC> struct EpiQ {
   StepParams p;
+  __device__ __forceinline__ EpiQ for_dir(int z) const { EpiQ e = *this; e.p.bind(z); return e; }
   __device__ __forceinline__ bool tile_alive(int z, int m0, int rows) const { return re2nn::tile_alive(p, z, m0, rows); }
-  __device__ __forceinline__ RowCtx row(int z, int m) const { return make_row(p, z, m); }
-  __device__ __forceinline__ Col col(int, int) const { return Col{0.f, 0.f}; }
-  __device__ __forceinline__ Pre prefetch(const RowCtx& r, int, int, int n) const {
-    return Pre{__ldg(p.vtab + (size_t)r.vrow * p.R + n), 0.f};
+  __device__ __forceinline__ RowCtx row(int m) const { return make_row(p, p.dir, m); }
+  __device__ __forceinline__ Col col(int) const { return Col{0.f, 0.f}; }
+  __device__ __forceinline__ Pre prefetch(const RowCtx& r, int, int n) const {
+    return Pre{__ldg(p.vtab + (size_t)((uint32_t)r.vrow * (uint32_t)p.R + (uint32_t)n)), 0.f};
   }
-  __device__ __forceinline__ void apply(const Col&, const RowCtx&, int z, int m, int n, float acc, const Pre& pre) const {
-    OperandFmt<PREC>::store(p.Q[z], (uint32_t)m * (uint32_t)p.ldq + (uint32_t)n, p.q_plane, acc * pre.a);
+  __device__ __forceinline__ void apply(const Col&, const RowCtx&, int m, int n, float acc, const Pre& pre) const {
+    OperandFmt<PREC>::store(p.Q[0], (uint32_t)m * (uint32_t)p.ldq + (uint32_t)n, p.q_plane, acc * pre.a);
   }
 };
 
 // E2: h_next = phi((Q @ S2^T + Hbar @ W) [* o]) ; gate blend ; write alpha/beta + next operands
-// (model_decompose_single.py:172-173,177-199)
-template <int PREC> struct EpiH {
+// (model_decompose_single.py:172-173,177-199).  NL / FARNN >= 0 fix update_nonlinear / farnn at compile
+// time (the hot configurations), -1 reads them from StepParams.
+template <int PREC, int NL = -1, int FARNN = -1> struct EpiH {
   static constexpr bool kFast = PREC == RE2NN_PREC_BF16;
   StepParams p;
+  __device__ __forceinline__ EpiH for_dir(int z) const { EpiH e = *this; e.p.bind(z); return e; }
   __device__ __forceinline__ bool tile_alive(int z, int m0, int rows) const { return re2nn::tile_alive(p, z, m0, rows); }
-  __device__ __forceinline__ RowCtx row(int z, int m) const { return make_row(p, z, m); }
-  __device__ __forceinline__ Col col(int, int n) const { return Col{__ldg(p.o + n), 0.f}; }
-  __device__ __forceinline__ Pre prefetch(const RowCtx&, int z, int m, int n) const {
-    if (p.farnn >= 1) {
+  __device__ __forceinline__ RowCtx row(int m) const { return make_row(p, p.dir, m); }
+  __device__ __forceinline__ int farnn() const { return FARNN >= 0 ? FARNN : p.farnn; }
+  __device__ __forceinline__ int nl() const { return NL >= 0 ? NL : p.nl; }
+  __device__ __forceinline__ Col col(int n) const { return Col{__ldg(p.o + n), 0.f}; }
+  __device__ __forceinline__ Pre prefetch(const RowCtx&, int m, int n) const {
+    if (farnn() >= 1) {
       const uint32_t si = (uint32_t)m * (uint32_t)p.S + (uint32_t)n;
-      return Pre{p.Z[z][si], p.H[z][si]};
+      return Pre{p.Z[0][si], p.H[0][si]};
     }
     return Pre{0.f, 0.f};
   }
-  __device__ __forceinline__ void apply(const Col& c, const RowCtx& r, int z, int m, int n, float acc, const Pre& pre) const {
-    float hn = z == 0 ? acc * c.a : acc;
-    hn = apply_nl_t<kFast>(hn, p.nl);
+  __device__ __forceinline__ void apply(const Col& c, const RowCtx& r, int m, int n, float acc, const Pre& pre) const {
+    float hn = p.dir == 0 ? acc * c.a : acc;
+    hn = apply_nl_t<kFast>(hn, nl());
     float hnew = hn;
     const uint32_t hi = (uint32_t)m * (uint32_t)p.ldh + (uint32_t)n;
-    if (p.farnn >= 1) {
+    if (farnn() >= 1) {
       hnew = (1.f - pre.a) * pre.b + pre.a * hn;
-      p.H[z][(uint32_t)m * (uint32_t)p.S + (uint32_t)n] = hnew;
-      OperandFmt<PREC>::store(p.Hst[z], hi, p.h_plane, hnew);
+      p.H[0][(uint32_t)m * (uint32_t)p.S + (uint32_t)n] = hnew;
+      OperandFmt<PREC>::store(p.Hst[0], hi, p.h_plane, hnew);
     }
-    if (p.farnn <= 1) OperandFmt<PREC>::store(p.Hbar_next[z], hi, p.h_plane, z == 1 ? hnew * c.a : hnew);
-    if (r.orow >= 0) p.out[z][(size_t)((uint32_t)m * (uint32_t)p.L + (uint32_t)r.orow) * p.S + n] = hnew;
+    if (farnn() <= 1) OperandFmt<PREC>::store(p.Hbar_next[0], hi, p.h_plane, p.dir == 1 ? hnew * c.a : hnew);
+    if (r.orow >= 0) p.out[0][(size_t)((uint32_t)m * (uint32_t)p.L + (uint32_t)r.orow) * (uint32_t)p.S + (uint32_t)n] = hnew;
   }
 };
 
@@ -165,27 +178,28 @@ template <int PREC> struct EpiH {
 template <int PREC> struct EpiGate {
   static constexpr bool kFast = PREC == RE2NN_PREC_BF16;
   StepParams p;
+  __device__ __forceinline__ EpiGate for_dir(int z) const { EpiGate e = *this; e.p.bind(z); return e; }
   __device__ __forceinline__ bool tile_alive(int z, int m0, int rows) const { return re2nn::tile_alive(p, z, m0, rows); }
-  __device__ __forceinline__ RowCtx row(int z, int m) const { return make_row(p, z, m); }
-  __device__ __forceinline__ Col col(int z, int n) const {
+  __device__ __forceinline__ RowCtx row(int m) const { return make_row(p, p.dir, m); }
+  __device__ __forceinline__ Col col(int n) const {
     if (n < p.S) return Col{0.f, 0.f};
-    return Col{__ldg(p.hinit[z] + (n - p.S)), __ldg(p.o + (n - p.S))};
+    return Col{__ldg(p.hinit[0] + (n - p.S)), __ldg(p.o + (n - p.S))};
   }
-  __device__ __forceinline__ Pre prefetch(const RowCtx& r, int z, int m, int n) const {
+  __device__ __forceinline__ Pre prefetch(const RowCtx& r, int m, int n) const {
     Pre q{__ldg(p.gtab + (size_t)r.vrow * p.ldg + n), 0.f};
-    if (n >= p.S) q.b = p.H[z][(uint32_t)m * (uint32_t)p.S + (uint32_t)(n - p.S)];
+    if (n >= p.S) q.b = p.H[0][(uint32_t)m * (uint32_t)p.S + (uint32_t)(n - p.S)];
     return q;
   }
-  __device__ __forceinline__ void apply(const Col& c, const RowCtx&, int z, int m, int n, float acc, const Pre& pre) const {
+  __device__ __forceinline__ void apply(const Col& c, const RowCtx&, int m, int n, float acc, const Pre& pre) const {
     float g = sigmoid_t<kFast>((acc + pre.a) * p.sig_k);
     if (n < p.S) {
-      p.Z[z][(uint32_t)m * (uint32_t)p.S + (uint32_t)n] = g;
+      p.Z[0][(uint32_t)m * (uint32_t)p.S + (uint32_t)n] = g;
     } else {
       const int s = n - p.S;
       float hb = (1.f - g) * c.a + g * pre.b;
-      if (z == 1) hb *= c.b;
-      OperandFmt<PREC>::store(p.Hbar_cur[z], (uint32_t)m * (uint32_t)p.ldh + (uint32_t)s, p.h_plane, hb);
-      if (p.Rg[z]) p.Rg[z][(uint32_t)m * (uint32_t)p.S + (uint32_t)s] = g;
+      if (p.dir == 1) hb *= c.b;
+      OperandFmt<PREC>::store(p.Hbar_cur[0], (uint32_t)m * (uint32_t)p.ldh + (uint32_t)s, p.h_plane, hb);
+      if (p.Rg[0]) p.Rg[0][(uint32_t)m * (uint32_t)p.S + (uint32_t)s] = g;
     }
   }
 };
@@ -195,11 +209,12 @@ struct EpiStore {
   float* C;
   int ldc;
   const float* bias;      // per-column or NULL
+  __device__ __forceinline__ EpiStore for_dir(int) const { return *this; }
   __device__ __forceinline__ bool tile_alive(int, int, int) const { return true; }
-  __device__ __forceinline__ RowCtx row(int, int) const { return RowCtx{0, 0, true}; }
-  __device__ __forceinline__ Col col(int, int n) const { return Col{bias ? __ldg(bias + n) : 0.f, 0.f}; }
-  __device__ __forceinline__ Pre prefetch(const RowCtx&, int, int, int) const { return Pre{0.f, 0.f}; }
-  __device__ __forceinline__ void apply(const Col& c, const RowCtx&, int, int m, int n, float acc, const Pre&) const {
+  __device__ __forceinline__ RowCtx row(int) const { return RowCtx{0, 0, true}; }
+  __device__ __forceinline__ Col col(int n) const { return Col{bias ? __ldg(bias + n) : 0.f, 0.f}; }
+  __device__ __forceinline__ Pre prefetch(const RowCtx&, int, int) const { return Pre{0.f, 0.f}; }
+  __device__ __forceinline__ void apply(const Col& c, const RowCtx&, int m, int n, float acc, const Pre&) const {
     C[(size_t)m * ldc + n] = acc + c.a;
   }
 };
@@ -210,13 +225,14 @@ struct EpiTokenTable {
   const float* V_embed;
   const float* beta_vec;
   int R, nl;
+  __device__ __forceinline__ EpiTokenTable for_dir(int) const { return *this; }
   __device__ __forceinline__ bool tile_alive(int, int, int) const { return true; }
-  __device__ __forceinline__ RowCtx row(int, int) const { return RowCtx{0, 0, true}; }
-  __device__ __forceinline__ Col col(int, int n) const { return Col{__ldg(beta_vec + n), 0.f}; }
-  __device__ __forceinline__ Pre prefetch(const RowCtx&, int, int m, int n) const {
+  __device__ __forceinline__ RowCtx row(int) const { return RowCtx{0, 0, true}; }
+  __device__ __forceinline__ Col col(int n) const { return Col{__ldg(beta_vec + n), 0.f}; }
+  __device__ __forceinline__ Pre prefetch(const RowCtx&, int m, int n) const {
     return Pre{__ldg(V_embed + (size_t)m * R + n), 0.f};
   }
-  __device__ __forceinline__ void apply(const Col& c, const RowCtx&, int, int m, int n, float acc, const Pre& pre) const {
+  __device__ __forceinline__ void apply(const Col& c, const RowCtx&, int m, int n, float acc, const Pre& pre) const {
     float g = apply_nl(acc, nl);
     table[(size_t)m * R + n] = pre.a * c.a + g * (1.f - c.a);
   }

@@ -27,13 +27,14 @@ struct ALoadAlphaBeta {
 };
 
 template <class Epi, class ALoad>
-__global__ void __launch_bounds__(256) simt_gemm_kernel(const GemmProblem prob, const Epi epi, const ALoad aload) {
+__global__ void __launch_bounds__(256) simt_gemm_kernel(const GemmProblem prob, const Epi epi_in, const ALoad aload) {
   constexpr int BM = 128, BN = 64, BK = 16, TM = 8, TN = 4;
   const int z = blockIdx.z;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int M = prob.M, N = prob.N;
   const int rows = min(BM, M - m0);
-  if (!epi.tile_alive(z, m0, rows)) return;
+  if (!epi_in.tile_alive(z, m0, rows)) return;
+  const Epi epi = epi_in.for_dir(z);
 
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
@@ -99,11 +100,11 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const GemmProblem prob, 
   for (int i = 0; i < TM; ++i) {
     const int m = m0 + ty * TM + i;
     if (m >= M) continue;
-    const RowCtx r = epi.row(z, m);
+    const RowCtx r = epi.row(m);
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       const int n = n0 + tx * TN + j;
-      if (n < N) epi.apply(epi.col(z, n), r, z, m, n, acc[i][j], epi.prefetch(r, z, m, n));
+      if (n < N) epi.apply(epi.col(n), r, m, n, acc[i][j], epi.prefetch(r, m, n));
     }
   }
 }

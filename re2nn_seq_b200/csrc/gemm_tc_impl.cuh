@@ -8,6 +8,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <algorithm>
+
 #include "gemm_common.cuh"
 
 #define RE2NN_HAVE_TC 1
@@ -22,6 +24,7 @@ struct __align__(64) TcLaunch {
   CUtensorMap maps[kTcMaxMaps];
   TcSeg seg[2][kTcMaxSeg];
   int nseg, nmaps, M, N, BN, ndir;
+  int bn;   // effective n-tile width (multiple of 16, <= BN): MMA N, TMA box rows of B, grid.y = ceil(N / bn)
 };
 typedef TcLaunch TcStepMaps;
 struct TcRecurrenceMaps { TcLaunch gate, g1[2], g2[2]; };
@@ -62,11 +65,26 @@ inline int make_operand_map(CUtensorMap* m, const void* base, size_t elem_off, i
   return 0;
 }
 
-inline int tc_pick_bn(int M, int N, int ndir) {
+// n-tile width: the step GEMMs are bound by shared-memory ingest (~64 B/clk/SM), so pick the split of N that
+// minimises bytes per SM: waves(m_tiles * nt CTAs over 148 SMs) * (A tile 16 KB + B tile bn * 128 B) per k-block.
+inline void tc_pick_bn(int M, int N, int ndir, int* bn_out, int* BN_out) {
   const long mt = (long)cdiv(M, 128) * ndir;
-  if (mt * cdiv(N, 256) >= 148 && N >= 192) return 256;
-  if (N > 64 && mt * cdiv(N, 128) >= 148) return 128;
-  return 64;
+  double best = 1e30;
+  int best_bn = 64;
+  for (int nt = 1; nt <= cdiv(N, 16); ++nt) {
+    int bn = ((cdiv(N, nt) + 15) / 16) * 16;
+    if (bn > 256) continue;
+    if (nt > 1 && bn * (nt - 1) >= N) continue;            // a narrower split already covers N
+    const int cls = bn <= 64 ? 64 : (bn <= 128 ? 128 : 256);
+    const int per_sm = cls == 256 ? 1 : 2;                  // CTAs resident per SM (smem / registers)
+    const long ctas = mt * nt;
+    const double waves = (double)((ctas + 148L * per_sm - 1) / (148L * per_sm));
+    const double conc = (double)std::min<long>(per_sm, (ctas + 147) / 148);   // CTAs sharing one SM's ingest
+    const double cost = waves * conc * (16384.0 + bn * 128.0) + 2000.0 * waves;
+    if (cost < best - 1e-9) { best = cost; best_bn = bn; }
+  }
+  *bn_out = best_bn;
+  *BN_out = best_bn <= 64 ? 64 : (best_bn <= 128 ? 128 : 256);
 }
 
 // Expand a GemmProblem (operands already in the PREC operand format, all B operands K-major) into maps.
@@ -74,7 +92,7 @@ template <int PREC>
 inline int tc_make_launch(const GemmProblem& g, TcLaunch* out) {
   memset(out, 0, sizeof(*out));
   out->M = g.M; out->N = g.N; out->ndir = g.ndir;
-  out->BN = tc_pick_bn(g.M, g.N, g.ndir);
+  tc_pick_bn(g.M, g.N, g.ndir, &out->bn, &out->BN);
   constexpr int kpb = 128 / OperandFmt<PREC>::kElemBytes;   // K elements per 128-byte block
   int nm = 0;
   for (int z = 0; z < g.ndir; ++z) {
@@ -87,13 +105,13 @@ inline int tc_make_launch(const GemmProblem& g, TcLaunch* out) {
       const int a_hi = nm++;
       if (int rc = make_operand_map<PREC>(&out->maps[a_hi], sg.A, 0, g.M, sg.K, sg.lda, 128)) return rc;
       const int b_hi = nm++;
-      if (int rc = make_operand_map<PREC>(&out->maps[b_hi], sg.B, 0, g.N, sg.K, sg.ldb, out->BN)) return rc;
+      if (int rc = make_operand_map<PREC>(&out->maps[b_hi], sg.B, 0, g.N, sg.K, sg.ldb, out->bn)) return rc;
       out->seg[z][ns++] = TcSeg{a_hi, b_hi, kb};
       if (PREC == RE2NN_PREC_TF32X3) {
         const int a_lo = nm++;
         if (int rc = make_operand_map<PREC>(&out->maps[a_lo], sg.A, sg.a_plane, g.M, sg.K, sg.lda, 128)) return rc;
         const int b_lo = nm++;
-        if (int rc = make_operand_map<PREC>(&out->maps[b_lo], sg.B, sg.b_plane, g.N, sg.K, sg.ldb, out->BN)) return rc;
+        if (int rc = make_operand_map<PREC>(&out->maps[b_lo], sg.B, sg.b_plane, g.N, sg.K, sg.ldb, out->bn)) return rc;
         out->seg[z][ns++] = TcSeg{a_lo, b_hi, kb};
         out->seg[z][ns++] = TcSeg{a_hi, b_lo, kb};
       }
@@ -184,17 +202,28 @@ template <int BN> struct TcCfg {
   static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 128 /*barriers*/ + 2048 /*row ctx*/;
 };
 
+// optional per-CTA phase trace (debug): 8 clock64 stamps per CTA when a buffer is installed
+__device__ unsigned long long* g_tc_trace = nullptr;
+__device__ __forceinline__ void tc_stamp(unsigned long long* t, int slot) {
+  if (t) t[slot] = clock64();
+}
+
 constexpr int kTcEpiWarps = 8;                       // two warps per TMEM lane quarter
 constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;
 
 template <int PREC, int BN, class Epi>
-__global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_constant__ TcLaunch L, const Epi epi) {
+__global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_constant__ TcLaunch L, const Epi epi_in) {
   using Cfg = TcCfg<BN>;
   constexpr bool TF32 = PREC == RE2NN_PREC_TF32X3;
   const int z = blockIdx.z;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+  const int bn = L.bn;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * bn;
   const int rows = min(128, L.M - m0);
-  if (!epi.tile_alive(z, m0, rows)) return;
+  unsigned long long* trace = nullptr;
+  if (g_tc_trace) trace = g_tc_trace + 8ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+  if (threadIdx.x == 0) tc_stamp(trace, 0);
+  if (!epi_in.tile_alive(z, m0, rows)) return;
+  if (threadIdx.x == 0) tc_stamp(trace, 1);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -231,6 +260,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot_p;
+  if (threadIdx.x == 0) tc_stamp(trace, 2);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -245,7 +275,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
           const uint32_t ph = (it / Cfg::kStages) & 1;
           mbar_wait(empty_bar(st), ph ^ 1);
           const uint32_t sa = base + st * Cfg::kStageBytes;
-          mbar_expect_tx(full_bar(st), Cfg::kStageBytes);
+          mbar_expect_tx(full_bar(st), (uint32_t)(Cfg::kABytes + bn * 128));
           tma_load_2d(sa, ma, full_bar(st), kb * kpb, m0);
           tma_load_2d(sa + Cfg::kABytes, mb, full_bar(st), kb * kpb, n0);
         }
@@ -255,7 +285,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
     if (lane == 0) {
       // instruction descriptor: D=f32, A/B = bf16 (1) or tf32 (2), both K-major, N>>3, M>>4
       const uint32_t fmt = TF32 ? 2u : 1u;
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((128u >> 4) << 24);
       for (int it = 0; it < total_kb; ++it) {
         const int st = it % Cfg::kStages;
         const uint32_t ph = (it / Cfg::kStages) & 1;
@@ -269,11 +299,13 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
         tc_commit(empty_bar(st));     // frees the smem slot once these MMAs have read it
       }
       tc_commit(tmem_full);           // accumulator complete
+      tc_stamp(trace, 3);             // all MMAs issued
     }
   } else {
     // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31.  tcgen05.ld hands lane i the 32 columns of
     // row i; a 32x33 shared-memory transpose turns that into "lane = column" so that every global access
     // of the epilogue functor is a full contiguous row segment (128 B fp32 / 64 B bf16 per warp request).
+    const Epi epi = epi_in.for_dir(z);       // direction-bound copy: plain members, no per-element z indexing
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int ew = warp - 2;                // epilogue warp index 0..7
     const int half = ew >> 2;               // which interleaved set of 32-column chunks this warp takes
@@ -284,7 +316,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
     int* ctx = reinterpret_cast<int*>(gen_base + Cfg::kStages * Cfg::kStageBytes + 128) + ew * 64;   // [vrow x32 | orow x32]
     {
       RowCtx mine{0, -1, false};
-      if (mrow0 + lane < L.M) mine = epi.row(z, mrow0 + lane);
+      if (mrow0 + lane < L.M) mine = epi.row(mrow0 + lane);
       ctx[lane] = mine.vrow;
       ctx[32 + lane] = mine.orow;
     }
@@ -292,22 +324,24 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
     const int nrows = min(32, L.M - mrow0);
     bool acc_ready = false;
 #pragma unroll 1
-    for (int c0 = half * 32; c0 < BN; c0 += 32 * (kTcEpiWarps / 4)) {
+    for (int c0 = half * 32; c0 < bn; c0 += 32 * (kTcEpiWarps / 4)) {
       if (n0 + c0 >= L.N) break;     // warp-uniform
       const int n = n0 + c0 + lane;
-      const bool col_ok = n < L.N;
-      const Col cc = col_ok ? epi.col(z, n) : Col{0.f, 0.f};
+      const bool col_ok = n < L.N && c0 + lane < bn;
+      const Col cc = col_ok ? epi.col(n) : Col{0.f, 0.f};
       // phase 1: every dependent global load of this 32x32 block in flight at once
       Pre pre[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         pre[i] = Pre{0.f, 0.f};
-        if (col_ok && i < nrows) pre[i] = epi.prefetch(RowCtx{ctx[i], ctx[32 + i], true}, z, mrow0 + i, n);
+        if (col_ok && i < nrows) pre[i] = epi.prefetch(RowCtx{ctx[i], ctx[32 + i], true}, mrow0 + i, n);
       }
       if (!acc_ready) {
+        if (ew == 0 && lane == 0) tc_stamp(trace, 4);   // first prefetch batch issued
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         acc_ready = true;
+        if (ew == 0 && lane == 0) tc_stamp(trace, 5);   // accumulator ready
       }
       uint32_t r[32];
       tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
@@ -318,7 +352,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         if (col_ok && i < nrows)
-          epi.apply(cc, RowCtx{ctx[i], ctx[32 + i], true}, z, mrow0 + i, n, tbuf[i * 33 + lane], pre[i]);
+          epi.apply(cc, RowCtx{ctx[i], ctx[32 + i], true}, mrow0 + i, n, tbuf[i * 33 + lane], pre[i]);
       }
       __syncwarp();
     }
@@ -327,8 +361,10 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
       tc_fence_after();
     }
     tc_fence_before();
+    if (ew == 0 && lane == 0) tc_stamp(trace, 6);       // epilogue of warp 2 done
   }
   __syncthreads();
+  if (threadIdx.x == 0) tc_stamp(trace, 7);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)BN));
@@ -344,7 +380,7 @@ inline cudaError_t launch_tc_bn(const TcLaunch& L, const Epi& epi, cudaStream_t 
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  dim3 grid(cdiv(L.M, 128), cdiv(L.N, BN), L.ndir);
+  dim3 grid(cdiv(L.M, 128), cdiv(L.N, L.bn), L.ndir);
   tc_gemm_kernel<PREC, BN, Epi><<<grid, kTcThreads, Cfg::kSmem, st>>>(L, epi);
   return cudaGetLastError();
 }

@@ -189,7 +189,19 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
     if (a.farnn >= 1)
       RE2NN_CUDA((launch_gemm<PREC>(0, g_gate, EpiGate<PREC>{p}, tm ? &tm->gate : nullptr, st)));
     RE2NN_CUDA((launch_gemm<PREC>(1, g_1[par], EpiQ<PREC>{p}, tm ? &tm->g1[par] : nullptr, st)));
-    RE2NN_CUDA((launch_gemm<PREC>(2, g_2[par], EpiH<PREC>{p}, tm ? &tm->g2[par] : nullptr, st)));
+    {   // compile-time specialisations of the hot configurations; everything else takes the generic functor
+      const TcStepMaps* m2 = tm ? &tm->g2[par] : nullptr;
+      cudaError_t e;
+      if (a.farnn == 0 && a.update_nonlinear == RE2NN_NL_TANH)
+        e = launch_gemm<PREC>(2, g_2[par], EpiH<PREC, RE2NN_NL_TANH, 0>{p}, m2, st);
+      else if (a.farnn == 0)
+        e = launch_gemm<PREC>(2, g_2[par], EpiH<PREC, -1, 0>{p}, m2, st);
+      else if (a.update_nonlinear == RE2NN_NL_TANH)
+        e = launch_gemm<PREC>(2, g_2[par], EpiH<PREC, RE2NN_NL_TANH, -1>{p}, m2, st);
+      else
+        e = launch_gemm<PREC>(2, g_2[par], EpiH<PREC, -1, -1>{p}, m2, st);
+      RE2NN_CUDA(e);
+    }
   }
   return 0;
 }
@@ -265,6 +277,11 @@ static int gemm_nt_tc(const float* A, const float* B, int M, int N, int K, float
 extern "C" {
 
 int re2nn_abi_version(void) { return RE2NN_ABI_VERSION; }
+
+int re2nn_debug_set_tc_trace(unsigned long long* device_buf) {
+  RE2NN_CUDA(cudaMemcpyToSymbol(g_tc_trace, &device_buf, sizeof(device_buf)));
+  return 0;
+}
 
 int re2nn_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
