@@ -104,7 +104,7 @@ typedef struct re2nn_recurrence_args {
   int32_t precision;           /* RE2NN_PREC_* */
   int32_t v_mode;              /* RE2NN_V_* */
   int32_t full_pad;            /* 1: also compute pad positions exactly like the reference does */
-  int32_t save_for_backward;   /* 1: keep per-step gate values (zt, rt) for re2nn_decompose_backward */
+  int32_t save_for_backward;   /* 1: fill the *_save slabs below for re2nn_decompose_backward (fp32 only) */
   float sigmoid_exponent;
   const int64_t* x;            /* B x Lpad token ids (RE2NN_V_TOKEN) or NULL */
   const int64_t* lengths;      /* B */
@@ -120,14 +120,52 @@ typedef struct re2nn_recurrence_args {
   const float* Wss2;           /* S x S (farnn==2) */
   float* alpha;                /* B x L x S out */
   float* beta;                 /* B x L x S out */
-  float* zsave;                /* 2 x L x B x S (farnn>=1 && save_for_backward) or NULL */
-  float* rsave;                /* 2 x L x B x S (farnn==2 && save_for_backward) or NULL */
+  /* save_for_backward slabs, step-major [direction][step][B][.] fp32, zero for rows that are already finished: */
+  float* hbar_save;            /* 2 x (L+1) x B x S  operand of step k (after reset gate / *o)          */
+  float* hst_save;             /* 2 x (L+1) x B x S  state before step k                               */
+  float* u_save;               /* 2 x L x B x R      hbar @ S1|S2 (before * v_t)                        */
+  float* a_save;               /* 2 x L x B x S      pre-activation before * o / phi                    */
+  float* zsave;                /* 2 x L x B x S      update gate (farnn>=1) or NULL                     */
+  float* rsave;                /* 2 x L x B x S      reset gate (farnn==2) or NULL                      */
   void* ws;                    /* scratch, >= re2nn_decompose_recurrence_workspace() bytes */
   size_t ws_bytes;
 } re2nn_recurrence_args;
 
 size_t re2nn_decompose_recurrence_workspace(const re2nn_recurrence_args* a);
 int re2nn_decompose_recurrence(const re2nn_recurrence_args* a, void* stream);
+
+/* ---- decompose i-FST backward (BPTT through both directions + label scores) ---------------------------
+ * replaces torch.autograd over forward_local (train_decompose.py:192).  Input: d loss / d all_scores.
+ * Outputs: gradients of every parameter the reference trains (NULL pointer = not wanted).
+ * fp32 CUDA-core path; weight gradients are reduced deterministically (split-K partials + ordered sum),
+ * token-table scatter-adds use float atomics. */
+typedef struct re2nn_backward_args {
+  int32_t B, Lpad, L, S, R, C;  /* C = columns of all_scores */
+  int32_t farnn, update_nonlinear, v_mode, full_pad, ce1;
+  int32_t table_rows;           /* rows of vtab (V+1, or B*Lpad in dense mode) */
+  float sigmoid_exponent;
+  const int64_t* x; const int64_t* lengths;
+  const float* dscores;         /* B x L x C */
+  const float* priority_mat;    /* C x C or NULL */
+  /* forward inputs */
+  const float *vtab, *S1, *S2, *W, *o, *h0, *hT, *Wss1, *Wss2, *Wrs1, *Wrs2, *C_mat;
+  /* forward outputs / saves */
+  const float *alpha, *beta, *hbar_save, *hst_save, *u_save, *a_save, *zsave, *rsave;
+  /* gradients (fp32, overwritten) */
+  float *dS1, *dS2, *dW, *dC, *d_o, *dh0, *dhT, *dWss1, *dWss2, *dWrs1, *dWrs2, *dbs1, *dbs2;
+  float* dvtab;                 /* table_rows x R */
+  void* ws; size_t ws_bytes;
+} re2nn_backward_args;
+size_t re2nn_decompose_backward_workspace(const re2nn_backward_args* a);
+int re2nn_decompose_backward(const re2nn_backward_args* a, void* stream);
+
+/* token-table backward: dvtab -> dV_embed (rows x R), dbeta_vec (R), dG (D x R), dE (rows x D); NULL = skip.
+ * (model_decompose.py:222-241 differentiated) */
+size_t re2nn_token_table_backward_workspace(int rows, int D, int R);
+int re2nn_token_table_backward(const float* dvtab, const float* V_embed, const float* E, const float* G,
+                               const float* beta_vec, int rows, int D, int R, int additional_nonlinear,
+                               float* dV_embed, float* dbeta_vec, float* dG, float* dE, void* ws,
+                               size_t ws_bytes, void* stream);
 
 /* ---- onehot i-FST recurrence, both directions ---------------------------------------------------
  * replaces FARNN_S_O_I_S.forward_score's recurrence (farnn/model_onehot.py:358-415):

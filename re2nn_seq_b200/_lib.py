@@ -31,7 +31,24 @@ class RecurrenceArgs(C.Structure):
         ('save_for_backward', i32), ('sigmoid_exponent', f32),
         ('x', vp), ('lengths', vp), ('vtab', vp), ('gtab', vp), ('S1', vp), ('S2', vp), ('W', vp),
         ('o', vp), ('h0', vp), ('hT', vp), ('Wss1', vp), ('Wss2', vp), ('alpha', vp), ('beta', vp),
-        ('zsave', vp), ('rsave', vp), ('ws', vp), ('ws_bytes', sz),
+        ('hbar_save', vp), ('hst_save', vp), ('u_save', vp), ('a_save', vp), ('zsave', vp), ('rsave', vp),
+        ('ws', vp), ('ws_bytes', sz),
+    ]
+
+
+class BackwardArgs(C.Structure):
+    _fields_ = [
+        ('B', i32), ('Lpad', i32), ('L', i32), ('S', i32), ('R', i32), ('C', i32),
+        ('farnn', i32), ('update_nonlinear', i32), ('v_mode', i32), ('full_pad', i32), ('ce1', i32),
+        ('table_rows', i32), ('sigmoid_exponent', f32),
+        ('x', vp), ('lengths', vp), ('dscores', vp), ('priority_mat', vp),
+        ('vtab', vp), ('S1', vp), ('S2', vp), ('W', vp), ('o', vp), ('h0', vp), ('hT', vp), ('Wss1', vp),
+        ('Wss2', vp), ('Wrs1', vp), ('Wrs2', vp), ('C_mat', vp),
+        ('alpha', vp), ('beta', vp), ('hbar_save', vp), ('hst_save', vp), ('u_save', vp), ('a_save', vp),
+        ('zsave', vp), ('rsave', vp),
+        ('dS1', vp), ('dS2', vp), ('dW', vp), ('dC', vp), ('d_o', vp), ('dh0', vp), ('dhT', vp), ('dWss1', vp),
+        ('dWss2', vp), ('dWrs1', vp), ('dWrs2', vp), ('dbs1', vp), ('dbs2', vp), ('dvtab', vp),
+        ('ws', vp), ('ws_bytes', sz),
     ]
 
 
@@ -66,6 +83,10 @@ SYMBOLS = {
     're2nn_output_vector_sum': (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),
     're2nn_decompose_recurrence_workspace': (sz, [C.POINTER(RecurrenceArgs)]),
     're2nn_decompose_recurrence': (C.c_int, [C.POINTER(RecurrenceArgs), vp]),
+    're2nn_decompose_backward_workspace': (sz, [C.POINTER(BackwardArgs)]),
+    're2nn_decompose_backward': (C.c_int, [C.POINTER(BackwardArgs), vp]),
+    're2nn_token_table_backward_workspace': (sz, [C.c_int, C.c_int, C.c_int]),
+    're2nn_token_table_backward': (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, sz, vp]),
     're2nn_onehot_recurrence': (C.c_int, [C.POINTER(OnehotArgs), vp]),
     're2nn_label_scores_workspace': (sz, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     're2nn_label_scores': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, sz,

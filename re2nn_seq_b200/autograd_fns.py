@@ -43,7 +43,7 @@ class _DecomposeScores(torch.autograd.Function):
                                            (dense_v is not None and ctx.needs_input_grad[4]))
         vtab, gtab, o = _prepare(consts, p, dense_v, None if need_grad else cache)
         Lpad = x.shape[1] if dense_v is None else dense_v.shape[1]
-        alpha, beta, zs, rs = ops.decompose_recurrence(
+        alpha, beta, saves = ops.decompose_recurrence(
             x, lengths, L, vtab, gtab, p['S1'], p['S2'], p['wildcard_mat'], o, p['h0'], p['hT'],
             p.get('Wss1'), p.get('Wss2'), consts['farnn'], consts['update_nonlinear'], consts['sigmoid_exponent'],
             precision=consts['precision'], v_mode=V_TOKEN if dense_v is None else V_DENSE,
@@ -53,7 +53,7 @@ class _DecomposeScores(torch.autograd.Function):
                                   precision=consts['precision'])
         if need_grad:
             ctx.consts, ctx.names, ctx.pr, ctx.L = consts, names, pr, L
-            ctx.saved = (p, x, dense_v, lengths, vtab, gtab, o, alpha, beta, zs, rs)
+            ctx.saved = (p, x, dense_v, lengths, vtab, gtab, o, alpha, beta, saves)
         return scores
 
     @staticmethod

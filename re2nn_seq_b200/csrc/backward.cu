@@ -1,0 +1,637 @@
+// Hand-written backward of the decompose i-FST path (fp32): label scores -> BPTT through both
+// recurrences (gates included) -> parameter gradients.  Replaces torch.autograd over
+// FARNN_S_D_W_I_S.forward_local / FARNN_S_SF.forward
+// (/root/reference/src_seq/farnn/model_decompose_single.py:138-269, train_decompose.py:192).
+//
+// Per step k = L-1 .. 0 (both directions in every launch):
+//   E1   G = g + dOut ; gate blend grads ; d pre-activation ; DA[k]                    (elementwise)
+//   GEMM dq  = DA[k] @ S2|S1
+//   E2   DU[k] = dq*v ; Q[k] = u*v ; dvtab[token] += dq*u                               (elementwise)
+//   GEMM dhb = DU[k] @ S1^T|S2^T + DA[k] @ W^T|W
+//   E3   reset-gate grads ; g <- carry + dh~ ; o / h_init products                      (elementwise)
+//   GEMM g  += [dz|dr] @ [Wss1|Wss2]^T                                                  (farnn >= 1)
+// After the sweep every weight gradient is ONE large transposed GEMM over all (step, sequence) rows
+// (K = 2*L*B), reduced deterministically (split-K partials + ordered sum); bias / vector gradients are
+// deterministic column sums of the per-step slabs.
+#include <algorithm>
+
+#include "gemm_simt.cuh"
+
+namespace re2nn {
+
+// ---- epilogues local to the backward ---------------------------------------------------------------------
+struct EpiStore2 {          // C_z = acc (per direction output pointers)
+  float* C[2];
+  int ldc;
+  int accumulate;           // C += acc
+  __device__ __forceinline__ EpiStore2 for_dir(int z) const { EpiStore2 e = *this; e.C[0] = C[z]; return e; }
+  __device__ __forceinline__ bool tile_alive(int, int, int) const { return true; }
+  __device__ __forceinline__ RowCtx row(int) const { return RowCtx{0, 0, true}; }
+  __device__ __forceinline__ Col col(int) const { return Col{0.f, 0.f}; }
+  __device__ __forceinline__ Pre prefetch(const RowCtx&, int m, int n) const {
+    return Pre{accumulate ? C[0][(size_t)m * ldc + n] : 0.f, 0.f};
+  }
+  __device__ __forceinline__ void apply(const Col&, const RowCtx&, int m, int n, float acc, const Pre& pre) const {
+    C[0][(size_t)m * ldc + n] = acc + pre.a;
+  }
+};
+
+// dAB = draw @ C ; dAlpha = dAB * beta ; dBeta = dAB * alpha  (valid rows only)
+struct EpiDAB {
+  const float* alpha; const float* beta; const int64_t* len;
+  float* dalpha; float* dbeta;
+  int L, S, full_pad;
+  __device__ __forceinline__ EpiDAB for_dir(int) const { return *this; }
+  __device__ __forceinline__ bool tile_alive(int, int, int) const { return true; }
+  __device__ __forceinline__ RowCtx row(int m) const {
+    int b = m / L, t = m - b * L;
+    return RowCtx{0, (full_pad || t < (int)len[b]) ? 0 : -1, true};
+  }
+  __device__ __forceinline__ Col col(int) const { return Col{0.f, 0.f}; }
+  __device__ __forceinline__ Pre prefetch(const RowCtx& r, int m, int n) const {
+    if (r.orow < 0) return Pre{0.f, 0.f};
+    size_t i = (size_t)m * S + n;
+    return Pre{alpha[i], beta[i]};
+  }
+  __device__ __forceinline__ void apply(const Col&, const RowCtx& r, int m, int n, float acc, const Pre& pre) const {
+    size_t i = (size_t)m * S + n;
+    dalpha[i] = r.orow < 0 ? 0.f : acc * pre.b;
+    dbeta[i] = r.orow < 0 ? 0.f : acc * pre.a;
+  }
+};
+
+// ---- transposed ("TN") GEMM: C[P x Q] = sum over pairs, rows m:  X[m, p] * Y[m, q]  ---------------------------
+struct TnPair { const float* X; const float* Y; int ldx, ldy; size_t rows; };
+struct TnProblem { int P, Q, npairs; TnPair pair[2]; };
+
+// XLoad hook lets dC form (alpha*beta) on the fly
+struct YLoadPlain {
+  __device__ __forceinline__ float operator()(const TnPair& pr, size_t m, int q) const { return __ldg(pr.Y + m * pr.ldy + q); }
+};
+struct YLoadAlphaBeta {
+  const float* beta; const int64_t* len; int L, full_pad;
+  __device__ __forceinline__ float operator()(const TnPair& pr, size_t m, int q) const {
+    int b = (int)(m / L), t = (int)(m - (size_t)b * L);
+    if (!full_pad && t >= (int)len[b]) return 0.f;
+    return __ldg(pr.Y + m * pr.ldy + q) * __ldg(beta + m * pr.ldy + q);
+  }
+};
+
+constexpr int kTnSplit = 64;
+
+template <class YLoad>
+__global__ void __launch_bounds__(256) tn_gemm_kernel(const TnProblem prob, float* __restrict__ partial, const YLoad yload) {
+  constexpr int BP = 64, BQ = 64, BK = 16;
+  __shared__ __align__(16) float Xs[BK][BP + 4];
+  __shared__ __align__(16) float Ys[BK][BQ + 4];
+  const int p0 = blockIdx.x * BP, q0 = blockIdx.y * BQ, split = blockIdx.z;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int pi = 0; pi < prob.npairs; ++pi) {
+    const TnPair pr = prob.pair[pi];
+    const size_t chunk = (pr.rows + kTnSplit - 1) / kTnSplit;
+    const size_t r0 = chunk * split, r1 = min(pr.rows, r0 + chunk);
+    for (size_t m0 = r0; m0 < r1; m0 += BK) {
+#pragma unroll
+      for (int i = 0; i < (BP * BK) / 256; ++i) {
+        int idx = tid + i * 256;
+        int pp = idx & (BP - 1), kk = idx >> 6;
+        float v = 0.f;
+        if (m0 + kk < r1 && p0 + pp < prob.P) v = __ldg(pr.X + (m0 + kk) * pr.ldx + p0 + pp);
+        Xs[kk][pp] = v;
+      }
+#pragma unroll
+      for (int i = 0; i < (BQ * BK) / 256; ++i) {
+        int idx = tid + i * 256;
+        int qq = idx & (BQ - 1), kk = idx >> 6;
+        float v = 0.f;
+        if (m0 + kk < r1 && q0 + qq < prob.Q) v = yload(pr, m0 + kk, q0 + qq);
+        Ys[kk][qq] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        const float4 a = *reinterpret_cast<const float4*>(&Xs[kk][ty * 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Ys[kk][tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+  float* out = partial + (size_t)split * prob.P * prob.Q;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int pp = p0 + ty * 4 + i;
+    if (pp >= prob.P) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int qq = q0 + tx * 4 + j;
+      if (qq < prob.Q) out[(size_t)pp * prob.Q + qq] = acc[i][j];
+    }
+  }
+}
+
+// out[i] (+)= sum_s partial[s][i]   (ordered => deterministic)
+__global__ void split_reduce_kernel(const float* __restrict__ partial, int nsplit, size_t n, float* __restrict__ out,
+                                    int accumulate) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float acc = accumulate ? out[i] : 0.f;
+    for (int s = 0; s < nsplit; ++s) acc += partial[(size_t)s * n + i];
+    out[i] = acc;
+  }
+}
+
+template <class YLoad>
+static cudaError_t run_tn(const TnProblem& prob, float* partial, float* out, int accumulate, const YLoad& yl, cudaStream_t st) {
+  dim3 grid(cdiv(prob.P, 64), cdiv(prob.Q, 64), kTnSplit);
+  tn_gemm_kernel<YLoad><<<grid, 256, 0, st>>>(prob, partial, yl);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  size_t n = (size_t)prob.P * prob.Q;
+  split_reduce_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 1184), 256, 0, st>>>(partial, kTnSplit, n, out, accumulate);
+  return cudaGetLastError();
+}
+
+// deterministic column sums: out[c] (+)= sum_r X[r, c]; one CTA per 32 columns, 32 x 32 threads
+__global__ void __launch_bounds__(1024) colsum_rows_kernel(const float* __restrict__ X, size_t rows, int cols, int ld,
+                                                           float* __restrict__ out, int accumulate) {
+  __shared__ float sh[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < cols)
+    for (size_t r = threadIdx.y; r < rows; r += 32) acc += X[r * ld + c];
+  sh[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = accumulate ? out[c] : 0.f;
+    for (int i = 0; i < 32; ++i) t += sh[i][threadIdx.x];
+    out[c] = t;
+  }
+}
+static cudaError_t colsum_rows(const float* X, size_t rows, int cols, int ld, float* out, int accumulate, cudaStream_t st) {
+  colsum_rows_kernel<<<cdiv(cols, 32), dim3(32, 32), 0, st>>>(X, rows, cols, ld, out, accumulate);
+  return cudaGetLastError();
+}
+
+// ---- per-step elementwise kernels ------------------------------------------------------------------------------
+struct BwdCtx {
+  int B, Lpad, L, S, R, k, farnn, nl, v_mode, full_pad;
+  float kappa;
+  const int64_t* x; const int64_t* len;
+  const float *vtab, *o, *h0, *hT;
+  const float *dalpha, *dbeta;                       // B x L x S
+  const float *hst_save, *u_save, *a_save, *zsave, *rsave;
+  float *g, *GA;                                     // 2 x B x S
+  float *DA, *DZR, *DOprod, *Pinit;                  // slabs 2 x L x B x (S | S*farnn)
+  float *DU, *Qs;                                    // slabs 2 x L x B x R
+  float *DQ, *DHb;                                   // 2 x B x R, 2 x B x S
+  float *dvtab, *dgtab;
+};
+
+__device__ __forceinline__ size_t slab(const BwdCtx& c, int z, int k, int width) {
+  return ((size_t)z * c.L + k) * c.B * width;
+}
+__device__ __forceinline__ size_t slab1(const BwdCtx& c, int z, int k, int width) {   // (L+1)-deep save slabs
+  return ((size_t)z * (c.L + 1) + k) * c.B * width;
+}
+
+__global__ void bwd_e1_kernel(const BwdCtx c) {
+  const size_t total = (size_t)2 * c.B * c.S;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int s = (int)(i % c.S);
+    const size_t rr = i / c.S;
+    const int b = (int)(rr % c.B), z = (int)(rr / c.B);
+    int tpos, orow;
+    bool alive;
+    step_pos(z, c.k, (int)c.len[b], c.full_pad, tpos, orow, alive);
+    const size_t e = (size_t)b * c.S + s;
+    const size_t sl = slab(c, z, c.k, c.S) + e;
+    const int gw = c.S * c.farnn;
+    if (!alive) {
+      c.DA[sl] = 0.f;
+      if (z == 0) c.DOprod[sl] = 0.f;
+      if (c.farnn >= 1) c.DZR[slab(c, z, c.k, gw) + (size_t)b * gw + s] = 0.f;
+      c.GA[(size_t)z * c.B * c.S + e] = 0.f;
+      continue;
+    }
+    const float* dout = z == 0 ? c.dalpha : c.dbeta;
+    const float G = c.g[(size_t)z * c.B * c.S + e] + dout[((size_t)b * c.L + orow) * c.S + s];
+    const float a = c.a_save[sl];
+    const float on = c.o[s];
+    const float hhat = apply_nl(z == 0 ? a * on : a, c.nl);
+    float dhhat = G, gA = 0.f;
+    if (c.farnn >= 1) {
+      const float zt = c.zsave[sl];
+      const float hk = c.hst_save[slab1(c, z, c.k, c.S) + e];
+      dhhat = G * zt;
+      gA = G * (1.f - zt);
+      const float dzpre = G * (hhat - hk) * zt * (1.f - zt) * c.kappa;
+      c.DZR[slab(c, z, c.k, gw) + (size_t)b * gw + s] = dzpre;
+    }
+    const float dpre = dhhat * nl_grad_from_out(hhat, c.nl);
+    if (z == 0) {
+      c.DA[sl] = dpre * on;
+      c.DOprod[sl] = dpre * a;
+    } else {
+      c.DA[sl] = dpre;
+    }
+    c.GA[(size_t)z * c.B * c.S + e] = gA;
+  }
+}
+
+__global__ void bwd_e2_kernel(const BwdCtx c) {
+  const size_t total = (size_t)2 * c.B * c.R;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i % c.R);
+    const size_t rr = i / c.R;
+    const int b = (int)(rr % c.B), z = (int)(rr / c.B);
+    int tpos, orow;
+    bool alive;
+    step_pos(z, c.k, (int)c.len[b], c.full_pad, tpos, orow, alive);
+    const size_t e = (size_t)b * c.R + r;
+    const size_t sl = slab(c, z, c.k, c.R) + e;
+    if (!alive) {
+      c.DU[sl] = 0.f;
+      c.Qs[sl] = 0.f;
+      continue;
+    }
+    const size_t vrow = c.v_mode == RE2NN_V_TOKEN ? (size_t)c.x[(size_t)b * c.Lpad + tpos] : (size_t)b * c.Lpad + tpos;
+    const float v = c.vtab[vrow * c.R + r];
+    const float u = c.u_save[sl];
+    const float dq = c.DQ[(size_t)z * c.B * c.R + e];
+    c.DU[sl] = dq * v;
+    c.Qs[sl] = u * v;
+    const float dv = dq * u;
+    if (dv != 0.f) atomicAdd(c.dvtab + vrow * c.R + r, dv);
+  }
+}
+
+__global__ void bwd_e3_kernel(const BwdCtx c) {
+  const size_t total = (size_t)2 * c.B * c.S;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int s = (int)(i % c.S);
+    const size_t rr = i / c.S;
+    const int b = (int)(rr % c.B), z = (int)(rr / c.B);
+    int tpos, orow;
+    bool alive;
+    step_pos(z, c.k, (int)c.len[b], c.full_pad, tpos, orow, alive);
+    const size_t e = (size_t)b * c.S + s;
+    const size_t sl = slab(c, z, c.k, c.S) + e;
+    const int gw = c.S * c.farnn;
+    if (!alive) {   // g keeps whatever it had (0 until the row's last live step)
+      if (z == 1) c.DOprod[sl] = 0.f;
+      if (c.farnn == 2) {
+        c.Pinit[sl] = 0.f;
+        c.DZR[slab(c, z, c.k, gw) + (size_t)b * gw + c.S + s] = 0.f;
+      }
+      continue;
+    }
+    const float dhb = c.DHb[(size_t)z * c.B * c.S + e];
+    const float on = c.o[s];
+    const float hk = c.hst_save[slab1(c, z, c.k, c.S) + e];
+    const float hinit = z == 0 ? c.h0[s] : c.hT[s];
+    float rt = 1.f;
+    if (c.farnn == 2) rt = c.rsave[sl];
+    const float htil = c.farnn == 2 ? (1.f - rt) * hinit + rt * hk : hk;
+    float dht = dhb;
+    if (z == 1) {
+      dht = dhb * on;
+      c.DOprod[sl] = dhb * htil;
+    }
+    float gB = dht;
+    if (c.farnn == 2) {
+      gB = dht * rt;
+      c.Pinit[sl] = dht * (1.f - rt);
+      const float drpre = dht * (hk - hinit) * rt * (1.f - rt) * c.kappa;
+      c.DZR[slab(c, z, c.k, gw) + (size_t)b * gw + c.S + s] = drpre;
+    }
+    c.g[(size_t)z * c.B * c.S + e] = c.GA[(size_t)z * c.B * c.S + e] + gB;
+  }
+}
+
+// dgtab[token] += [dz | dr] of this step (after the gate slab is complete)
+__global__ void bwd_gate_scatter_kernel(const BwdCtx c) {
+  const int gw = c.S * c.farnn;
+  const size_t total = (size_t)2 * c.B * gw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int col = (int)(i % gw);
+    const size_t rr = i / gw;
+    const int b = (int)(rr % c.B), z = (int)(rr / c.B);
+    int tpos, orow;
+    bool alive;
+    step_pos(z, c.k, (int)c.len[b], c.full_pad, tpos, orow, alive);
+    if (!alive) continue;
+    const float v = c.DZR[slab(c, z, c.k, gw) + (size_t)b * gw + col];
+    if (v == 0.f) continue;
+    const size_t vrow = c.v_mode == RE2NN_V_TOKEN ? (size_t)c.x[(size_t)b * c.Lpad + tpos] : (size_t)b * c.Lpad + tpos;
+    atomicAdd(c.dgtab + vrow * gw + col, v);
+  }
+}
+
+// dhT += sum_b dbeta[b, n_b - 1, :]   (beta_n = hT is emitted directly)
+__global__ void bwd_direct_hT_kernel(const float* __restrict__ dbeta, const int64_t* __restrict__ len, int B, int L,
+                                     int S, float* __restrict__ dhT) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  float acc = dhT[s];
+  for (int b = 0; b < B; ++b) {
+    int n = (int)len[b];
+    if (n >= 1 && n <= L) acc += dbeta[((size_t)b * L + (n - 1)) * S + s];
+  }
+  dhT[s] = acc;
+}
+
+// token table backward, elementwise part: gen = phi(E@G) arrives as the GEMM accumulator
+struct EpiTokenBwd {
+  const float* dvtab; const float* V_embed; const float* beta_vec;
+  float* dV; float* dbeta_prod; float* dGpre;
+  int R, nl;
+  __device__ __forceinline__ EpiTokenBwd for_dir(int) const { return *this; }
+  __device__ __forceinline__ bool tile_alive(int, int, int) const { return true; }
+  __device__ __forceinline__ RowCtx row(int) const { return RowCtx{0, 0, true}; }
+  __device__ __forceinline__ Col col(int n) const { return Col{__ldg(beta_vec + n), 0.f}; }
+  __device__ __forceinline__ Pre prefetch(const RowCtx&, int m, int n) const {
+    size_t i = (size_t)m * R + n;
+    return Pre{dvtab[i], V_embed[i]};
+  }
+  __device__ __forceinline__ void apply(const Col& c, const RowCtx&, int m, int n, float acc, const Pre& pre) const {
+    const size_t i = (size_t)m * R + n;
+    const float gen = apply_nl(acc, nl);
+    if (dV) dV[i] = pre.a * c.a;
+    dbeta_prod[i] = pre.a * (pre.b - gen);
+    dGpre[i] = pre.a * (1.f - c.a) * nl_grad_from_out(gen, nl);
+  }
+};
+
+static size_t bwd_carve(const re2nn_backward_args& a, char* base, BwdCtx* c, float** draw, float** partial,
+                        float** dalpha, float** dbeta) {
+  size_t off = 0;
+  auto take = [&](size_t floats) -> float* {
+    float* p = base ? (float*)(base + off) : nullptr;
+    off += align_up(floats * 4, 256);
+    return p;
+  };
+  const size_t B = a.B, L = a.L, S = a.S, R = a.R, gw = (size_t)a.S * a.farnn;
+  BwdCtx x;
+  memset(&x, 0, sizeof(x));
+  float* dA = take(B * L * S);
+  float* dBt = take(B * L * S);
+  x.g = take(2 * B * S);
+  x.GA = take(2 * B * S);
+  x.DA = take(2 * L * B * S);
+  x.DOprod = take(2 * L * B * S);
+  x.DU = take(2 * L * B * R);
+  x.Qs = take(2 * L * B * R);
+  x.DQ = take(2 * B * R);
+  x.DHb = take(2 * B * S);
+  if (a.farnn >= 1) {
+    x.DZR = take(2 * L * B * gw);
+    x.dgtab = take((size_t)a.table_rows * gw);
+  }
+  if (a.farnn == 2) x.Pinit = take(2 * L * B * S);
+  float* dr = a.priority_mat ? take(B * L * (size_t)a.C) : nullptr;
+  size_t pmax = std::max({S * R, S * S, (size_t)a.C * S, gw ? S * S : (size_t)0, gw ? R * S : (size_t)0});
+  float* part = take((size_t)kTnSplit * pmax);
+  if (c) *c = x;
+  if (draw) *draw = dr;
+  if (partial) *partial = part;
+  if (dalpha) *dalpha = dA;
+  if (dbeta) *dbeta = dBt;
+  return off;
+}
+
+static int grid_for(size_t total) { return (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 16); }
+
+static int run_backward(const re2nn_backward_args& a, cudaStream_t st) {
+  BwdCtx c;
+  float *draw_ws, *partial, *dalpha, *dbeta;
+  const size_t need = bwd_carve(a, (char*)a.ws, &c, &draw_ws, &partial, &dalpha, &dbeta);
+  RE2NN_CHECK(a.ws && a.ws_bytes >= need, "decompose_backward: workspace too small (%zu < %zu)", a.ws_bytes, need);
+  const int B = a.B, L = a.L, S = a.S, R = a.R, C = a.C, gw = a.S * a.farnn;
+  const size_t M = (size_t)B * L;
+  c.B = B; c.Lpad = a.Lpad; c.L = L; c.S = S; c.R = R; c.farnn = a.farnn; c.nl = a.update_nonlinear;
+  c.v_mode = a.v_mode; c.full_pad = a.full_pad; c.kappa = a.sigmoid_exponent;
+  c.x = a.x; c.len = a.lengths; c.vtab = a.vtab; c.o = a.o; c.h0 = a.h0; c.hT = a.hT;
+  c.dalpha = dalpha; c.dbeta = dbeta;
+  c.hst_save = a.hst_save; c.u_save = a.u_save; c.a_save = a.a_save; c.zsave = a.zsave; c.rsave = a.rsave;
+  c.dvtab = a.dvtab;
+
+  // 0. undo the priority layer: draw = dscores @ P^T
+  const float* draw = a.dscores;
+  GemmProblem g;
+  if (a.priority_mat) {
+    memset(&g, 0, sizeof(g));
+    g.M = (int)M; g.N = C; g.nseg = 1; g.ndir = 1;
+    g.seg[0][0] = GemmSeg{a.dscores, a.priority_mat, C, C, C, 1, 0, 0};
+    RE2NN_CUDA(launch_simt_gemm(g, EpiStore{draw_ws, C, nullptr}, ALoadPlain{}, st));
+    draw = draw_ws;
+  }
+  // 1. dAB = draw @ C  ->  dAlpha, dBeta
+  memset(&g, 0, sizeof(g));
+  g.M = (int)M; g.N = S; g.nseg = 1; g.ndir = 1;
+  g.seg[0][0] = GemmSeg{draw, a.C_mat, C, S, C, 0, 0, 0};
+  RE2NN_CUDA(launch_simt_gemm(g, EpiDAB{a.alpha, a.beta, a.lengths, dalpha, dbeta, L, S, a.full_pad}, ALoadPlain{}, st));
+  // 2. dC = draw^T @ (alpha * beta)
+  if (a.dC) {
+    TnProblem t;
+    memset(&t, 0, sizeof(t));
+    t.P = C; t.Q = S; t.npairs = 1;
+    t.pair[0] = TnPair{draw, a.alpha, C, S, M};
+    RE2NN_CUDA(run_tn(t, partial, a.dC, 0, YLoadAlphaBeta{a.beta, a.lengths, L, a.full_pad}, st));
+  }
+  // 3. sweep
+  RE2NN_CUDA(cudaMemsetAsync(c.g, 0, (size_t)2 * B * S * 4, st));
+  RE2NN_CUDA(cudaMemsetAsync(a.dvtab, 0, (size_t)a.table_rows * R * 4, st));
+  if (a.farnn >= 1) RE2NN_CUDA(cudaMemsetAsync(c.dgtab, 0, (size_t)a.table_rows * gw * 4, st));
+  for (int k = L - 1; k >= 0; --k) {
+    c.k = k;
+    bwd_e1_kernel<<<grid_for((size_t)2 * B * S), 256, 0, st>>>(c);
+    RE2NN_LAUNCH_CHECK();
+    // dq = DA[k] @ S2 (fwd) | S1 (bwd)
+    memset(&g, 0, sizeof(g));
+    g.M = B; g.N = R; g.nseg = 1; g.ndir = 2;
+    for (int z = 0; z < 2; ++z)
+      g.seg[z][0] = GemmSeg{c.DA + ((size_t)z * L + k) * B * S, z == 0 ? a.S2 : a.S1, S, R, S, 0, 0, 0};
+    RE2NN_CUDA(launch_simt_gemm(g, EpiStore2{{c.DQ, c.DQ + (size_t)B * R}, R, 0}, ALoadPlain{}, st));
+    bwd_e2_kernel<<<grid_for((size_t)2 * B * R), 256, 0, st>>>(c);
+    RE2NN_LAUNCH_CHECK();
+    // dhb = DU[k] @ S1^T + DA[k] @ W^T (fwd) | DU[k] @ S2^T + DA[k] @ W (bwd)
+    memset(&g, 0, sizeof(g));
+    g.M = B; g.N = S; g.nseg = 2; g.ndir = 2;
+    for (int z = 0; z < 2; ++z) {
+      g.seg[z][0] = GemmSeg{c.DU + ((size_t)z * L + k) * B * R, z == 0 ? a.S1 : a.S2, R, R, R, 1, 0, 0};
+      g.seg[z][1] = GemmSeg{c.DA + ((size_t)z * L + k) * B * S, a.W, S, S, S, z == 0 ? 1 : 0, 0, 0};
+    }
+    RE2NN_CUDA(launch_simt_gemm(g, EpiStore2{{c.DHb, c.DHb + (size_t)B * S}, S, 0}, ALoadPlain{}, st));
+    bwd_e3_kernel<<<grid_for((size_t)2 * B * S), 256, 0, st>>>(c);
+    RE2NN_LAUNCH_CHECK();
+    if (a.farnn >= 1) {
+      // g += [dz | dr] @ [Wss1 | Wss2]^T
+      memset(&g, 0, sizeof(g));
+      g.M = B; g.N = S; g.nseg = a.farnn; g.ndir = 2;
+      for (int z = 0; z < 2; ++z) {
+        const float* dzr = c.DZR + ((size_t)z * L + k) * B * gw;
+        g.seg[z][0] = GemmSeg{dzr, a.Wss1, gw, S, S, 1, 0, 0};
+        if (a.farnn == 2) g.seg[z][1] = GemmSeg{dzr + S, a.Wss2, gw, S, S, 1, 0, 0};
+      }
+      RE2NN_CUDA(launch_simt_gemm(g, EpiStore2{{c.g, c.g + (size_t)B * S}, S, 1}, ALoadPlain{}, st));
+      bwd_gate_scatter_kernel<<<grid_for((size_t)2 * B * gw), 256, 0, st>>>(c);
+      RE2NN_LAUNCH_CHECK();
+    }
+  }
+  // 4. weight gradients: one transposed GEMM each over all (step, sequence) rows
+  const size_t rows1 = (size_t)L * B;                    // per-direction slab rows
+  const float* Hb0 = a.hbar_save;                        // (L+1)-deep slabs: direction stride (L+1)*B*S
+  const float* Hb1 = a.hbar_save + (size_t)(L + 1) * B * S;
+  const float *DA0 = c.DA, *DA1 = c.DA + rows1 * S, *DU0 = c.DU, *DU1 = c.DU + rows1 * R;
+  const float *Q0 = c.Qs, *Q1 = c.Qs + rows1 * R;
+  TnProblem t;
+  if (a.dS1) {   // fwd: hbar^T du ; bwd: da^T q
+    memset(&t, 0, sizeof(t));
+    t.P = S; t.Q = R; t.npairs = 2;
+    t.pair[0] = TnPair{Hb0, DU0, S, R, rows1};
+    t.pair[1] = TnPair{DA1, Q1, S, R, rows1};
+    RE2NN_CUDA(run_tn(t, partial, a.dS1, 0, YLoadPlain{}, st));
+  }
+  if (a.dS2) {   // fwd: da^T q ; bwd: hbar^T du
+    memset(&t, 0, sizeof(t));
+    t.P = S; t.Q = R; t.npairs = 2;
+    t.pair[0] = TnPair{DA0, Q0, S, R, rows1};
+    t.pair[1] = TnPair{Hb1, DU1, S, R, rows1};
+    RE2NN_CUDA(run_tn(t, partial, a.dS2, 0, YLoadPlain{}, st));
+  }
+  if (a.dW) {    // fwd: hbar^T da ; bwd: da^T hbar
+    memset(&t, 0, sizeof(t));
+    t.P = S; t.Q = S; t.npairs = 2;
+    t.pair[0] = TnPair{Hb0, DA0, S, S, rows1};
+    t.pair[1] = TnPair{DA1, Hb1, S, S, rows1};
+    RE2NN_CUDA(run_tn(t, partial, a.dW, 0, YLoadPlain{}, st));
+  }
+  if (a.farnn >= 1) {
+    const float* Hs0 = a.hst_save;
+    const float* Hs1 = a.hst_save + (size_t)(L + 1) * B * S;
+    const float* Z0 = c.DZR;
+    const float* Z1 = c.DZR + rows1 * gw;
+    if (a.dWss1) {
+      memset(&t, 0, sizeof(t));
+      t.P = S; t.Q = S; t.npairs = 2;
+      t.pair[0] = TnPair{Hs0, Z0, S, gw, rows1};
+      t.pair[1] = TnPair{Hs1, Z1, S, gw, rows1};
+      RE2NN_CUDA(run_tn(t, partial, a.dWss1, 0, YLoadPlain{}, st));
+    }
+    if (a.farnn == 2 && a.dWss2) {
+      memset(&t, 0, sizeof(t));
+      t.P = S; t.Q = S; t.npairs = 2;
+      t.pair[0] = TnPair{Hs0, Z0 + S, S, gw, rows1};
+      t.pair[1] = TnPair{Hs1, Z1 + S, S, gw, rows1};
+      RE2NN_CUDA(run_tn(t, partial, a.dWss2, 0, YLoadPlain{}, st));
+    }
+    // token-side gate parameters through the gate table: Wrs = vtab^T dgtab, bs = colsum(dgtab), dvtab += dgtab Wrs^T
+    if (a.dWrs1) {
+      memset(&t, 0, sizeof(t));
+      t.P = R; t.Q = S; t.npairs = 1;
+      t.pair[0] = TnPair{a.vtab, c.dgtab, R, gw, (size_t)a.table_rows};
+      RE2NN_CUDA(run_tn(t, partial, a.dWrs1, 0, YLoadPlain{}, st));
+    }
+    if (a.farnn == 2 && a.dWrs2) {
+      memset(&t, 0, sizeof(t));
+      t.P = R; t.Q = S; t.npairs = 1;
+      t.pair[0] = TnPair{a.vtab, c.dgtab + S, R, gw, (size_t)a.table_rows};
+      RE2NN_CUDA(run_tn(t, partial, a.dWrs2, 0, YLoadPlain{}, st));
+    }
+    if (a.dbs1) RE2NN_CUDA(colsum_rows(c.dgtab, a.table_rows, S, gw, a.dbs1, 0, st));
+    if (a.farnn == 2 && a.dbs2) RE2NN_CUDA(colsum_rows(c.dgtab + S, a.table_rows, S, gw, a.dbs2, 0, st));
+    memset(&g, 0, sizeof(g));
+    g.M = a.table_rows; g.N = R; g.nseg = a.farnn; g.ndir = 1;
+    g.seg[0][0] = GemmSeg{c.dgtab, a.Wrs1, gw, S, S, 1, 0, 0};
+    if (a.farnn == 2) g.seg[0][1] = GemmSeg{c.dgtab + S, a.Wrs2, gw, S, S, 1, 0, 0};
+    RE2NN_CUDA(launch_simt_gemm(g, EpiStore2{{a.dvtab, a.dvtab}, R, 1}, ALoadPlain{}, st));
+  }
+  // 5. vector gradients
+  if (a.d_o) RE2NN_CUDA(colsum_rows(c.DOprod, (size_t)2 * rows1, S, S, a.d_o, 0, st));
+  if (a.dh0) {
+    RE2NN_CUDA(colsum_rows(c.g, B, S, S, a.dh0, 0, st));
+    if (a.farnn == 2) RE2NN_CUDA(colsum_rows(c.Pinit, rows1, S, S, a.dh0, 1, st));
+  }
+  if (a.dhT) {
+    RE2NN_CUDA(colsum_rows(c.g + (size_t)B * S, B, S, S, a.dhT, 0, st));
+    if (a.farnn == 2) RE2NN_CUDA(colsum_rows(c.Pinit + rows1 * S, rows1, S, S, a.dhT, 1, st));
+    bwd_direct_hT_kernel<<<cdiv(S, 128), 128, 0, st>>>(dbeta, a.lengths, B, L, S, a.dhT);
+    RE2NN_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // namespace re2nn
+
+using namespace re2nn;
+
+extern "C" {
+
+size_t re2nn_decompose_backward_workspace(const re2nn_backward_args* a) {
+  if (!a) return 0;
+  return bwd_carve(*a, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+int re2nn_decompose_backward(const re2nn_backward_args* a, void* stream) {
+  RE2NN_CHECK(a != nullptr, "decompose_backward: null args");
+  RE2NN_CHECK(a->B > 0 && a->L > 0 && a->S > 0 && a->R > 0 && a->C > 0, "decompose_backward: bad dims");
+  RE2NN_CHECK(a->farnn >= 0 && a->farnn <= 2, "decompose_backward: farnn must be 0, 1 or 2");
+  RE2NN_CHECK(a->dscores && a->lengths && a->vtab && a->S1 && a->S2 && a->W && a->o && a->h0 && a->hT && a->C_mat &&
+                  a->alpha && a->beta && a->hbar_save && a->hst_save && a->u_save && a->a_save && a->dvtab,
+              "decompose_backward: null tensor");
+  RE2NN_CHECK(a->v_mode == RE2NN_V_DENSE || a->x, "decompose_backward: token mode needs x");
+  RE2NN_CHECK(a->farnn == 0 || (a->zsave && a->Wss1 && a->Wrs1), "decompose_backward: farnn>=1 needs gate tensors");
+  RE2NN_CHECK(a->farnn < 2 || (a->rsave && a->Wss2 && a->Wrs2), "decompose_backward: farnn==2 needs reset-gate tensors");
+  return run_backward(*a, (cudaStream_t)stream);
+}
+
+size_t re2nn_token_table_backward_workspace(int rows, int D, int R) {
+  return align_up((size_t)rows * R * 4, 256) * 2 + align_up((size_t)kTnSplit * D * R * 4, 256) + 256;
+}
+
+int re2nn_token_table_backward(const float* dvtab, const float* V_embed, const float* E, const float* G,
+                               const float* beta_vec, int rows, int D, int R, int additional_nonlinear,
+                               float* dV_embed, float* dbeta_vec, float* dG, float* dE, void* ws, size_t ws_bytes,
+                               void* stream) {
+  RE2NN_CHECK(dvtab && V_embed && E && G && beta_vec && ws, "token_table_backward: null tensor");
+  RE2NN_CHECK(ws_bytes >= re2nn_token_table_backward_workspace(rows, D, R), "token_table_backward: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* w = (char*)ws;
+  float* dbeta_prod = (float*)w;
+  w += align_up((size_t)rows * R * 4, 256);
+  float* dGpre = (float*)w;
+  w += align_up((size_t)rows * R * 4, 256);
+  float* partial = (float*)w;
+  GemmProblem g;
+  memset(&g, 0, sizeof(g));
+  g.M = rows; g.N = R; g.nseg = 1; g.ndir = 1;
+  g.seg[0][0] = GemmSeg{E, G, D, R, D, 0, 0, 0};
+  RE2NN_CUDA(launch_simt_gemm(g, EpiTokenBwd{dvtab, V_embed, beta_vec, dV_embed, dbeta_prod, dGpre, R, additional_nonlinear},
+                              ALoadPlain{}, st));
+  if (dbeta_vec) RE2NN_CUDA(colsum_rows(dbeta_prod, rows, R, R, dbeta_vec, 0, st));
+  if (dG) {
+    TnProblem t;
+    memset(&t, 0, sizeof(t));
+    t.P = D; t.Q = R; t.npairs = 1;
+    t.pair[0] = TnPair{E, dGpre, D, R, (size_t)rows};
+    RE2NN_CUDA(run_tn(t, partial, dG, 0, YLoadPlain{}, st));
+  }
+  if (dE) {
+    memset(&g, 0, sizeof(g));
+    g.M = rows; g.N = D; g.nseg = 1; g.ndir = 1;
+    g.seg[0][0] = GemmSeg{dGpre, G, R, R, R, 1, 0, 0};
+    RE2NN_CUDA(launch_simt_gemm(g, EpiStore{dE, D, nullptr}, ALoadPlain{}, st));
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -79,6 +79,9 @@ struct StepParams {
   float* Z[2];                                    // fp32 update gate B x S (farnn>=1)
   float* Rg[2];                                   // optional save of reset gate
   float* out[2];                                  // alpha / beta : B x L x S
+  float* Usave[2];                                // training: u = hbar @ S1|S2          (B x R slab of this step)
+  float* Asave[2];                                // training: pre-activation a          (B x S slab of this step)
+  float* HstNext[2];                              // training: state before step k+1     (B x S slab)
   int dir;                                        // set by bind(): the direction this CTA works on
   // Move direction z into slot 0 so the epilogue addresses plain members (registers after inlining)
   // instead of indexing the constant bank with a run-time z for every element.
@@ -86,6 +89,7 @@ struct StepParams {
     dir = z;
     hinit[0] = hinit[z]; Q[0] = Q[z]; Hbar_next[0] = Hbar_next[z]; Hbar_cur[0] = Hbar_cur[z];
     Hst[0] = Hst[z]; H[0] = H[z]; Z[0] = Z[z]; Rg[0] = Rg[z]; out[0] = out[z];
+    Usave[0] = Usave[z]; Asave[0] = Asave[z]; HstNext[0] = HstNext[z];
   }
 };
 
@@ -134,8 +138,9 @@ template <int PREC> struct EpiQ {
   __device__ __forceinline__ Pre prefetch(const RowCtx& r, int, int n) const {
     return Pre{__ldg(p.vtab + (size_t)((uint32_t)r.vrow * (uint32_t)p.R + (uint32_t)n)), 0.f};
   }
-  __device__ __forceinline__ void apply(const Col&, const RowCtx&, int m, int n, float acc, const Pre& pre) const {
+  __device__ __forceinline__ void apply(const Col&, const RowCtx& r, int m, int n, float acc, const Pre& pre) const {
     OperandFmt<PREC>::store(p.Q[0], (uint32_t)m * (uint32_t)p.ldq + (uint32_t)n, p.q_plane, acc * pre.a);
+    if (p.Usave[0]) p.Usave[0][(uint32_t)m * (uint32_t)p.R + (uint32_t)n] = r.orow >= 0 ? acc : 0.f;
   }
 };
 
@@ -163,9 +168,16 @@ template <int PREC, int NL = -1, int FARNN = -1> struct EpiH {
     hn = apply_nl_t<kFast>(hn, nl());
     float hnew = hn;
     const uint32_t hi = (uint32_t)m * (uint32_t)p.ldh + (uint32_t)n;
+    const uint32_t si = (uint32_t)m * (uint32_t)p.S + (uint32_t)n;
+    if (farnn() >= 1) hnew = (1.f - pre.a) * pre.b + pre.a * hn;
+    if (p.Asave[0]) {   // training: keep what BPTT needs; rows that are finished hold exact zeros
+      const bool live = r.orow >= 0;
+      p.Asave[0][si] = live ? acc : 0.f;
+      if (!live) hnew = 0.f;
+      p.HstNext[0][si] = hnew;
+    }
     if (farnn() >= 1) {
-      hnew = (1.f - pre.a) * pre.b + pre.a * hn;
-      p.H[0][(uint32_t)m * (uint32_t)p.S + (uint32_t)n] = hnew;
+      p.H[0][si] = hnew;
       OperandFmt<PREC>::store(p.Hst[0], hi, p.h_plane, hnew);
     }
     if (farnn() <= 1) OperandFmt<PREC>::store(p.Hbar_next[0], hi, p.h_plane, p.dir == 1 ? hnew * c.a : hnew);

@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         pre[i] = Pre{0.f, 0.f};
-        if (col_ok && i < nrows) pre[i] = epi.prefetch(RowCtx{ctx[i], ctx[32 + i], true}, mrow0 + i, n);
+        if (col_ok && i < nrows) pre[i] = epi.prefetch(RowCtx{ctx[i], ctx[32 + i], ctx[32 + i] >= 0}, mrow0 + i, n);
       }
       if (!acc_ready) {
         if (ew == 0 && lane == 0) tc_stamp(trace, 4);   // first prefetch batch issued
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         if (col_ok && i < nrows)
-          epi.apply(cc, RowCtx{ctx[i], ctx[32 + i], true}, mrow0 + i, n, tbuf[i * 33 + lane], pre[i]);
+          epi.apply(cc, RowCtx{ctx[i], ctx[32 + i], ctx[32 + i] >= 0}, mrow0 + i, n, tbuf[i * 33 + lane], pre[i]);
       }
       __syncwarp();
     }

@@ -60,7 +60,8 @@ static size_t carve(const re2nn_recurrence_args& a, char* base, RecWs* ws) {
 // ---- init: step "-1" ------------------------------------------------------------------------------
 template <int PREC>
 __global__ void rec_init_kernel(int B, int L, int S, int farnn, const int64_t* len, const float* h0, const float* hT,
-                                const float* o, RecWs w, int ldh, size_t h_plane, float* beta) {
+                                const float* o, RecWs w, int ldh, size_t h_plane, float* beta, float* hst_save,
+                                float* hbar_save) {
   const size_t total = (size_t)2 * B * S;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int s = (int)(i % S);
@@ -72,6 +73,11 @@ __global__ void rec_init_kernel(int B, int L, int S, int farnn, const int64_t* l
       OperandFmt<PREC>::store(w.Hst[z], (size_t)m * ldh + s, h_plane, h);
     }
     if (farnn <= 1) OperandFmt<PREC>::store(w.Hbar[0][z], (size_t)m * ldh + s, h_plane, z == 1 ? h * o[s] : h);
+    if (hst_save) {   // training: slab 0 of direction z
+      const size_t slab = (size_t)z * (L + 1) * B * S;
+      hst_save[slab + (size_t)m * S + s] = h;
+      if (farnn <= 1) hbar_save[slab + (size_t)m * S + s] = z == 1 ? h * o[s] : h;
+    }
     if (z == 1) {
       int n = (int)len[m];
       if (n >= 1 && n <= L) beta[((size_t)m * L + (n - 1)) * S + s] = h;   // beta_n = hT
@@ -131,7 +137,9 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
     size_t total = (size_t)2 * B * S;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    rec_init_kernel<PREC><<<blocks, 256, 0, st>>>(B, L, S, a.farnn, a.lengths, a.h0, a.hT, a.o, w, ldh, h_plane, a.beta);
+    rec_init_kernel<PREC><<<blocks, 256, 0, st>>>(B, L, S, a.farnn, a.lengths, a.h0, a.hT, a.o, w, ldh, h_plane, a.beta,
+                                                  a.save_for_backward ? a.hst_save : nullptr,
+                                                  a.save_for_backward ? a.hbar_save : nullptr);
     RE2NN_LAUNCH_CHECK();
   }
 
@@ -176,30 +184,47 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
   p.out[0] = a.alpha; p.out[1] = a.beta;
   for (int z = 0; z < 2; ++z) { p.Q[z] = w.Q[z]; p.Hst[z] = w.Hst[z]; p.H[z] = w.H[z]; }
 
+  const bool saving = a.save_for_backward != 0;
   for (int k = 0; k < L; ++k) {
     p.k = k;
     const int par = k & 1;
+    GemmProblem gg = g_gate, g1 = g_1[par], g2 = g_2[par];
     for (int z = 0; z < 2; ++z) {
       p.Hbar_cur[z] = w.Hbar[par][z];
       p.Hbar_next[z] = w.Hbar[par ^ 1][z];
-      const size_t slab = ((size_t)z * L + k) * B * S;
-      p.Z[z] = (a.save_for_backward && a.zsave) ? a.zsave + slab : w.Z[z];
-      p.Rg[z] = (a.save_for_backward && a.rsave) ? a.rsave + slab : nullptr;
+      p.Z[z] = w.Z[z];
+      p.Rg[z] = nullptr;
+      if (saving) {   // fp32 only: operands live in the step-major save slabs instead of the ping-pong buffers
+        const size_t sS = (size_t)B * S, sR = (size_t)B * R;
+        float* hb_k = a.hbar_save + ((size_t)z * (L + 1) + k) * sS;
+        float* hs_k = a.hst_save + ((size_t)z * (L + 1) + k) * sS;
+        p.Hbar_cur[z] = hb_k;
+        p.Hbar_next[z] = hb_k + sS;
+        p.HstNext[z] = hs_k + sS;
+        p.Hst[z] = hs_k + sS;
+        p.Usave[z] = a.u_save + ((size_t)z * L + k) * sR;
+        p.Asave[z] = a.a_save + ((size_t)z * L + k) * sS;
+        if (a.farnn >= 1) p.Z[z] = a.zsave + ((size_t)z * L + k) * sS;
+        if (a.farnn == 2) p.Rg[z] = a.rsave + ((size_t)z * L + k) * sS;
+        gg.seg[z][0].A = hs_k;
+        g1.seg[z][0].A = hb_k;
+        g2.seg[z][1].A = hb_k;
+      }
     }
     if (a.farnn >= 1)
-      RE2NN_CUDA((launch_gemm<PREC>(0, g_gate, EpiGate<PREC>{p}, tm ? &tm->gate : nullptr, st)));
-    RE2NN_CUDA((launch_gemm<PREC>(1, g_1[par], EpiQ<PREC>{p}, tm ? &tm->g1[par] : nullptr, st)));
+      RE2NN_CUDA((launch_gemm<PREC>(0, gg, EpiGate<PREC>{p}, tm ? &tm->gate : nullptr, st)));
+    RE2NN_CUDA((launch_gemm<PREC>(1, g1, EpiQ<PREC>{p}, tm ? &tm->g1[par] : nullptr, st)));
     {   // compile-time specialisations of the hot configurations; everything else takes the generic functor
       const TcStepMaps* m2 = tm ? &tm->g2[par] : nullptr;
       cudaError_t e;
       if (a.farnn == 0 && a.update_nonlinear == RE2NN_NL_TANH)
-        e = launch_gemm<PREC>(2, g_2[par], EpiH<PREC, RE2NN_NL_TANH, 0>{p}, m2, st);
+        e = launch_gemm<PREC>(2, g2, EpiH<PREC, RE2NN_NL_TANH, 0>{p}, m2, st);
       else if (a.farnn == 0)
-        e = launch_gemm<PREC>(2, g_2[par], EpiH<PREC, -1, 0>{p}, m2, st);
+        e = launch_gemm<PREC>(2, g2, EpiH<PREC, -1, 0>{p}, m2, st);
       else if (a.update_nonlinear == RE2NN_NL_TANH)
-        e = launch_gemm<PREC>(2, g_2[par], EpiH<PREC, RE2NN_NL_TANH, -1>{p}, m2, st);
+        e = launch_gemm<PREC>(2, g2, EpiH<PREC, RE2NN_NL_TANH, -1>{p}, m2, st);
       else
-        e = launch_gemm<PREC>(2, g_2[par], EpiH<PREC, -1, -1>{p}, m2, st);
+        e = launch_gemm<PREC>(2, g2, EpiH<PREC, -1, -1>{p}, m2, st);
       RE2NN_CUDA(e);
     }
   }
@@ -327,6 +352,12 @@ int re2nn_decompose_recurrence(const re2nn_recurrence_args* a, void* stream) {
               "decompose_recurrence: null tensor");
   RE2NN_CHECK(a->farnn == 0 || (a->gtab && a->Wss1), "decompose_recurrence: farnn>=1 needs gtab and Wss1");
   RE2NN_CHECK(a->farnn < 2 || a->Wss2, "decompose_recurrence: farnn==2 needs Wss2");
+  if (a->save_for_backward) {
+    RE2NN_CHECK(a->precision == RE2NN_PREC_FP32, "decompose_recurrence: save_for_backward needs precision fp32");
+    RE2NN_CHECK(a->hbar_save && a->hst_save && a->u_save && a->a_save, "decompose_recurrence: missing save slabs");
+    RE2NN_CHECK(a->farnn == 0 || a->zsave, "decompose_recurrence: farnn>=1 training needs zsave");
+    RE2NN_CHECK(a->farnn < 2 || a->rsave, "decompose_recurrence: farnn==2 training needs rsave");
+  }
   cudaStream_t st = (cudaStream_t)stream;
   switch (a->precision) {
     case RE2NN_PREC_FP32: return run_recurrence<RE2NN_PREC_FP32>(*a, st);

@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import NL, PREC, V_DENSE, V_TOKEN, OnehotArgs, RecurrenceArgs, check, fn
+from ._lib import NL, PREC, V_DENSE, V_TOKEN, BackwardArgs, OnehotArgs, RecurrenceArgs, check, fn
 
 _LAUNCHES = {'n': 0}   # launch counter read by bench.py ("gpu_launches")
 
@@ -85,7 +85,7 @@ def output_vector_sum(C_mat, wildcard_vec=None):
 def decompose_recurrence(x, lengths, L, vtab, gtab, S1, S2, W, o, h0, hT, Wss1, Wss2, farnn,
                          update_nonlinear, sigmoid_exponent, precision='fp32', v_mode=V_TOKEN,
                          full_pad=False, save_for_backward=False, Lpad=None):
-    """Returns (alpha, beta[, zsave, rsave]) — B x L x S each; pad rows are left at 0."""
+    """Returns (alpha, beta, saves): alpha/beta B x L x S (pad rows undefined); saves = per-step slabs or None."""
     B = lengths.shape[0]
     S, R = S1.shape
     dev = S1.device
@@ -98,11 +98,15 @@ def decompose_recurrence(x, lengths, L, vtab, gtab, S1, S2, W, o, h0, hT, Wss1, 
     # pad rows are never read downstream (label_scores masks them), so no zero-fill is needed
     alpha = torch.empty((B, L, S), dtype=torch.float32, device=dev)
     beta = torch.empty((B, L, S), dtype=torch.float32, device=dev)
-    zsave = rsave = None
-    if save_for_backward and farnn >= 1:
-        zsave = torch.empty((2, L, B, S), dtype=torch.float32, device=dev)
-        if farnn == 2:
-            rsave = torch.empty((2, L, B, S), dtype=torch.float32, device=dev)
+    saves = None
+    if save_for_backward:
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
+        saves = dict(hbar=z(2, L + 1, B, S), hst=z(2, L + 1, B, S), u=z(2, L, B, R), a=z(2, L, B, S),
+                     z=z(2, L, B, S) if farnn >= 1 else None, r=z(2, L, B, S) if farnn == 2 else None)
+        a.hbar_save, a.hst_save = _f32(saves['hbar']), _f32(saves['hst'])
+        a.u_save, a.a_save = _f32(saves['u']), _f32(saves['a'])
+        a.zsave = _f32(saves['z']) if saves['z'] is not None else None
+        a.rsave = _f32(saves['r']) if saves['r'] is not None else None
     a.x = _i64(x) if x is not None else None
     a.lengths = _i64(lengths)
     a.vtab, a.gtab = _f32(vtab), (_f32(gtab) if gtab is not None else None)
@@ -110,14 +114,12 @@ def decompose_recurrence(x, lengths, L, vtab, gtab, S1, S2, W, o, h0, hT, Wss1, 
     a.Wss1 = _f32(Wss1) if Wss1 is not None else None
     a.Wss2 = _f32(Wss2) if Wss2 is not None else None
     a.alpha, a.beta = _f32(alpha), _f32(beta)
-    a.zsave = _f32(zsave) if zsave is not None else None
-    a.rsave = _f32(rsave) if rsave is not None else None
     need = fn['re2nn_decompose_recurrence_workspace'](C.byref(a))
     ws = torch.empty((need,), dtype=torch.uint8, device=dev)
     a.ws, a.ws_bytes = C.c_void_p(ws.data_ptr()), need
     check(fn['re2nn_decompose_recurrence'](C.byref(a), _stream()), 'decompose_recurrence')
     _count(1 + (1 if farnn == 2 or precision != 'fp32' else 0) + L * (2 + (1 if farnn else 0)))
-    return alpha, beta, zsave, rsave
+    return alpha, beta, saves
 
 
 def onehot_recurrence(x, lengths, L, language, W, o, h0, hT, update_nonlinear, max_semiring=False, full_pad=False):
@@ -250,4 +252,78 @@ def gemm_nt(A, B, precision='fp32'):
     check(fn['re2nn_gemm_nt'](PREC[precision], _f32(A), _f32(B), M, N, K, _f32(out), C.c_void_p(ws.data_ptr()), need,
                               _stream()), 'gemm_nt')
     _count(1 if precision == 'fp32' else 3)
+    return out
+
+
+def decompose_backward(consts, p, x, dense_v, lengths, L, vtab, o, alpha, beta, saves, dscores, pr_mat, want):
+    """BPTT through both directions.  `want` = set of gradient names to produce.  Returns dict name -> tensor
+    (plus 'vtab' = d loss / d token-table rows, 'o' = d loss / d output_vector_sum)."""
+    B = lengths.shape[0]
+    S, R = p['S1'].shape
+    Cn = p['C_output_mat'].shape[0]
+    dev = dscores.device
+    farnn = consts['farnn']
+    a = BackwardArgs()
+    a.B, a.L, a.S, a.R, a.C = B, L, S, R, Cn
+    a.Lpad = x.shape[1] if dense_v is None else dense_v.shape[1]
+    a.farnn, a.update_nonlinear = farnn, NL[consts['update_nonlinear']]
+    a.v_mode = V_TOKEN if dense_v is None else V_DENSE
+    a.full_pad, a.ce1 = int(consts['full_pad']), int(consts['ce1'])
+    a.table_rows = vtab.shape[0]
+    a.sigmoid_exponent = float(consts['sigmoid_exponent'])
+    a.x = _i64(x) if x is not None else None
+    a.lengths, a.dscores = _i64(lengths), _f32(dscores)
+    a.priority_mat = _f32(pr_mat) if pr_mat is not None else None
+    a.vtab, a.S1, a.S2, a.W, a.o = _f32(vtab), _f32(p['S1']), _f32(p['S2']), _f32(p['wildcard_mat']), _f32(o)
+    a.h0, a.hT, a.C_mat = _f32(p['h0']), _f32(p['hT']), _f32(p['C_output_mat'])
+    for n in ('Wss1', 'Wss2', 'Wrs1', 'Wrs2'):
+        setattr(a, n, _f32(p[n]) if n in p else None)
+    a.alpha, a.beta = _f32(alpha), _f32(beta)
+    a.hbar_save, a.hst_save, a.u_save, a.a_save = (_f32(saves[k]) for k in ('hbar', 'hst', 'u', 'a'))
+    a.zsave = _f32(saves['z']) if saves['z'] is not None else None
+    a.rsave = _f32(saves['r']) if saves['r'] is not None else None
+    out = {}
+
+    def grad(name, like, field):
+        if name in want:
+            out[name] = torch.empty_like(like)
+            setattr(a, field, _f32(out[name]))
+
+    grad('S1', p['S1'], 'dS1'); grad('S2', p['S2'], 'dS2'); grad('wildcard_mat', p['wildcard_mat'], 'dW')
+    grad('h0', p['h0'], 'dh0'); grad('hT', p['hT'], 'dhT')
+    out['C_output_mat'] = torch.empty_like(p['C_output_mat']); a.dC = _f32(out['C_output_mat'])
+    out['o'] = torch.empty((S,), dtype=torch.float32, device=dev); a.d_o = _f32(out['o'])
+    if farnn >= 1:
+        grad('Wss1', p['Wss1'], 'dWss1'); grad('Wrs1', p['Wrs1'], 'dWrs1'); grad('bs1', p['bs1'], 'dbs1')
+    if farnn == 2:
+        grad('Wss2', p['Wss2'], 'dWss2'); grad('Wrs2', p['Wrs2'], 'dWrs2'); grad('bs2', p['bs2'], 'dbs2')
+    out['vtab'] = torch.empty_like(vtab); a.dvtab = _f32(out['vtab'])
+    need = fn['re2nn_decompose_backward_workspace'](C.byref(a))
+    ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+    a.ws, a.ws_bytes = C.c_void_p(ws.data_ptr()), need
+    check(fn['re2nn_decompose_backward'](C.byref(a), _stream()), 'decompose_backward')
+    _count(4 + L * (5 + (2 if farnn else 0)) + 12)
+    return out
+
+
+def token_table_backward(dvtab, V_embed, E, G, beta_vec, additional_nonlinear, want):
+    rows, R = V_embed.shape
+    D = E.shape[1]
+    dev = dvtab.device
+    out = {}
+    dV = torch.empty_like(V_embed) if 'V_embed' in want else None
+    dbeta = torch.empty_like(beta_vec) if 'beta_vec' in want else None
+    dG = torch.empty_like(G) if 'embed_r_generalized' in want else None
+    dE = torch.empty_like(E) if 'embedding' in want else None
+    need = fn['re2nn_token_table_backward_workspace'](rows, D, R)
+    ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+    check(fn['re2nn_token_table_backward'](_f32(dvtab), _f32(V_embed), _f32(E), _f32(G), _f32(beta_vec), rows, D, R,
+                                           NL[additional_nonlinear], _f32(dV) if dV is not None else None,
+                                           _f32(dbeta) if dbeta is not None else None,
+                                           _f32(dG) if dG is not None else None, _f32(dE) if dE is not None else None,
+                                           C.c_void_p(ws.data_ptr()), need, _stream()), 'token_table_backward')
+    _count(5)
+    for k, v in (('V_embed', dV), ('beta_vec', dbeta), ('embed_r_generalized', dG), ('embedding', dE)):
+        if v is not None:
+            out[k] = v
     return out

@@ -130,3 +130,51 @@ def test_decompose_cfg2_shapes_vs_oracle(farnn, crf):
     np.testing.assert_array_equal(true.cpu().numpy(), o_true)
     mism = int((pred.cpu().numpy() != o_pred).sum())
     assert mism == 0, 'decoded tags differ at %d of %d positions' % (mism, len(o_pred))
+
+
+@pytest.mark.parametrize('name', [n for n in DEC if 'max' not in n])
+def test_decompose_gradients_golden(name):
+    """loss.backward() through the CUDA backward vs the reference's autograd gradients."""
+    z, meta = load_golden(name)
+    m = build_module(name, z, meta).cuda()
+    x, lab, lens = _t(z['x']), _t(z['labels']), _t(z['lengths'])
+    if meta['kind'] == 'sf':
+        loss, _, _ = m(_t(z['dense_v']), lab, lens, True)
+    else:
+        loss, _, _ = m.forward_local(x, lab, lens, train=True)
+    assert rel_err(loss.item(), z['loss']) < TOL
+    loss.backward()
+    gold = golden_grads(z)
+    params = dict(m.named_parameters())
+    assert gold, 'fixture without gradients'
+    for k, ref in gold.items():
+        g = params[k].grad
+        assert g is not None, 'no gradient for ' + k
+        if np.abs(ref).max() == 0:
+            assert g.abs().max().item() < 1e-6, k
+        else:
+            err = rel_err(g.cpu().numpy(), ref)
+            assert err < 2e-4, '%s: rel err %.3e' % (k, err)      # reference gradients are themselves fp32
+
+
+@pytest.mark.parametrize('farnn,crf', [(0, 1), (2, 1), (1, 0)])
+def test_decompose_gradients_cfg3_shapes_vs_oracle(farnn, crf):
+    """SNIPS-shaped factors, gradients against the float64 autograd oracle within 1e-5 * max|grad| ... 1e-4."""
+    from oracle import re2nn_oracle_torch as ot
+    m, args, x, lens, lab = _random_decompose(7, 500, 300, 200, 72, 100, 24, 20, farnn=farnn, use_crf=crf,
+                                              update_nonlinear='tanh', beta=0.1, train_beta=1, train_h0=1, train_hT=1,
+                                              train_V_embed=1, train_wildcard=1)
+    loss, _, _ = m.forward_local(_t(x), _t(lab), _t(lens), train=True)
+    loss.backward()
+    rename = {'embedding.weight': 'embedding', 'crf.transitions': 'crf_transitions',
+              'priority_layer.priority_mat': 'priority_mat', 'priority_layer.priority_bias': 'priority_bias'}
+    p64 = {rename.get(k, k): v.detach().cpu().numpy().astype(np.float64) for k, v in m.state_dict().items()}
+    names = [rename.get(k, k) for k, v in m.named_parameters() if v.requires_grad]
+    o_loss, g64 = ot.grads(p64, x, lab, lens, args, names=names)
+    assert rel_err(loss.item(), o_loss) < TOL
+    for k, v in m.named_parameters():
+        if not v.requires_grad:
+            continue
+        ref = g64[rename.get(k, k)]
+        err = rel_err(v.grad.cpu().numpy(), ref)
+        assert err < 1e-4, '%s: rel err %.3e' % (k, err)

@@ -56,3 +56,24 @@ def test_helpers_ragged():
     np.testing.assert_array_equal(r, [[3, 2, 1, 0], [4, 5, 6, 7], [9, 8, 10, 11]])
     np.testing.assert_array_equal(orc.flatten_rows(a, lens), [0, 1, 2, 3, 4, 8, 9])
     np.testing.assert_array_equal(orc.length_mask(lens), a % 4 < lens[:, None])
+
+
+@pytest.mark.parametrize('name', [n for n in golden_files('dec_') + golden_files('sf_') if 'max' not in n])
+def test_decompose_gradients(name):
+    """The autograd restatement reproduces the reference's own parameter gradients."""
+    from helpers import golden_grads
+    from oracle import re2nn_oracle_torch as ot
+    z, meta = load_golden(name)
+    p, args = oracle_params(z, np.float64), args_of(meta)
+    gold = golden_grads(z)
+    rename = {'embedding.weight': 'embedding', 'crf.transitions': 'crf_transitions'}
+    names = [rename.get(k, k) for k in gold]
+    dense_v = z['dense_v'] if meta['kind'] == 'sf' else None
+    loss, g = ot.grads(p, z['x'], z['labels'], z['lengths'], args, dense_v, names=names)
+    assert rel_err(loss, z['loss']) < 1e-5
+    for k, ref in gold.items():
+        mine = g[rename.get(k, k)]
+        if np.abs(ref).max() == 0:
+            assert mine is None or np.abs(mine).max() < 1e-7, k
+        else:
+            assert rel_err(mine, ref) < 2e-4, (k, rel_err(mine, ref))    # reference grads are fp32
