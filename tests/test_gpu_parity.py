@@ -103,6 +103,8 @@ def _random_decompose(seed, V, S, R, C, D, B, Lmax, **flags):
                 if hasattr(m, n):
                     getattr(m, n).mul_(0.05)
             m.bs1.fill_(0.3)
+            if hasattr(m, 'bs2'):
+                m.bs2.fill_(-0.1)
     return m.cuda(), args, x, lens, lab
 
 
