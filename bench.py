@@ -36,6 +36,8 @@ def parse():
     ap.add_argument('--config', default='cfg2')
     ap.add_argument('--precision', default=os.environ.get('RE2NN_PRECISION', 'auto'))
     ap.add_argument('--farnn', type=int, default=0)
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train'],
+                    help="infer = BASELINE configs[1] (headline); train = configs[2]: fwd+bwd+grad all-reduce, B=1024/GPU")
     ap.add_argument('--cpu-sample', type=int, default=256, help='sequences in the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
@@ -196,6 +198,8 @@ def main():
     import re2nn_seq_b200 as r
     from re2nn_seq_b200 import ops, synth
 
+    if a.mode == 'train' and a.config == 'cfg2':
+        a.config = 'cfg3'
     c, args, f, x, lens, lab = build_workload(a.config, rank, a.farnn)
     torch.manual_seed(0)
     m = r.FARNN_S_D_W_I_S(args=args, o_idx=0, **f)
@@ -207,25 +211,44 @@ def main():
     m.precision = prec
     p_oracle = oracle_params_from_module(m) if rank == 0 else None
     m = m.cuda().eval()
+    bucket = None
+    if a.mode == 'train':
+        from re2nn_seq_b200 import dist as rd
+        m.train()
+        m.precision = prec = 'fp32'
+        bucket = rd.GradBucket(m)
 
     n_tok = int(lens.sum())
     xd, ld, yd = torch.from_numpy(x).cuda(), torch.from_numpy(lens).cuda(), torch.from_numpy(lab).cuda()
     xh, lh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(lens).pin_memory(), torch.from_numpy(lab).pin_memory()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device='cuda')   # > 126 MB L2
 
+    def train_step(xg, yg, lg):
+        for q in bucket.params:
+            q.grad = None
+        loss, pred, _ = m.forward_local(xg, yg, lg, train=True)
+        loss.backward()
+        bucket.all_reduce()                # one all-reduce(SUM) of the flat gradient bucket (NCCL when N>1)
+        return loss, pred, None
+
     def step_device():
+        if a.mode == 'train':
+            return train_step(xd, yd, ld)
         with torch.no_grad():
             return m.forward_local(xd, yd, ld, train=False)
 
     pred_host = torch.empty((n_tok,), dtype=torch.int64).pin_memory()
 
     def step_e2e():
-        with torch.no_grad():
-            xg = xh.cuda(non_blocking=True)
-            lg = lh.cuda(non_blocking=True)
-            yg = yh.cuda(non_blocking=True)
-            _, pred, _ = m.forward_local(xg, yg, lg, train=False)
-            pred_host.copy_(pred, non_blocking=True)
+        xg = xh.cuda(non_blocking=True)
+        lg = lh.cuda(non_blocking=True)
+        yg = yh.cuda(non_blocking=True)
+        if a.mode == 'train':
+            _, pred, _ = train_step(xg, yg, lg)
+        else:
+            with torch.no_grad():
+                _, pred, _ = m.forward_local(xg, yg, lg, train=False)
+        pred_host.copy_(pred, non_blocking=True)
 
     for _ in range(max(a.warmup, 3)):
         step_device()
@@ -298,8 +321,11 @@ def main():
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': {'fp32': 'f32', 'bf16': 'bf16', 'tf32x3': 'tf32x3'}[prec], 'data': 'synthetic',
-            'config': {'workload': 'cfg2 decompose i-FST inference + Viterbi (V=%d,C=%d,S=%d,R=%d,D=%d,len<=%d,B=%d per GPU)'
-                                   % (c['V'], c['C'], S, R, D, c['Lmax'], c['B']),
+            'config': {'workload': '%s decompose i-FST %s (V=%d,C=%d,S=%d,R=%d,D=%d,len<=%d,B=%d per GPU)'
+                                   % (a.config, 'training step: fwd + CRF loss + bwd + grad all-reduce + Viterbi'
+                                      if a.mode == 'train' else 'inference + Viterbi', c['V'], c['C'], S, R, D,
+                                      c['Lmax'], c['B']),
+                       'mode': a.mode,
                        'farnn': a.farnn, 'precision': prec, 'tokens_per_step_per_gpu': n_tok,
                        'l2': 'flushed between timed iterations (256 MB write)',
                        'whole_step_tflops': value * flops_per_position(S, R, D, Cp, a.farnn) / 1e12},

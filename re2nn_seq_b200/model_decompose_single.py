@@ -150,7 +150,8 @@ class _DecomposeBase(nn.Module):
             if self.use_crf:
                 loss = self.crf.neg_log_likelihood_loss(all_scores, None, lab, lengths=lengths)
             else:
-                loss = autograd_fns.ce_loss(all_scores, lengths, lab, N)
+                # under data parallelism every rank divides by the GLOBAL token count (re2nn_seq_b200/dist.py)
+                loss = autograd_fns.ce_loss(all_scores, lengths, lab, getattr(self, 'global_tokens', None) or N)
             mt = self.args.marryup_type
             if mt in ('kd', 'pr'):
                 from .kd import KD_loss, PR_loss
