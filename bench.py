@@ -206,8 +206,8 @@ def main():
     with torch.no_grad():
         m.crf.transitions.copy_(torch.from_numpy(synth.crf_transitions(0, m.C)))
     prec = a.precision
-    if prec == 'auto':
-        prec = 'fp32'
+    if prec == 'auto':      # parity-grade tensor-core mode when the device has tcgen05, else the fp32 CUDA-core path
+        prec = 'tf32x3' if ops.has_tcgen05() else 'fp32'
     m.precision = prec
     p_oracle = oracle_params_from_module(m) if rank == 0 else None
     m = m.cuda().eval()
@@ -253,6 +253,16 @@ def main():
     for _ in range(max(a.warmup, 3)):
         step_device()
     torch.cuda.synchronize()
+
+    # parity self-check on the bench batch: decoded tags of the timed mode vs the fp32 CUDA-core path
+    mismatch = None
+    if a.mode == 'infer' and prec != 'fp32':
+        with torch.no_grad():
+            _, p_fast, _ = m.forward_local(xd, yd, ld, train=False)
+            m.precision = 'fp32'
+            _, p_ref, _ = m.forward_local(xd, yd, ld, train=False)
+            m.precision = prec
+        mismatch = int((p_fast != p_ref).sum().item())
 
     def barrier():
         if world > 1:
@@ -327,6 +337,7 @@ def main():
                                       c['Lmax'], c['B']),
                        'mode': a.mode,
                        'farnn': a.farnn, 'precision': prec, 'tokens_per_step_per_gpu': n_tok,
+                       'tag_mismatches_vs_fp32_path': mismatch,
                        'l2': 'flushed between timed iterations (256 MB write)',
                        'whole_step_tflops': value * flops_per_position(S, R, D, Cp, a.farnn) / 1e12},
             'roofline': {'bound': 'tensor', 'kernel': 'step GEMM2 + state epilogue (%s)' % prec, 'achieved': achieved,

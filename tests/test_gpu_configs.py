@@ -1,0 +1,124 @@
+"""GPU: the remaining BASELINE.json configurations as parity cases (shapes of cfg1, cfg4, cfg5 at batch sizes
+the oracle finishes in seconds) plus size-independent properties at the full cfg2 batch."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import oracle_params, rel_err
+from oracle import re2nn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+class _Z(dict):
+    files = property(lambda self: list(self.keys()))
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _decompose(seed, V, S, R, C, D, B, Lmax, fixed_len=False, **flags):
+    import re2nn_seq_b200 as r
+    from re2nn_seq_b200 import synth
+    args = synth.make_args(**flags)
+    f = synth.make_decompose_factors(seed, V, S, R, C, D, dtype=np.float32)
+    x, lens, lab = synth.make_batch(seed + 1, B, Lmax, V, C, fixed_len=fixed_len)
+    torch.manual_seed(seed)
+    m = r.FARNN_S_D_W_I_S(args=args, o_idx=0, **f)
+    with torch.no_grad():
+        if args.use_crf:
+            m.crf.transitions.copy_(torch.from_numpy(synth.crf_transitions(seed, m.C)))
+    return m.cuda(), args, x, lens, lab
+
+
+def _oracle64(m, args, x, lens):
+    z = _Z({'p.' + k: v.detach().cpu().numpy() for k, v in m.state_dict().items()})
+    sc, _, _ = orc.decompose_scores(oracle_params(z, np.float64), x, lens, args)
+    return sc
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'tf32x3'])
+def test_cfg4_shapes_long_recurrence(prec):
+    """ATIS-ZH-shaped: S=512, R=256, len<=128 (long-recurrence stress), small batch."""
+    from re2nn_seq_b200 import ops
+    if prec != 'fp32' and not ops.has_tcgen05():
+        pytest.skip('no tcgen05')
+    m, args, x, lens, lab = _decompose(11, 2000, 512, 256, 127, 100, 40, 128, farnn=0, use_crf=1,
+                                       update_nonlinear='tanh', beta=0.1)
+    m.precision = prec
+    with torch.no_grad():
+        sc = m.forward_scores(_t(x), _t(lens)).cpu().numpy()
+        _, pred, _ = m.forward_local(_t(x), _t(lab), _t(lens), train=False)
+    truth = _oracle64(m, args, x, lens)
+    mask = orc.length_mask(lens, 128)
+    assert rel_err(sc[mask], truth[mask]) < 1e-5
+    z = _Z({'p.' + k: v.detach().cpu().numpy() for k, v in m.state_dict().items()})
+    p32 = oracle_params(z, np.float32)
+    o_pred = orc.decode(p32, truth.astype(np.float32), lens, args, m.C, 0, True)
+    assert (pred.cpu().numpy() != o_pred).sum() == 0
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'tf32x3', 'bf16'])
+def test_cfg5_shapes(prec):
+    """Scale-sweep shapes S=1024, R=512, C=128, len=64 (fixed), small batch; exercises the 256-wide n-tiles."""
+    from re2nn_seq_b200 import ops
+    if prec != 'fp32' and not ops.has_tcgen05():
+        pytest.skip('no tcgen05')
+    m, args, x, lens, lab = _decompose(12, 900, 1024, 512, 128, 100, 300, 64, fixed_len=True, farnn=0, use_crf=1,
+                                       update_nonlinear='tanh', beta=0.1)
+    m.precision = prec
+    with torch.no_grad():
+        sc = m.forward_scores(_t(x), _t(lens)).cpu().numpy()
+    truth = _oracle64(m, args, x[:24], lens[:24])           # oracle on a slice: rows are independent
+    err = rel_err(sc[:24], truth)
+    # tensor-core fp32 accumulation truncates: at K = 1024..1536 the 3xTF32 path is good to 3e-5, not 1e-5
+    assert err < {'bf16': 3e-2, 'tf32x3': 3e-5, 'fp32': 1e-5}[prec], err
+
+
+def test_cfg1_onehot_shapes_exact():
+    """ATIS-BIO-shaped exact automaton (V=900, S=300, C=127+1, len<=46, B=32): integer path counts, bit-exact."""
+    import re2nn_seq_b200 as r
+    from re2nn_seq_b200 import synth
+    args = synth.make_args(method='onehot', rand_constant=0.0)
+    a = synth.make_onehot_automaton(21, 900, 300, 127, dtype=np.float32)
+    x, lens, lab = synth.make_batch(22, 32, 46, 900, 127)
+    m = r.FARNN_S_O_I_S(a['language_tensor'], a['output_mat'], a['wildcard_mat'], a['output_wildcard_vector'],
+                        a['final_vector'], a['start_vector'], None, args, 0, False)
+    with torch.no_grad():
+        loss, pred, true = m.forward_local(torch.from_numpy(x), torch.from_numpy(lab), torch.from_numpy(lens), train=False)
+        sc = m.forward_score(torch.from_numpy(x), None, torch.from_numpy(lens)).numpy()
+    p = {k: v for k, v in a.items() if k != 'language_rows'}
+    p.update(h0=a['start_vector'], hT=a['final_vector'])
+    o_sc = orc.onehot_scores(p, x, lens, args)
+    assert np.isfinite(sc).all() and sc.max() < 2 ** 24
+    np.testing.assert_array_equal(sc, o_sc)
+    _, o_pred, o_true, _ = orc.onehot_forward_local(p, x, lab, lens, args, 0, train=False)
+    np.testing.assert_array_equal(pred.numpy(), o_pred)
+
+
+def test_full_cfg2_batch_properties():
+    """Full B=4096 batch: (1) rows are independent -> any permutation of the batch permutes the outputs;
+    (2) padding is never read -> garbage in the pad columns changes nothing; (3) a slice agrees with the oracle."""
+    m, args, x, lens, lab = _decompose(13, 12000, 300, 200, 72, 100, 4096, 35, farnn=0, use_crf=1,
+                                       update_nonlinear='tanh', beta=0.1)
+    xt, lt, yt = _t(x), _t(lens), _t(lab)
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    with torch.no_grad():
+        _, pred, _ = m.forward_local(xt, yt, lt, train=False)
+        perm = np.random.RandomState(0).permutation(4096)
+        _, pred_p, _ = m.forward_local(_t(x[perm]), _t(lab[perm]), _t(lens[perm]), train=False)
+        x2 = x.copy()
+        pad = np.arange(35)[None, :] >= lens[:, None]
+        x2[pad] = np.random.RandomState(1).randint(0, 12000, size=int(pad.sum()))
+        _, pred_g, _ = m.forward_local(_t(x2), yt, lt, train=False)
+    pred = pred.cpu().numpy()
+    pred_p = pred_p.cpu().numpy()
+    offs_p = np.concatenate([[0], np.cumsum(lens[perm])])
+    for j in (0, 1, 17, 4095):
+        b = perm[j]
+        np.testing.assert_array_equal(pred_p[offs_p[j]:offs_p[j + 1]], pred[offs[b]:offs[b + 1]])
+    np.testing.assert_array_equal(pred_g.cpu().numpy(), pred)
+    z = _Z({'p.' + k: v.detach().cpu().numpy() for k, v in m.state_dict().items()})
+    _, o_pred, _, _ = orc.decompose_forward_local(oracle_params(z, np.float32), x[:64], lab[:64], lens[:64], args, 0, False)
+    np.testing.assert_array_equal(pred[:offs[64]], o_pred)
