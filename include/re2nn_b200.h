@@ -57,9 +57,9 @@ int re2nn_has_tcgen05(void);
  * launch counts per kernel class (0 = gate GEMM, 1 = GEMM1 + Q epilogue, 2 = GEMM2 + state epilogue)
  * and resets the counters. */
 int re2nn_profile_enable(int on);
-/* debug: install (or clear with NULL) a device buffer receiving 8 clock64 stamps per CTA of every
+/* debug: install (or clear with NULL) a device buffer receiving 32 clock64 stamps per CTA of every
  * tcgen05 step-GEMM launch (entry, alive-check, setup, MMAs issued, prefetch issued, accumulator ready,
- * epilogue done, exit); slot = 8 * linear CTA id, overwritten by every launch. */
+ * epilogue done, exit, then arrival time of the first 24 k-blocks); slot = 32 * linear CTA id. */
 int re2nn_debug_set_tc_trace(unsigned long long* device_buf);
 int re2nn_profile_read(double* ms_out_host, int64_t* count_out_host);
 
@@ -187,6 +187,26 @@ typedef struct re2nn_onehot_args {
   float* beta;                 /* B x L x S */
 } re2nn_onehot_args;
 int re2nn_onehot_recurrence(const re2nn_onehot_args* a, void* stream);
+
+/* ---- onehot i-FST backward (sum semiring) ----------------------------------------------------------------
+ * replaces torch.autograd over FARNN_S_O_I_S.forward_score (train_onehot.py:179-181): the only trained
+ * parameter of that module is language_tensor (model_onehot.py:326-340).  dalpha/dbeta: d loss / d states
+ * (B x L x S, from re2nn_label_scores_backward); dlanguage ((V+1) x S x S) must be zero-initialised and
+ * receives the scatter-added outer products (float atomics). */
+typedef struct re2nn_onehot_backward_args {
+  int32_t B, Lpad, L, S, update_nonlinear, full_pad;
+  const int64_t* x; const int64_t* lengths;
+  const float *language, *W, *o, *h0, *hT, *alpha, *beta, *dalpha, *dbeta;
+  float* dlanguage;
+} re2nn_onehot_backward_args;
+int re2nn_onehot_backward(const re2nn_onehot_backward_args* a, void* stream);
+
+/* d loss / d alpha, d loss / d beta from d loss / d scores:  dAB = dscores [@ P^T] @ C ; dalpha = dAB*beta,
+ * dbeta = dAB*alpha (zero at pads).  ws: B*L*C floats when priority_mat != NULL. */
+int re2nn_label_scores_backward(const float* dscores, const float* alpha, const float* beta,
+                                const int64_t* lengths, int B, int L, int S, const float* C_mat, int C,
+                                const float* priority_mat, int full_pad, float* dalpha, float* dbeta,
+                                float* ws, void* stream);
 
 /* ---- per-position label scores -------------------------------------------------------------------
  * scores[b,t,c] = sum_s C[c,s] * alpha[b,t,s] * beta[b,t,s]  for t < lengths[b] (all t if full_pad);

@@ -52,6 +52,14 @@ class BackwardArgs(C.Structure):
     ]
 
 
+class OnehotBackwardArgs(C.Structure):
+    _fields_ = [
+        ('B', i32), ('Lpad', i32), ('L', i32), ('S', i32), ('update_nonlinear', i32), ('full_pad', i32),
+        ('x', vp), ('lengths', vp), ('language', vp), ('W', vp), ('o', vp), ('h0', vp), ('hT', vp),
+        ('alpha', vp), ('beta', vp), ('dalpha', vp), ('dbeta', vp), ('dlanguage', vp),
+    ]
+
+
 class OnehotArgs(C.Structure):
     _fields_ = [
         ('B', i32), ('Lpad', i32), ('L', i32), ('S', i32), ('update_nonlinear', i32),
@@ -88,6 +96,8 @@ SYMBOLS = {
     're2nn_token_table_backward_workspace': (sz, [C.c_int, C.c_int, C.c_int]),
     're2nn_token_table_backward': (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, sz, vp]),
     're2nn_onehot_recurrence': (C.c_int, [C.POINTER(OnehotArgs), vp]),
+    're2nn_onehot_backward': (C.c_int, [C.POINTER(OnehotBackwardArgs), vp]),
+    're2nn_label_scores_backward': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp]),
     're2nn_label_scores_workspace': (sz, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     're2nn_label_scores': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, sz,
                                      vp]),

@@ -31,4 +31,10 @@ def decompose_backward(ctx, dscores):
 
 
 def onehot_backward(ctx, dscores):
-    raise NotImplementedError("re2nn_b200: the onehot backward (language_tensor gradient) is not built yet")
+    consts = ctx.consts
+    if consts['max_semiring']:
+        raise NotImplementedError("re2nn_b200: the max-product onehot backward is not built (train_mode='max')")
+    x, lengths, h0, hT, language, W, output_mat, o, alpha, beta = ctx.saved
+    pr_mat = ctx.pr[0].detach() if consts['use_priority'] else None
+    return ops.onehot_backward(x, lengths, ctx.L, language, W, o, h0, hT, alpha, beta, dscores, output_mat, pr_mat,
+                               consts['update_nonlinear'], consts['full_pad'])

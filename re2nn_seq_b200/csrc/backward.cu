@@ -594,6 +594,28 @@ int re2nn_decompose_backward(const re2nn_backward_args* a, void* stream) {
   return run_backward(*a, (cudaStream_t)stream);
 }
 
+int re2nn_label_scores_backward(const float* dscores, const float* alpha, const float* beta, const int64_t* lengths,
+                                int B, int L, int S, const float* C_mat, int C, const float* priority_mat,
+                                int full_pad, float* dalpha, float* dbeta, float* ws, void* stream) {
+  RE2NN_CHECK(dscores && alpha && beta && lengths && C_mat && dalpha && dbeta, "label_scores_backward: null tensor");
+  RE2NN_CHECK(!priority_mat || ws, "label_scores_backward: priority needs a workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* draw = dscores;
+  GemmProblem g;
+  if (priority_mat) {
+    memset(&g, 0, sizeof(g));
+    g.M = B * L; g.N = C; g.nseg = 1; g.ndir = 1;
+    g.seg[0][0] = GemmSeg{dscores, priority_mat, C, C, C, 1, 0, 0};
+    RE2NN_CUDA(launch_simt_gemm(g, EpiStore{ws, C, nullptr}, ALoadPlain{}, st));
+    draw = ws;
+  }
+  memset(&g, 0, sizeof(g));
+  g.M = B * L; g.N = S; g.nseg = 1; g.ndir = 1;
+  g.seg[0][0] = GemmSeg{draw, C_mat, C, S, C, 0, 0, 0};
+  RE2NN_CUDA(launch_simt_gemm(g, EpiDAB{alpha, beta, lengths, dalpha, dbeta, L, S, full_pad}, ALoadPlain{}, st));
+  return 0;
+}
+
 size_t re2nn_token_table_backward_workspace(int rows, int D, int R) {
   return align_up((size_t)rows * R * 4, 256) * 2 + align_up((size_t)kTnSplit * D * R * 4, 256) + 256;
 }

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
   const int m0 = blockIdx.x * 128, n0 = blockIdx.y * bn;
   const int rows = min(128, L.M - m0);
   unsigned long long* trace = nullptr;
-  if (g_tc_trace) trace = g_tc_trace + 8ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+  if (g_tc_trace) trace = g_tc_trace + 32ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
   if (threadIdx.x == 0) tc_stamp(trace, 0);
   if (!epi_in.tile_alive(z, m0, rows)) return;
   if (threadIdx.x == 0) tc_stamp(trace, 1);
@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
         const int st = it % Cfg::kStages;
         const uint32_t ph = (it / Cfg::kStages) & 1;
         mbar_wait(full_bar(st), ph);
+        if (it < 24) tc_stamp(trace, 8 + it);   // debug: when did k-block `it` land?
         tc_fence_after();
         const uint32_t sa = base + st * Cfg::kStageBytes;
         const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + Cfg::kABytes);

@@ -114,9 +114,108 @@ __global__ void __launch_bounds__(kOhThreads) onehot_recurrence_kernel(const re2
   }
 }
 
+// Backward of the sum-semiring recurrence for one (sequence, direction): walks the steps in reverse, keeps the
+// state gradient in shared memory, scatter-adds dT[x_t] += outer products and propagates g through T[x_t].
+//   fwd: pre = (h_prev . T) * o, h = phi(pre):  dacc = G*phi'(h)*o ; dT[s][j] += h_prev[s]*dacc[j] ; g_prev[s] = sum_j T[s][j]*dacc[j]
+//   bwd: pre = T . (h_prev*o),   h = phi(pre):  dacc = G*phi'(h)   ; dT[s][j] += dacc[s]*hh[j]     ; g_prev[j] = o[j]*sum_s dacc[s]*T[s][j]
+__global__ void __launch_bounds__(kOhThreads) onehot_backward_kernel(const re2nn_onehot_backward_args a) {
+  extern __shared__ float smem[];
+  const int S = a.S;
+  float* g = smem;            // S   gradient w.r.t. the state produced by the current step
+  float* dacc = smem + S;     // S
+  float* hprev = smem + 2 * S;  // S   operand of the step (bwd: already * o)
+  float* part = smem + 3 * S;   // kOhWarps * S
+  const int b = blockIdx.x, z = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = (int)a.lengths[b];
+  const float* __restrict__ W = a.W;
+  const float* __restrict__ o = a.o;
+  const float* states = z == 0 ? a.alpha : a.beta;
+  const float* dstates = z == 0 ? a.dalpha : a.dbeta;
+  for (int s = tid; s < S; s += kOhThreads) g[s] = 0.f;
+  __syncthreads();
+  for (int k = a.L - 1; k >= 0; --k) {
+    int tpos, orow;
+    bool alive;
+    step_pos(z, k, n, a.full_pad, tpos, orow, alive);
+    if (!alive) continue;     // block-uniform
+    // state before this step: output row of step k-1, or the initial vector
+    int tp2, oprev;
+    bool al2;
+    if (k > 0) step_pos(z, k - 1, n, a.full_pad, tp2, oprev, al2); else oprev = -1;
+    const int64_t tok = a.x[(size_t)b * a.Lpad + tpos];
+    const float* __restrict__ T = a.language + (size_t)tok * S * S;
+    float* __restrict__ dT = a.dlanguage + (size_t)tok * S * S;
+    for (int s = tid; s < S; s += kOhThreads) {
+      const float h = states[((size_t)b * a.L + orow) * S + s];
+      const float G = g[s] + dstates[((size_t)b * a.L + orow) * S + s];
+      float d = G * nl_grad_from_out(h, a.update_nonlinear);
+      if (z == 0) d *= o[s];
+      dacc[s] = d;
+      float hp = k > 0 ? states[((size_t)b * a.L + oprev) * S + s] : (z == 0 ? a.h0[s] : a.hT[s]);
+      hprev[s] = z == 0 ? hp : hp * o[s];
+    }
+    __syncthreads();
+    if (z == 0) {
+      // rows s over warps, columns j over lanes: dT[s][j] += hprev[s]*dacc[j]; g_prev[s] = sum_j (T+W)[s][j]*dacc[j]
+      for (int s = warp; s < S; s += kOhWarps) {
+        const float hs = hprev[s];
+        float acc = 0.f;
+        for (int j = lane; j < S; j += 32) {
+          const float dj = dacc[j];
+          acc = fmaf(__ldg(T + (size_t)s * S + j) + __ldg(W + (size_t)s * S + j), dj, acc);
+          const float v = hs * dj;
+          if (v != 0.f) atomicAdd(dT + (size_t)s * S + j, v);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) part[s] = acc;
+      }
+      __syncthreads();
+      for (int s = tid; s < S; s += kOhThreads) g[s] = part[s];
+      __syncthreads();
+    } else {
+      // dT[s][j] += dacc[s]*hh[j]; g_prev[j] = o[j] * sum_s dacc[s]*(T+W)[s][j]: warps stride rows, lanes columns
+      for (int jb = 0; jb < S; jb += 32) {
+        const int j = jb + lane;
+        float acc = 0.f;
+        if (j < S) {
+          const float hj = hprev[j];
+          for (int s = warp; s < S; s += kOhWarps) {
+            const float ds = dacc[s];
+            acc = fmaf(__ldg(T + (size_t)s * S + j) + __ldg(W + (size_t)s * S + j), ds, acc);
+            const float v = ds * hj;
+            if (v != 0.f) atomicAdd(dT + (size_t)s * S + j, v);
+          }
+          part[warp * S + j] = acc;
+        }
+      }
+      __syncthreads();
+      for (int j = tid; j < S; j += kOhThreads) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < kOhWarps; ++w) acc += part[w * S + j];
+        g[j] = acc * o[j];
+      }
+      __syncthreads();
+    }
+  }
+}
+
 }  // namespace re2nn
 
 using namespace re2nn;
+
+extern "C" int re2nn_onehot_backward(const re2nn_onehot_backward_args* a, void* stream) {
+  RE2NN_CHECK(a != nullptr, "onehot_backward: null args");
+  RE2NN_CHECK(a->x && a->lengths && a->language && a->W && a->o && a->h0 && a->hT && a->alpha && a->beta &&
+                  a->dalpha && a->dbeta && a->dlanguage, "onehot_backward: null tensor");
+  const size_t smem = (size_t)(3 + kOhWarps) * a->S * sizeof(float);
+  RE2NN_CHECK(smem <= 220 * 1024, "onehot_backward: S=%d too large", a->S);
+  RE2NN_CUDA(cudaFuncSetAttribute(onehot_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  onehot_backward_kernel<<<dim3(a->B, 2), kOhThreads, smem, (cudaStream_t)stream>>>(*a);
+  RE2NN_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int re2nn_onehot_recurrence(const re2nn_onehot_args* a, void* stream) {
   RE2NN_CHECK(a != nullptr, "onehot_recurrence: null args");

@@ -119,14 +119,14 @@ class _DecomposeBase(nn.Module):
         return names
 
     # ---- decode (model_decompose.py:339-371) ------------------------------------------------------
-    def decode(self, all_scores, flattened_all_scores, mask, lengths, _shape=None):
+    def decode(self, all_scores, flattened_all_scores, mask, lengths, _shape=None, _offsets=None):
         """all_scores B x L x C -> flat predictions N (int64).  `flattened_all_scores` and `mask`
         are accepted for signature compatibility; the kernels address valid positions directly."""
         with torch.no_grad():
             dev = all_scores.device
             lengths = lengths.to(dev).contiguous()
             N = _shape[1] if _shape is not None else int(lengths.sum())
-            offsets = exclusive_offsets(lengths)
+            offsets = exclusive_offsets(lengths) if _offsets is None else _offsets
             ce1 = self.args.local_loss_func == 'CE1'
             sc = all_scores.detach().contiguous()
             if self.use_crf:
@@ -139,11 +139,24 @@ class _DecomposeBase(nn.Module):
         return flat
 
     # ---- loss + decode tail shared by forward_local / forward (model_decompose_single.py:271-304) ---
-    def _finish(self, all_scores, label, lengths, train, re_tags, shape):
+    def _length_order(self, lengths, re_tags):
+        """Process sequences longest-first so 128-row tiles finish together and are skipped once all their rows
+        are done (the reference computes every pad position; only valid positions are observable).  Outputs keep
+        the caller's order: flat predictions are scattered through the original offsets."""
+        if not getattr(self, 'sort_by_length', True) or re_tags is not None or lengths.shape[0] <= 128:
+            return None, None
+        _, order = torch.sort(lengths, descending=True, stable=True)
+        return order, exclusive_offsets(lengths).index_select(0, order)
+
+    def _finish(self, all_scores, label, lengths, train, re_tags, shape, order=None, offsets=None, orig=None):
         L, N = shape
         dev = all_scores.device
         label = label.to(dev)
-        flattened_true_labels = flatten(label[:, :L], lengths)
+        if order is None:
+            flattened_true_labels = flatten(label[:, :L], lengths)
+        else:
+            flattened_true_labels = flatten(label[:, :L], orig)
+            label = label.index_select(0, order)
         loss = None
         if train:
             lab = label.contiguous()
@@ -165,7 +178,7 @@ class _DecomposeBase(nn.Module):
                     kl = PR_loss(all_scores, re_tags[:, :L, :], self.args)
                     pi = max(self.args.c2_kdpr, self.args.c3_pr ** self.t)
                     loss = pi * loss + (1 - pi) * kl
-        pred = self.decode(all_scores, None, None, lengths, _shape=shape)
+        pred = self.decode(all_scores, None, None, lengths, _shape=shape, _offsets=offsets)
         return loss, pred, flattened_true_labels
 
     def _recurrence_consts(self):
@@ -254,8 +267,13 @@ class FARNN_S_D_W_I_S(_DecomposeBase):
         dev = self._device()
         lengths = lengths.to(dev).contiguous()
         shape = self._host_shape(lengths)
-        all_scores = self.forward_scores(input, lengths, shape)
-        return self._finish(all_scores, label, lengths, train, re_tags, shape)
+        order, offsets = self._length_order(lengths, re_tags)
+        if order is None:
+            all_scores = self.forward_scores(input, lengths, shape)
+            return self._finish(all_scores, label, lengths, train, re_tags, shape)
+        ls = lengths.index_select(0, order)
+        all_scores = self.forward_scores(input.to(dev).index_select(0, order), ls, shape)
+        return self._finish(all_scores, label, ls, train, re_tags, shape, order, offsets, lengths)
 
 
 class FARNN_S_SF(_DecomposeBase):
@@ -317,5 +335,10 @@ class FARNN_S_SF(_DecomposeBase):
         dev = self._device()
         lengths = lengths.to(dev).contiguous()
         shape = self._host_shape(lengths)
-        all_scores = self.forward_scores(input, lengths, shape)
-        return self._finish(all_scores, label, lengths, train, re_tags, shape)
+        order, offsets = self._length_order(lengths, re_tags)
+        if order is None:
+            all_scores = self.forward_scores(input, lengths, shape)
+            return self._finish(all_scores, label, lengths, train, re_tags, shape)
+        ls = lengths.index_select(0, order)
+        all_scores = self.forward_scores(input.to(dev).index_select(0, order), ls, shape)
+        return self._finish(all_scores, label, ls, train, re_tags, shape, order, offsets, lengths)

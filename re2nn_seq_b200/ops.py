@@ -8,7 +8,8 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import NL, PREC, V_DENSE, V_TOKEN, BackwardArgs, OnehotArgs, RecurrenceArgs, check, fn
+from ._lib import (NL, PREC, V_DENSE, V_TOKEN, BackwardArgs, OnehotArgs, OnehotBackwardArgs, RecurrenceArgs, check,
+                   fn)
 
 _LAUNCHES = {'n': 0}   # launch counter read by bench.py ("gpu_launches")
 
@@ -327,3 +328,29 @@ def token_table_backward(dvtab, V_embed, E, G, beta_vec, additional_nonlinear, w
         if v is not None:
             out[k] = v
     return out
+
+
+def onehot_backward(x, lengths, L, language, W, o, h0, hT, alpha, beta, dscores, C_mat, pr_mat, update_nonlinear,
+                    full_pad):
+    """d loss / d language_tensor for the sum-semiring onehot recurrence."""
+    B, Lpad = x.shape
+    S = W.shape[0]
+    Cn = C_mat.shape[0]
+    dev = W.device
+    dalpha = torch.empty_like(alpha)
+    dbeta = torch.empty_like(beta)
+    ws = torch.empty((B, L, Cn), dtype=torch.float32, device=dev) if pr_mat is not None else None
+    check(fn['re2nn_label_scores_backward'](_f32(dscores), _f32(alpha), _f32(beta), _i64(lengths), B, L, S, _f32(C_mat),
+                                            Cn, _f32(pr_mat) if pr_mat is not None else None, int(full_pad),
+                                            _f32(dalpha), _f32(dbeta), _f32(ws) if ws is not None else None, _stream()),
+          'label_scores_backward')
+    dlang = torch.zeros_like(language)
+    a = OnehotBackwardArgs()
+    a.B, a.Lpad, a.L, a.S = B, Lpad, L, S
+    a.update_nonlinear, a.full_pad = NL[update_nonlinear], int(full_pad)
+    a.x, a.lengths = _i64(x), _i64(lengths)
+    a.language, a.W, a.o, a.h0, a.hT = _f32(language), _f32(W), _f32(o), _f32(h0), _f32(hT)
+    a.alpha, a.beta, a.dalpha, a.dbeta, a.dlanguage = _f32(alpha), _f32(beta), _f32(dalpha), _f32(dbeta), _f32(dlang)
+    check(fn['re2nn_onehot_backward'](C.byref(a), _stream()), 'onehot_backward')
+    _count(3 if pr_mat is not None else 2)
+    return dlang

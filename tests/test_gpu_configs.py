@@ -122,3 +122,27 @@ def test_full_cfg2_batch_properties():
     z = _Z({'p.' + k: v.detach().cpu().numpy() for k, v in m.state_dict().items()})
     _, o_pred, _, _ = orc.decompose_forward_local(oracle_params(z, np.float32), x[:64], lab[:64], lens[:64], args, 0, False)
     np.testing.assert_array_equal(pred[:offs[64]], o_pred)
+
+
+def test_longest_first_order_is_invisible():
+    """Sorting by length (tile skipping) changes neither predictions, loss nor gradients (up to fp32 summation order)."""
+    m, args, x, lens, lab = _decompose(14, 800, 96, 64, 11, 32, 300, 17, farnn=2, use_crf=1, update_nonlinear='tanh',
+                                       beta=0.1)
+    with torch.no_grad():
+        for n in ('Wss1', 'Wrs1', 'Wss2', 'Wrs2'):
+            getattr(m, n).mul_(0.1)
+    res = []
+    for flag in (True, False):
+        m.sort_by_length = flag
+        for q in m.parameters():
+            q.grad = None
+        loss, pred, true = m.forward_local(_t(x), _t(lab), _t(lens), train=True)
+        loss.backward()
+        res.append((loss.item(), pred.cpu().numpy(), true.cpu().numpy(),
+                    {k: v.grad.cpu().numpy() for k, v in m.named_parameters() if v.requires_grad}))
+    (l1, p1, t1, g1), (l0, p0, t0, g0) = res
+    np.testing.assert_array_equal(p1, p0)
+    np.testing.assert_array_equal(t1, t0)
+    assert abs(l1 - l0) <= 1e-5 * abs(l0)
+    for k in g0:
+        assert rel_err(g1[k], g0[k]) < 2e-5, k

@@ -180,3 +180,22 @@ def test_decompose_gradients_cfg3_shapes_vs_oracle(farnn, crf):
         ref = g64[rename.get(k, k)]
         err = rel_err(v.grad.cpu().numpy(), ref)
         assert err < 1e-4, '%s: rel err %.3e' % (k, err)
+
+
+@pytest.mark.parametrize('name', golden_files('one_'))
+def test_onehot_gradients_golden(name):
+    """train_onehot.py trains language_tensor with CE: its gradient through the CUDA backward vs the reference."""
+    z, meta = load_golden(name)
+    m = build_module(name, z, meta)
+    x, lab, lens = torch.from_numpy(z['x']), torch.from_numpy(z['labels']), torch.from_numpy(z['lengths'])
+    loss, _, _ = m.forward_local(x, lab, lens, train=True)
+    assert rel_err(loss.item(), z['loss']) < TOL
+    if meta['flags'].get('train_mode') == 'max':
+        with pytest.raises(NotImplementedError):
+            loss.backward()
+        return
+    loss.backward()
+    gold = golden_grads(z)
+    assert list(gold) == ['language_tensor']
+    err = rel_err(m.language_tensor.grad.cpu().numpy(), gold['language_tensor'])
+    assert err < 2e-4, err
