@@ -134,6 +134,12 @@ typedef struct re2nn_recurrence_args {
 size_t re2nn_decompose_recurrence_workspace(const re2nn_recurrence_args* a);
 int re2nn_decompose_recurrence(const re2nn_recurrence_args* a, void* stream);
 
+/* Same recurrence under the max-product semiring (train_mode == 'max': model_decompose_single.py:159-166,
+ * utils.py:192-195).  Takes the same argument block (precision ignored: fp32; save_for_backward must be 0);
+ * ws >= re2nn_decompose_max_workspace(S, R) bytes.  Inference only. */
+size_t re2nn_decompose_max_workspace(int S, int R);
+int re2nn_decompose_max_recurrence(const re2nn_recurrence_args* a, void* stream);
+
 /* ---- decompose i-FST backward (BPTT through both directions + label scores) ---------------------------
  * replaces torch.autograd over forward_local (train_decompose.py:192).  Input: d loss / d all_scores.
  * Outputs: gradients of every parameter the reference trains (NULL pointer = not wanted).

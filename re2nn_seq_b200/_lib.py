@@ -95,6 +95,8 @@ SYMBOLS = {
     're2nn_decompose_backward': (C.c_int, [C.POINTER(BackwardArgs), vp]),
     're2nn_token_table_backward_workspace': (sz, [C.c_int, C.c_int, C.c_int]),
     're2nn_token_table_backward': (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, sz, vp]),
+    're2nn_decompose_max_workspace': (sz, [C.c_int, C.c_int]),
+    're2nn_decompose_max_recurrence': (C.c_int, [C.POINTER(RecurrenceArgs), vp]),
     're2nn_onehot_recurrence': (C.c_int, [C.POINTER(OnehotArgs), vp]),
     're2nn_onehot_backward': (C.c_int, [C.POINTER(OnehotBackwardArgs), vp]),
     're2nn_label_scores_backward': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp]),

@@ -41,16 +41,20 @@ class _DecomposeScores(torch.autograd.Function):
         p = {n: t.detach().contiguous() for n, t in zip(names, tensors)}
         need_grad = consts['grad_on'] and (any(ctx.needs_input_grad[8:]) or
                                            (dense_v is not None and ctx.needs_input_grad[4]))
+        mx = consts.get('max_semiring', False)
+        ctx.max_semiring = mx
+        if mx:
+            need_grad = False        # inference-only semiring; backward raises
         vtab, gtab, o = _prepare(consts, p, dense_v, None if need_grad else cache)
         Lpad = x.shape[1] if dense_v is None else dense_v.shape[1]
         alpha, beta, saves = ops.decompose_recurrence(
             x, lengths, L, vtab, gtab, p['S1'], p['S2'], p['wildcard_mat'], o, p['h0'], p['hT'],
             p.get('Wss1'), p.get('Wss2'), consts['farnn'], consts['update_nonlinear'], consts['sigmoid_exponent'],
             precision=consts['precision'], v_mode=V_TOKEN if dense_v is None else V_DENSE,
-            full_pad=consts['full_pad'], save_for_backward=need_grad, Lpad=Lpad)
+            full_pad=consts['full_pad'], save_for_backward=need_grad, Lpad=Lpad, max_semiring=mx)
         pm, pb = (pr if consts['use_priority'] else (None, None))
         scores = ops.label_scores(alpha, beta, lengths, p['C_output_mat'], pm, pb, full_pad=consts['full_pad'],
-                                  precision=consts['precision'])
+                                  precision='fp32' if mx else consts['precision'])
         if need_grad:
             ctx.consts, ctx.names, ctx.pr, ctx.L = consts, names, pr, L
             ctx.saved = (p, x, dense_v, lengths, vtab, gtab, o, alpha, beta, saves)
@@ -59,6 +63,8 @@ class _DecomposeScores(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dscores):
         from . import backward as bw
+        if ctx.max_semiring:
+            raise NotImplementedError("re2nn_b200: train_mode='max' (max-product semiring) is inference-only")
         grads = bw.decompose_backward(ctx, dscores.contiguous())
         dense_g = grads.pop('__dense_v__', None)
         out = [None, None, None, None, dense_g, None, None, None]

@@ -183,9 +183,7 @@ class _DecomposeBase(nn.Module):
 
     def _recurrence_consts(self):
         a = self.args
-        if a.train_mode == 'max':
-            raise NotImplementedError("re2nn_b200: train_mode='max' is not built for the decompose path yet")
-        return dict(farnn=a.farnn, update_nonlinear=_nl_name(a.update_nonlinear, _UPDATE_NL),
+        return dict(farnn=a.farnn, max_semiring=(a.train_mode == 'max'), update_nonlinear=_nl_name(a.update_nonlinear, _UPDATE_NL),
                     sigmoid_exponent=float(a.sigmoid_exponent), precision=self.precision,
                     ce1=(a.local_loss_func == 'CE1'), use_priority=bool(a.use_priority),
                     additional_nonlinear=_nl_name(a.additional_nonlinear, _ADD_NL),

@@ -85,7 +85,7 @@ def output_vector_sum(C_mat, wildcard_vec=None):
 
 def decompose_recurrence(x, lengths, L, vtab, gtab, S1, S2, W, o, h0, hT, Wss1, Wss2, farnn,
                          update_nonlinear, sigmoid_exponent, precision='fp32', v_mode=V_TOKEN,
-                         full_pad=False, save_for_backward=False, Lpad=None):
+                         full_pad=False, save_for_backward=False, Lpad=None, max_semiring=False):
     """Returns (alpha, beta, saves): alpha/beta B x L x S (pad rows undefined); saves = per-step slabs or None."""
     B = lengths.shape[0]
     S, R = S1.shape
@@ -115,6 +115,13 @@ def decompose_recurrence(x, lengths, L, vtab, gtab, S1, S2, W, o, h0, hT, Wss1, 
     a.Wss1 = _f32(Wss1) if Wss1 is not None else None
     a.Wss2 = _f32(Wss2) if Wss2 is not None else None
     a.alpha, a.beta = _f32(alpha), _f32(beta)
+    if max_semiring:
+        need = fn['re2nn_decompose_max_workspace'](S, R)
+        ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+        a.ws, a.ws_bytes = C.c_void_p(ws.data_ptr()), need
+        check(fn['re2nn_decompose_max_recurrence'](C.byref(a), _stream()), 'decompose_max_recurrence')
+        _count(3)
+        return alpha, beta, saves
     need = fn['re2nn_decompose_recurrence_workspace'](C.byref(a))
     ws = torch.empty((need,), dtype=torch.uint8, device=dev)
     a.ws, a.ws_bytes = C.c_void_p(ws.data_ptr()), need

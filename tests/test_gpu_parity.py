@@ -25,8 +25,6 @@ DEC = [n for n in golden_files('dec_') + golden_files('sf_')]
 @pytest.mark.parametrize('name', DEC)
 def test_decompose_golden(name):
     z, meta = load_golden(name)
-    if meta['flags'].get('train_mode') == 'max':
-        pytest.skip("train_mode='max' decompose path not built yet")
     m = build_module(name, z, meta).cuda()
     x, lab, lens = _t(z['x']), _t(z['labels']), _t(z['lengths'])
     inp = _t(z['dense_v']) if meta['kind'] == 'sf' else x
