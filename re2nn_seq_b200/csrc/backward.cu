@@ -223,7 +223,7 @@ __global__ void bwd_e1_kernel(const BwdCtx c) {
       continue;
     }
     const float* dout = z == 0 ? c.dalpha : c.dbeta;
-    const float G = c.g[(size_t)z * c.B * c.S + e] + dout[((size_t)b * c.L + orow) * c.S + s];
+    const float G = c.g[(size_t)z * c.B * c.S + e] + (orow >= 0 ? dout[((size_t)b * c.L + orow) * c.S + s] : 0.f);
     const float a = c.a_save[sl];
     const float on = c.o[s];
     const float hhat = apply_nl(z == 0 ? a * on : a, c.nl);

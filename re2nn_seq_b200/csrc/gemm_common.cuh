@@ -140,7 +140,7 @@ template <int PREC> struct EpiQ {
   }
   __device__ __forceinline__ void apply(const Col&, const RowCtx& r, int m, int n, float acc, const Pre& pre) const {
     OperandFmt<PREC>::store(p.Q[0], (uint32_t)m * (uint32_t)p.ldq + (uint32_t)n, p.q_plane, acc * pre.a);
-    if (p.Usave[0]) p.Usave[0][(uint32_t)m * (uint32_t)p.R + (uint32_t)n] = r.orow >= 0 ? acc : 0.f;
+    if (p.Usave[0]) p.Usave[0][(uint32_t)m * (uint32_t)p.R + (uint32_t)n] = r.alive ? acc : 0.f;
   }
 };
 
@@ -171,7 +171,7 @@ template <int PREC, int NL = -1, int FARNN = -1> struct EpiH {
     const uint32_t si = (uint32_t)m * (uint32_t)p.S + (uint32_t)n;
     if (farnn() >= 1) hnew = (1.f - pre.a) * pre.b + pre.a * hn;
     if (p.Asave[0]) {   // training: keep what BPTT needs; rows that are finished hold exact zeros
-      const bool live = r.orow >= 0;
+      const bool live = r.alive;          // note: a live row may have no output row (backward direction, beta_0)
       p.Asave[0][si] = live ? acc : 0.f;
       if (!live) hnew = 0.f;
       p.HstNext[0][si] = hnew;

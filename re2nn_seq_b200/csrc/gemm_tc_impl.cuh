@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
       RowCtx mine{0, -1, false};
       if (mrow0 + lane < L.M) mine = epi.row(mrow0 + lane);
       ctx[lane] = mine.vrow;
-      ctx[32 + lane] = mine.orow;
+      ctx[32 + lane] = mine.orow;   // (alive is only consumed by the fp32 training path; here alive <=> orow >= 0 or unused)
     }
     __syncwarp();
     const int nrows = min(32, L.M - mrow0);

@@ -53,7 +53,7 @@ def _randomise_trainables(model, seed, names):
             t.add_(torch.randn(t.shape, generator=g) * scale)
 
 
-def decompose_case(name, seed, dims, flags, sf=False, priority=False):
+def decompose_case(name, seed, dims, flags, sf=False, priority=False, marry=False):
     V, S, R, C, D, B, Lmax = dims
     args = synth.make_args(**flags)
     f = synth.make_decompose_factors(seed, V, S, R, C, D, lang_frac=0.5)
@@ -107,6 +107,11 @@ def decompose_case(name, seed, dims, flags, sf=False, priority=False):
         vecs = (rs.randn(B, Lmax, R) / np.sqrt(R)).astype(np.float32)
         out['dense_v'] = vecs
         loss, pred, true = model(torch.from_numpy(vecs), yt, lt, True)
+    elif marry:
+        rs = np.random.RandomState(seed + 5)
+        re_tags = rs.rand(B, Lmax, C).astype(np.float32)              # teacher scores, B x L x C (RE.py output)
+        out['re_tags'] = re_tags
+        loss, pred, true = model.forward_local(xt, yt, lt, train=True, re_tags=torch.from_numpy(re_tags))
     else:
         loss, pred, true = model.forward_local(xt, yt, lt, train=True)
     loss.backward()
@@ -201,6 +206,10 @@ def main():
                                                         local_loss_func='CE', additional_nonlinear='relu', **tr_all))
     decompose_case('dec_f2_none_crf_relutanh', 18, dims, dict(farnn=2, update_nonlinear='none', use_crf=1, beta=0.1,
                                                             additional_nonlinear='relutanh', train_c_output=1))
+    decompose_case('dec_f0_tanh_ce_kd', 21, dims, dict(farnn=0, update_nonlinear='tanh', use_crf=0, beta=0.3,
+                                                     marryup_type='kd', c1_kdpr=2.0, c2_kdpr=0.4), marry=True)
+    decompose_case('dec_f2_tanh_crf_pr', 22, dims, dict(farnn=2, update_nonlinear='tanh', use_crf=1, beta=0.2,
+                                                      marryup_type='pr', c1_kdpr=1.5, c2_kdpr=0.3, c3_pr=0.9), marry=True)
     decompose_case('sf_f2_tanh_crf', 19, dims, dict(farnn=2, update_nonlinear='tanh', use_crf=1), sf=True)
     decompose_case('sf_f0_relu_ce', 20, dims, dict(farnn=0, update_nonlinear='relu', use_crf=0), sf=True)
     odims = (25, 11, 4, 6, 8)          # V, S, C, B, Lmax

@@ -28,12 +28,17 @@ def test_decompose_golden(name):
     m = build_module(name, z, meta).cuda()
     x, lab, lens = _t(z['x']), _t(z['labels']), _t(z['lengths'])
     inp = _t(z['dense_v']) if meta['kind'] == 'sf' else x
+    re_tags = _t(z['re_tags']) if 're_tags' in z.files else None
     with torch.no_grad():
         scores = m.forward_scores(inp, lens)
         if meta['kind'] == 'sf':
             loss, pred, true = m(inp, lab, lens, True)
         else:
-            loss, pred, true = m.forward_local(inp, lab, lens, train=True)
+            loss, pred, true = m.forward_local(inp, lab, lens, train=True, re_tags=re_tags)
+        m.full_pad = True                                   # reference semantics at pad positions
+        full = m.forward_scores(inp, lens).cpu().numpy()
+        m.full_pad = False
+    assert rel_err(full, z['all_scores']) < TOL            # every position, pads included
     L = int(z['lengths'].max())
     mask = orc.length_mask(z['lengths'], L)
     got = scores.cpu().numpy()
@@ -141,7 +146,8 @@ def test_decompose_gradients_golden(name):
     if meta['kind'] == 'sf':
         loss, _, _ = m(_t(z['dense_v']), lab, lens, True)
     else:
-        loss, _, _ = m.forward_local(x, lab, lens, train=True)
+        re_tags = _t(z['re_tags']) if 're_tags' in z.files else None      # KD / PR: scores at pads feed the loss
+        loss, _, _ = m.forward_local(x, lab, lens, train=True, re_tags=re_tags)
     assert rel_err(loss.item(), z['loss']) < TOL
     loss.backward()
     gold = golden_grads(z)
