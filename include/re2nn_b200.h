@@ -38,7 +38,9 @@ enum { RE2NN_NL_NONE = 0, RE2NN_NL_RELU = 1, RE2NN_NL_TANH = 2, RE2NN_NL_RELUTAN
 enum {
   RE2NN_PREC_FP32 = 0,      /* fp32 FFMA on CUDA cores: bit-for-bit the reference's operand precision */
   RE2NN_PREC_BF16 = 1,      /* tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM */
-  RE2NN_PREC_TF32X3 = 2     /* tcgen05 kind::tf32, 3-term split (hi*hi + hi*lo + lo*hi): fp32-grade */
+  RE2NN_PREC_TF32X3 = 2,    /* tcgen05 kind::tf32, 3-term split (hi*hi + hi*lo + lo*hi): fp32-grade */
+  RE2NN_PREC_FP16X3 = 3     /* tcgen05 kind::f16 on fp16 planes hi + 2^-11*lo (same 22-bit budget as TF32X3 at half
+                               the operand bytes); operands must stay below 65504 in magnitude */
 };
 /* how the per-step rank factor v_t is addressed */
 enum {

@@ -20,7 +20,7 @@ lib = C.CDLL(LIB_PATH)
 vp, i32, i64, f32, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 
 NL = {'none': 0, 'relu': 1, 'tanh': 2, 'relutanh': 3, 'sigmoid': 4}
-PREC = {'fp32': 0, 'bf16': 1, 'tf32x3': 2}
+PREC = {'fp32': 0, 'bf16': 1, 'tf32x3': 2, 'fp16x3': 3}
 V_TOKEN, V_DENSE = 0, 1
 
 

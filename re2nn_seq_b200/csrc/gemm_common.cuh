@@ -4,6 +4,7 @@
 // and hands every accumulator element to an epilogue functor instead of writing C.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -48,14 +49,28 @@ template <> struct OperandFmt<RE2NN_PREC_TF32X3> {
     ((float*)base)[idx + plane] = tf32_hi(v - hi);
   }
 };
+// fp16 split: v = hi + lo * 2^-11 with hi = fp16(v), lo = fp16((v - hi) * 2^11): 22 mantissa bits in 4 bytes.
+// The residual is kept scaled so it stays a normal fp16 number; its products go to a second accumulator that
+// the epilogue folds in with the 2^-11 factor.
+constexpr float kFp16LoScale = 2048.f;
+template <> struct OperandFmt<RE2NN_PREC_FP16X3> {
+  static constexpr int kElemBytes = 2, kPlanes = 2, kLdAlign = 8;
+  __device__ static __forceinline__ void store(void* base, size_t idx, size_t plane, float v) {
+    const __half hi = __float2half_rn(v);
+    ((__half*)base)[idx] = hi;
+    ((__half*)base)[idx + plane] = __float2half_rn((v - __half2float(hi)) * kFp16LoScale);
+  }
+};
+inline bool prec_is_16bit(int prec) { return prec == RE2NN_PREC_BF16 || prec == RE2NN_PREC_FP16X3; }
+inline bool prec_is_split(int prec) { return prec == RE2NN_PREC_TF32X3 || prec == RE2NN_PREC_FP16X3; }
 inline int operand_ld(int prec, int K) {
-  int a = prec == RE2NN_PREC_BF16 ? 8 : (prec == RE2NN_PREC_TF32X3 ? 4 : 1);
+  int a = prec_is_16bit(prec) ? 8 : (prec == RE2NN_PREC_TF32X3 ? 4 : 1);
   return (K + a - 1) / a * a;
 }
 inline size_t operand_bytes(int prec, size_t rows, int K) {
   size_t ld = operand_ld(prec, K);
-  size_t eb = prec == RE2NN_PREC_BF16 ? 2 : 4;
-  size_t planes = prec == RE2NN_PREC_TF32X3 ? 2 : 1;
+  size_t eb = prec_is_16bit(prec) ? 2 : 4;
+  size_t planes = prec_is_split(prec) ? 2 : 1;
   return align_up(rows * ld * eb * planes, 256);
 }
 

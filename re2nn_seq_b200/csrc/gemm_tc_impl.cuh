@@ -19,7 +19,7 @@ namespace re2nn {
 constexpr int kTcMaxMaps = 16;
 constexpr int kTcMaxSeg = 6;
 
-struct TcSeg { int a_map, b_map, kblocks; };
+struct TcSeg { int a_map, b_map, a_lo, b_lo, kblocks; };   // *_lo: TF32X3 residual planes (else -1)
 struct __align__(64) TcLaunch {
   CUtensorMap maps[kTcMaxMaps];
   TcSeg seg[2][kTcMaxSeg];
@@ -50,6 +50,9 @@ template <int PREC>
 inline int make_operand_map(CUtensorMap* m, const void* base, size_t elem_off, int rows, int K, int ld, int box_rows) {
   PFN_tmapEncodeTiled enc = tmap_encoder();
   RE2NN_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  const CUtensorMapDataType dt = PREC == RE2NN_PREC_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                 : PREC == RE2NN_PREC_FP16X3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                             : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   constexpr int eb = OperandFmt<PREC>::kElemBytes;
   const char* addr = (const char*)base + elem_off * eb;
   cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -57,7 +60,7 @@ inline int make_operand_map(CUtensorMap* m, const void* base, size_t elem_off, i
   cuuint32_t box[2] = {(cuuint32_t)(128 / eb), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   RE2NN_CHECK(((uintptr_t)addr & 15) == 0 && (gstride[0] & 15) == 0, "tensor map: operand not 16-byte aligned");
-  CUresult r = enc(m, PREC == RE2NN_PREC_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+  CUresult r = enc(m, dt, 2,
                    (void*)addr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   RE2NN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%d box_rows=%d", (int)r, rows, K,
@@ -67,7 +70,7 @@ inline int make_operand_map(CUtensorMap* m, const void* base, size_t elem_off, i
 
 // n-tile width: the step GEMMs are bound by shared-memory ingest (~64 B/clk/SM), so pick the split of N that
 // minimises bytes per SM: waves(m_tiles * nt CTAs over 148 SMs) * (A tile 16 KB + B tile bn * 128 B) per k-block.
-inline void tc_pick_bn(int M, int N, int ndir, int* bn_out, int* BN_out) {
+inline void tc_pick_bn(int M, int N, int ndir, int planes, int* bn_out, int* BN_out) {
   const long mt = (long)cdiv(M, 128) * ndir;
   double best = 1e30;
   int best_bn = 64;
@@ -76,11 +79,11 @@ inline void tc_pick_bn(int M, int N, int ndir, int* bn_out, int* BN_out) {
     if (bn > 256) continue;
     if (nt > 1 && bn * (nt - 1) >= N) continue;            // a narrower split already covers N
     const int cls = bn <= 64 ? 64 : (bn <= 128 ? 128 : 256);
-    const int per_sm = cls == 256 ? 1 : 2;                  // CTAs resident per SM (smem / registers)
+    const int per_sm = (cls == 256 || (planes == 2 && cls == 128)) ? 1 : 2;   // CTAs resident per SM (smem / registers)
     const long ctas = mt * nt;
     const double waves = (double)((ctas + 148L * per_sm - 1) / (148L * per_sm));
     const double conc = (double)std::min<long>(per_sm, (ctas + 147) / 148);   // CTAs sharing one SM's ingest
-    const double cost = waves * conc * (16384.0 + bn * 128.0) + 2000.0 * waves;
+    const double cost = waves * conc * planes * (16384.0 + bn * 128.0) + 2000.0 * waves;
     if (cost < best - 1e-9) { best = cost; best_bn = bn; }
   }
   *bn_out = best_bn;
@@ -92,7 +95,7 @@ template <int PREC>
 inline int tc_make_launch(const GemmProblem& g, TcLaunch* out) {
   memset(out, 0, sizeof(*out));
   out->M = g.M; out->N = g.N; out->ndir = g.ndir;
-  tc_pick_bn(g.M, g.N, g.ndir, &out->bn, &out->BN);
+  tc_pick_bn(g.M, g.N, g.ndir, OperandFmt<PREC>::kPlanes, &out->bn, &out->BN);
   constexpr int kpb = 128 / OperandFmt<PREC>::kElemBytes;   // K elements per 128-byte block
   int nm = 0;
   for (int z = 0; z < g.ndir; ++z) {
@@ -106,15 +109,14 @@ inline int tc_make_launch(const GemmProblem& g, TcLaunch* out) {
       if (int rc = make_operand_map<PREC>(&out->maps[a_hi], sg.A, 0, g.M, sg.K, sg.lda, 128)) return rc;
       const int b_hi = nm++;
       if (int rc = make_operand_map<PREC>(&out->maps[b_hi], sg.B, 0, g.N, sg.K, sg.ldb, out->bn)) return rc;
-      out->seg[z][ns++] = TcSeg{a_hi, b_hi, kb};
-      if (PREC == RE2NN_PREC_TF32X3) {
-        const int a_lo = nm++;
+      int a_lo = -1, b_lo = -1;
+      if (OperandFmt<PREC>::kPlanes == 2) {
+        a_lo = nm++;
         if (int rc = make_operand_map<PREC>(&out->maps[a_lo], sg.A, sg.a_plane, g.M, sg.K, sg.lda, 128)) return rc;
-        const int b_lo = nm++;
+        b_lo = nm++;
         if (int rc = make_operand_map<PREC>(&out->maps[b_lo], sg.B, sg.b_plane, g.N, sg.K, sg.ldb, out->bn)) return rc;
-        out->seg[z][ns++] = TcSeg{a_lo, b_hi, kb};
-        out->seg[z][ns++] = TcSeg{a_hi, b_lo, kb};
       }
+      out->seg[z][ns++] = TcSeg{a_hi, b_hi, a_lo, b_lo, kb};
     }
     out->nseg = ns;
   }
@@ -194,11 +196,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int BN> struct TcCfg {
-  static constexpr int kStages = BN == 64 ? 3 : (BN == 128 ? 3 : 4);
-  static constexpr int kABytes = 128 * 128;
-  static constexpr int kBBytes = BN * 128;
+// One pipeline stage holds, per 128-byte k-block: the A tile (128 rows) and the B tile (BN rows); the 3xTF32
+// path keeps the residual ("lo") planes next to them so each operand byte is fetched once and feeds
+// three MMAs (hi*hi, lo*hi, hi*lo).
+template <int PREC, int BN> struct TcCfg {
+  static constexpr int kPlanes = OperandFmt<PREC>::kPlanes;
+  static constexpr int kAccs = PREC == RE2NN_PREC_FP16X3 ? 2 : 1;   // fp16 split keeps the residual products apart
+  static constexpr int kATile = 128 * 128;
+  static constexpr int kBTile = BN * 128;
+  static constexpr int kABytes = kATile * kPlanes;
+  static constexpr int kBBytes = kBTile * kPlanes;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = kPlanes == 1 ? (BN == 128 ? 3 : 4) : (BN == 128 ? 3 : 2);
   static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 128 /*barriers*/ + 2048 /*row ctx*/;
 };
 
@@ -213,8 +222,10 @@ constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;
 
 template <int PREC, int BN, class Epi>
 __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_constant__ TcLaunch L, const Epi epi_in) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<PREC, BN>;
   constexpr bool TF32 = PREC == RE2NN_PREC_TF32X3;
+  constexpr bool SPLIT = Cfg::kPlanes == 2;
+  constexpr bool TWOACC = Cfg::kAccs == 2;
   const int z = blockIdx.z;
   const int bn = L.bn;
   const int m0 = blockIdx.x * 128, n0 = blockIdx.y * bn;
@@ -244,6 +255,10 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
     for (int s = 0; s < nseg; ++s) {
       tma_prefetch_desc(&L.maps[L.seg[z][s].a_map]);
       tma_prefetch_desc(&L.maps[L.seg[z][s].b_map]);
+      if (SPLIT) {
+        tma_prefetch_desc(&L.maps[L.seg[z][s].a_lo]);
+        tma_prefetch_desc(&L.maps[L.seg[z][s].b_lo]);
+      }
     }
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), 1);
@@ -253,7 +268,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)(BN * Cfg::kAccs)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
@@ -275,16 +291,20 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
           const uint32_t ph = (it / Cfg::kStages) & 1;
           mbar_wait(empty_bar(st), ph ^ 1);
           const uint32_t sa = base + st * Cfg::kStageBytes;
-          mbar_expect_tx(full_bar(st), (uint32_t)(Cfg::kABytes + bn * 128));
+          mbar_expect_tx(full_bar(st), (uint32_t)(Cfg::kPlanes * (Cfg::kATile + bn * 128)));
           tma_load_2d(sa, ma, full_bar(st), kb * kpb, m0);
           tma_load_2d(sa + Cfg::kABytes, mb, full_bar(st), kb * kpb, n0);
+          if (SPLIT) {
+            tma_load_2d(sa + Cfg::kATile, &L.maps[sg.a_lo], full_bar(st), kb * kpb, m0);
+            tma_load_2d(sa + Cfg::kABytes + Cfg::kBTile, &L.maps[sg.b_lo], full_bar(st), kb * kpb, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // instruction descriptor: D=f32, A/B = bf16 (1) or tf32 (2), both K-major, N>>3, M>>4
-      const uint32_t fmt = TF32 ? 2u : 1u;
+      const uint32_t fmt = TF32 ? 2u : (PREC == RE2NN_PREC_FP16X3 ? 0u : 1u);   // 0 = f16, 1 = bf16, 2 = tf32
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((128u >> 4) << 24);
       for (int it = 0; it < total_kb; ++it) {
         const int st = it % Cfg::kStages;
@@ -297,6 +317,15 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // 4 x 32-byte K steps per 128-byte block (16 bf16 / 8 tf32 each)
           tc_mma<TF32>(tmem_acc, da + 2u * k, db + 2u * k, idesc, (it | k) != 0 ? 1u : 0u);
+        if (SPLIT) {   // residual terms: lo*hi and hi*lo (lo*lo is below fp32 resolution)
+          const uint64_t dal = make_smem_desc(sa + Cfg::kATile), dbl = make_smem_desc(sa + Cfg::kABytes + Cfg::kBTile);
+          const uint32_t acc_lo = TWOACC ? tmem_acc + (uint32_t)BN : tmem_acc;   // fp16 split: scaled residual accumulator
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            tc_mma<TF32>(acc_lo, dal + 2u * k, db + 2u * k, idesc, TWOACC ? ((it | k) != 0 ? 1u : 0u) : 1u);
+            tc_mma<TF32>(acc_lo, da + 2u * k, dbl + 2u * k, idesc, 1u);
+          }
+        }
         tc_commit(empty_bar(st));     // frees the smem slot once these MMAs have read it
       }
       tc_commit(tmem_full);           // accumulator complete
@@ -346,8 +375,16 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
       }
       uint32_t r[32];
       tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      if (TWOACC) {
+        uint32_t r2[32];
+        tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), r2);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j)
+          tbuf[lane * 33 + j] = fmaf(__uint_as_float(r2[j]), 1.f / kFp16LoScale, __uint_as_float(r[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
+      }
       __syncwarp();
       // phase 2: lane = column, loop over rows: every store is a contiguous row segment
 #pragma unroll
@@ -368,13 +405,13 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
   if (threadIdx.x == 0) tc_stamp(trace, 7);
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)(BN * Cfg::kAccs)));
   }
 }
 
 template <int PREC, int BN, class Epi>
 inline cudaError_t launch_tc_bn(const TcLaunch& L, const Epi& epi, cudaStream_t st) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<PREC, BN>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<PREC, BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);

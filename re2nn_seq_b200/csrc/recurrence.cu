@@ -367,6 +367,9 @@ int re2nn_decompose_recurrence(const re2nn_recurrence_args* a, void* stream) {
     case RE2NN_PREC_TF32X3:
       RE2NN_CHECK(re2nn_has_tcgen05(), "decompose_recurrence: tcgen05 path needs an sm_100 device");
       return run_recurrence<RE2NN_PREC_TF32X3>(*a, st);
+    case RE2NN_PREC_FP16X3:
+      RE2NN_CHECK(re2nn_has_tcgen05(), "decompose_recurrence: tcgen05 path needs an sm_100 device");
+      return run_recurrence<RE2NN_PREC_FP16X3>(*a, st);
     default: return set_error("decompose_recurrence: unknown precision %d", a->precision);
   }
 }
@@ -392,6 +395,7 @@ int re2nn_gemm_nt(int precision, const float* A, const float* B, int M, int N, i
   RE2NN_CHECK(ws && ws_bytes >= re2nn_gemm_nt_workspace(precision, M, N, K), "gemm_nt: workspace too small");
   if (precision == RE2NN_PREC_BF16) return gemm_nt_tc<RE2NN_PREC_BF16>(A, B, M, N, K, C, ws, st);
   if (precision == RE2NN_PREC_TF32X3) return gemm_nt_tc<RE2NN_PREC_TF32X3>(A, B, M, N, K, C, ws, st);
+  if (precision == RE2NN_PREC_FP16X3) return gemm_nt_tc<RE2NN_PREC_FP16X3>(A, B, M, N, K, C, ws, st);
   return set_error("gemm_nt: unknown precision %d", precision);
 }
 
@@ -454,7 +458,9 @@ int re2nn_label_scores(const float* alpha, const float* beta, const int64_t* len
     RE2NN_CHECK(re2nn_has_tcgen05(), "label_scores: tcgen05 path needs an sm_100 device");
     int rc = precision == RE2NN_PREC_BF16
                  ? label_scores_tc<RE2NN_PREC_BF16>(alpha, beta, lengths, B, L, S, C_mat, C, full_pad, raw, wp, st)
-                 : label_scores_tc<RE2NN_PREC_TF32X3>(alpha, beta, lengths, B, L, S, C_mat, C, full_pad, raw, wp, st);
+                 : precision == RE2NN_PREC_FP16X3
+                       ? label_scores_tc<RE2NN_PREC_FP16X3>(alpha, beta, lengths, B, L, S, C_mat, C, full_pad, raw, wp, st)
+                       : label_scores_tc<RE2NN_PREC_TF32X3>(alpha, beta, lengths, B, L, S, C_mat, C, full_pad, raw, wp, st);
     if (rc) return rc;
   }
   if (priority_mat) {

@@ -19,7 +19,7 @@ def _need_tc():
         pytest.skip('no tcgen05 device')
 
 
-@pytest.mark.parametrize('prec,tol', [('fp32', 2e-6), ('tf32x3', 2e-5), ('bf16', 1.5e-2)])
+@pytest.mark.parametrize('prec,tol', [('fp32', 2e-6), ('tf32x3', 2e-5), ('fp16x3', 2e-5), ('bf16', 1.5e-2)])
 @pytest.mark.parametrize('M,N,K', SHAPES)
 def test_gemm_nt(prec, tol, M, N, K):
     from re2nn_seq_b200 import ops
@@ -42,7 +42,7 @@ def test_gemm_nt_exact_integers():
     A = torch.randint(-3, 4, (300, 200), generator=g).float().cuda()
     B = torch.randint(-3, 4, (150, 200), generator=g).float().cuda()
     ref = (A.double() @ B.double().t()).float()
-    for prec in ('bf16', 'tf32x3'):
+    for prec in ('bf16', 'tf32x3', 'fp16x3'):
         C = ops.gemm_nt(A, B, prec)
         assert torch.equal(C, ref), prec
 
@@ -62,8 +62,9 @@ def _truth(m, args, x, lens):
     return sc, z
 
 
+@pytest.mark.parametrize('mode', ['tf32x3', 'fp16x3'])
 @pytest.mark.parametrize('farnn', [0, 2])
-def test_recurrence_tf32x3_matches_fp32_tolerance(farnn):
+def test_recurrence_tf32x3_matches_fp32_tolerance(farnn, mode):
     _need_tc()
     m, args, x, lens, lab = _model(farnn, 1)
     truth, z = _truth(m, args, x, lens)
@@ -73,7 +74,7 @@ def test_recurrence_tf32x3_matches_fp32_tolerance(farnn):
         m.precision = 'fp32'
         s32 = m.forward_scores(xt, lt).cpu().numpy()
         _, p32, _ = m.forward_local(xt, yt, lt, train=False)
-        m.precision = 'tf32x3'
+        m.precision = mode
         s3 = m.forward_scores(xt, lt).cpu().numpy()
         _, p3, _ = m.forward_local(xt, yt, lt, train=False)
     assert rel_err(s32[mask], truth[mask]) < 1e-5
