@@ -63,6 +63,9 @@ int re2nn_profile_enable(int on);
  * tcgen05 step-GEMM launch (entry, alive-check, setup, MMAs issued, prefetch issued, accumulator ready,
  * epilogue done, exit, then arrival time of the first 24 k-blocks); slot = 32 * linear CTA id. */
 int re2nn_debug_set_tc_trace(unsigned long long* device_buf);
+/* debug: per-launch timeline: buf[2*i], buf[2*i+1] = %globaltimer (ns) at entry / exit of CTA (0,0,0) of the i-th
+ * tcgen05 step-GEMM launch since the call (up to 4096 launches); NULL clears. */
+int re2nn_debug_set_tc_timeline(unsigned long long* device_buf);
 int re2nn_profile_read(double* ms_out_host, int64_t* count_out_host);
 
 /* ---- stand-alone GEMM through the step-GEMM mainloops (unit-test / calibration entry) -------------------
@@ -238,6 +241,11 @@ int re2nn_label_scores(const float* alpha, const float* beta, const int64_t* len
 int re2nn_argmax_decode(const float* scores, const int64_t* lengths, const int64_t* offsets,
                         int B, int L, int C, int clamp_col, float threshold, int64_t o_idx,
                         int64_t* flat_pred, int64_t* padded_pred, void* stream);
+
+/* flat[offsets[b] + t] = padded[b, t] for t < lengths[b]: utils.py:153-164 `flatten` for int64 labels, without
+ * the Python loop over the batch (padded rows have stride Lrow, the first L columns are considered). */
+int re2nn_flatten_i64(const int64_t* padded, const int64_t* lengths, const int64_t* offsets, int B, int Lrow,
+                      int L, int64_t* flat, void* stream);
 
 /* ---- CRF Viterbi ------------------------------------------------------------------------------------
  * replaces CRF._viterbi_decode (baselines/crf.py:102-195) plus decode()'s CRF branch

@@ -83,6 +83,7 @@ SYMBOLS = {
     're2nn_has_tcgen05': (C.c_int, []),
     're2nn_profile_enable': (C.c_int, [C.c_int]),
     're2nn_debug_set_tc_trace': (C.c_int, [vp]),
+    're2nn_debug_set_tc_timeline': (C.c_int, [vp]),
     're2nn_profile_read': (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     're2nn_gemm_nt_workspace': (sz, [C.c_int, C.c_int, C.c_int, C.c_int]),
     're2nn_gemm_nt': (C.c_int, [C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, sz, vp]),
@@ -104,6 +105,7 @@ SYMBOLS = {
     're2nn_label_scores': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, sz,
                                      vp]),
     're2nn_argmax_decode': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, i64, vp, vp, vp]),
+    're2nn_flatten_i64': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
     're2nn_crf_viterbi': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, i64, vp, vp, vp, vp]),
     're2nn_crf_nll': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
     're2nn_crf_nll_backward': (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),

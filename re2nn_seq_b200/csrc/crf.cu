@@ -340,6 +340,15 @@ __global__ void colsum_kernel(const float* __restrict__ Cm, int C, int S, const 
   o[s] = wv ? acc + wv[s] : acc;
 }
 
+// flat[offsets[b] + t] = padded[b, t] for t < len[b]   (utils.py:153-164 flatten, without the boolean-mask sync)
+__global__ void flatten_i64_kernel(const int64_t* __restrict__ padded, const int64_t* __restrict__ len,
+                                   const int64_t* __restrict__ offsets, int B, int Lrow, int L, int64_t* __restrict__ flat) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)B * L) return;
+  const int b = (int)(i / L), t = (int)(i - (long long)b * L);
+  if (t < (int)len[b]) flat[offsets[b] + t] = padded[(size_t)b * Lrow + t];
+}
+
 static const size_t kSmemLimit = 200 * 1024;
 
 }  // namespace re2nn
@@ -351,6 +360,15 @@ extern "C" {
 int re2nn_output_vector_sum(const float* C_mat, int C, int S, const float* wildcard_vec, float* o, void* stream) {
   RE2NN_CHECK(C_mat && o && C > 0 && S > 0, "output_vector_sum: bad arguments");
   colsum_kernel<<<cdiv(S, 128), 128, 0, (cudaStream_t)stream>>>(C_mat, C, S, wildcard_vec, o);
+  RE2NN_LAUNCH_CHECK();
+  return 0;
+}
+
+int re2nn_flatten_i64(const int64_t* padded, const int64_t* lengths, const int64_t* offsets, int B, int Lrow, int L,
+                      int64_t* flat, void* stream) {
+  RE2NN_CHECK(padded && lengths && offsets && flat && L <= Lrow, "flatten_i64: bad arguments");
+  const long long n = (long long)B * L;
+  flatten_i64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(padded, lengths, offsets, B, Lrow, L, flat);
   RE2NN_LAUNCH_CHECK();
   return 0;
 }

@@ -153,9 +153,15 @@ template <int PREC> struct EpiQ {
   __device__ __forceinline__ Pre prefetch(const RowCtx& r, int, int n) const {
     return Pre{__ldg(p.vtab + (size_t)((uint32_t)r.vrow * (uint32_t)p.R + (uint32_t)n)), 0.f};
   }
-  __device__ __forceinline__ void apply(const Col&, const RowCtx& r, int m, int n, float acc, const Pre& pre) const {
-    OperandFmt<PREC>::store(p.Q[0], (uint32_t)m * (uint32_t)p.ldq + (uint32_t)n, p.q_plane, acc * pre.a);
-    if (p.Usave[0]) p.Usave[0][(uint32_t)m * (uint32_t)p.R + (uint32_t)n] = r.alive ? acc : 0.f;
+  __device__ __forceinline__ float compute(const Col&, float acc, const Pre& pre) const { return acc * pre.a; }
+  __device__ __forceinline__ void apply(const Col& c, const RowCtx& r, int m, int n, float acc, const Pre& pre) const {
+    store(c, r, m, n, compute(c, acc, pre), acc, pre);
+  }
+  __device__ __forceinline__ void store(const Col&, const RowCtx& r, int m, int n, float q, float acc, const Pre&) const {
+    OperandFmt<PREC>::store(p.Q[0], (uint32_t)m * (uint32_t)p.ldq + (uint32_t)n, p.q_plane, q);
+    if constexpr (PREC == RE2NN_PREC_FP32) {     // training saves exist on the fp32 path only
+      if (p.Usave[0]) p.Usave[0][(uint32_t)m * (uint32_t)p.R + (uint32_t)n] = r.alive ? acc : 0.f;
+    }
   }
 };
 
@@ -178,18 +184,27 @@ template <int PREC, int NL = -1, int FARNN = -1> struct EpiH {
     }
     return Pre{0.f, 0.f};
   }
-  __device__ __forceinline__ void apply(const Col& c, const RowCtx& r, int m, int n, float acc, const Pre& pre) const {
+  // compute() is pure arithmetic so a mainloop can evaluate a batch of rows back to back (independent MUFU
+  // chains) before any store is issued; store() does the memory side.
+  __device__ __forceinline__ float compute(const Col& c, float acc, const Pre& pre) const {
     float hn = p.dir == 0 ? acc * c.a : acc;
     hn = apply_nl_t<kFast>(hn, nl());
-    float hnew = hn;
+    if (farnn() >= 1) hn = (1.f - pre.a) * pre.b + pre.a * hn;
+    return hn;
+  }
+  __device__ __forceinline__ void apply(const Col& c, const RowCtx& r, int m, int n, float acc, const Pre& pre) const {
+    store(c, r, m, n, compute(c, acc, pre), acc, pre);
+  }
+  __device__ __forceinline__ void store(const Col& c, const RowCtx& r, int m, int n, float hnew, float acc, const Pre&) const {
     const uint32_t hi = (uint32_t)m * (uint32_t)p.ldh + (uint32_t)n;
     const uint32_t si = (uint32_t)m * (uint32_t)p.S + (uint32_t)n;
-    if (farnn() >= 1) hnew = (1.f - pre.a) * pre.b + pre.a * hn;
-    if (p.Asave[0]) {   // training: keep what BPTT needs; rows that are finished hold exact zeros
-      const bool live = r.alive;          // note: a live row may have no output row (backward direction, beta_0)
-      p.Asave[0][si] = live ? acc : 0.f;
-      if (!live) hnew = 0.f;
-      p.HstNext[0][si] = hnew;
+    if constexpr (PREC == RE2NN_PREC_FP32) {     // training saves exist on the fp32 path only
+      if (p.Asave[0]) {   // keep what BPTT needs; rows that are finished hold exact zeros
+        const bool live = r.alive;          // note: a live row may have no output row (backward direction, beta_0)
+        p.Asave[0][si] = live ? acc : 0.f;
+        if (!live) hnew = 0.f;
+        p.HstNext[0][si] = hnew;
+      }
     }
     if (farnn() >= 1) {
       p.H[0][si] = hnew;
@@ -217,8 +232,13 @@ template <int PREC> struct EpiGate {
     if (n >= p.S) q.b = p.H[0][(uint32_t)m * (uint32_t)p.S + (uint32_t)(n - p.S)];
     return q;
   }
-  __device__ __forceinline__ void apply(const Col& c, const RowCtx&, int m, int n, float acc, const Pre& pre) const {
-    float g = sigmoid_t<kFast>((acc + pre.a) * p.sig_k);
+  __device__ __forceinline__ float compute(const Col&, float acc, const Pre& pre) const {
+    return sigmoid_t<kFast>((acc + pre.a) * p.sig_k);
+  }
+  __device__ __forceinline__ void apply(const Col& c, const RowCtx& r, int m, int n, float acc, const Pre& pre) const {
+    store(c, r, m, n, compute(c, acc, pre), acc, pre);
+  }
+  __device__ __forceinline__ void store(const Col& c, const RowCtx&, int m, int n, float g, float, const Pre& pre) const {
     if (n < p.S) {
       p.Z[0][(uint32_t)m * (uint32_t)p.S + (uint32_t)n] = g;
     } else {
@@ -226,7 +246,9 @@ template <int PREC> struct EpiGate {
       float hb = (1.f - g) * c.a + g * pre.b;
       if (p.dir == 1) hb *= c.b;
       OperandFmt<PREC>::store(p.Hbar_cur[0], (uint32_t)m * (uint32_t)p.ldh + (uint32_t)s, p.h_plane, hb);
-      if (p.Rg[0]) p.Rg[0][(uint32_t)m * (uint32_t)p.S + (uint32_t)s] = g;
+      if constexpr (PREC == RE2NN_PREC_FP32) {
+        if (p.Rg[0]) p.Rg[0][(uint32_t)m * (uint32_t)p.S + (uint32_t)s] = g;
+      }
     }
   }
 };
@@ -241,8 +263,12 @@ struct EpiStore {
   __device__ __forceinline__ RowCtx row(int) const { return RowCtx{0, 0, true}; }
   __device__ __forceinline__ Col col(int n) const { return Col{bias ? __ldg(bias + n) : 0.f, 0.f}; }
   __device__ __forceinline__ Pre prefetch(const RowCtx&, int, int) const { return Pre{0.f, 0.f}; }
-  __device__ __forceinline__ void apply(const Col& c, const RowCtx&, int m, int n, float acc, const Pre&) const {
-    C[(size_t)m * ldc + n] = acc + c.a;
+  __device__ __forceinline__ float compute(const Col& c, float acc, const Pre&) const { return acc + c.a; }
+  __device__ __forceinline__ void apply(const Col& c, const RowCtx& r, int m, int n, float acc, const Pre& pre) const {
+    store(c, r, m, n, compute(c, acc, pre), acc, pre);
+  }
+  __device__ __forceinline__ void store(const Col&, const RowCtx&, int m, int n, float v, float, const Pre&) const {
+    C[(size_t)m * ldc + n] = v;
   }
 };
 

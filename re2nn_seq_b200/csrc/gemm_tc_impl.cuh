@@ -213,6 +213,13 @@ template <int PREC, int BN> struct TcCfg {
 
 // optional per-CTA phase trace (debug): 8 clock64 stamps per CTA when a buffer is installed
 __device__ unsigned long long* g_tc_trace = nullptr;
+__device__ unsigned long long* g_tc_timeline = nullptr;   // [launch][2] globaltimer ns of CTA (0,0,0): entry, exit
+__device__ unsigned int g_tc_timeline_ctr = 0;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void tc_stamp(unsigned long long* t, int slot) {
   if (t) t[slot] = clock64();
 }
@@ -233,6 +240,11 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
   unsigned long long* trace = nullptr;
   if (g_tc_trace) trace = g_tc_trace + 32ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
   if (threadIdx.x == 0) tc_stamp(trace, 0);
+  unsigned int tl_idx = 0xffffffffu;
+  if (g_tc_timeline && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    tl_idx = atomicAdd(&g_tc_timeline_ctr, 1u);
+    if (tl_idx < 4096) g_tc_timeline[2 * tl_idx] = globaltimer_ns();
+  }
   if (!epi_in.tile_alive(z, m0, rows)) return;
   if (threadIdx.x == 0) tc_stamp(trace, 1);
 
@@ -386,11 +398,33 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
         for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
       }
       __syncwarp();
-      // phase 2: lane = column, loop over rows: every store is a contiguous row segment
+      // phase 2: lane = column, rows in batches of 16: all accumulator reads first, then 16 independent
+      // epilogue evaluations (the compiler interleaves their MUFU / convert / store chains), unguarded when the
+      // 32x32 block is interior
+      const bool interior = nrows == 32 && n0 + c0 + 32 <= L.N && c0 + 32 <= bn;   // warp-uniform
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (col_ok && i < nrows)
-          epi.apply(cc, RowCtx{ctx[i], ctx[32 + i], ctx[32 + i] >= 0}, mrow0 + i, n, tbuf[i * 33 + lane], pre[i]);
+      for (int h0 = 0; h0 < 32; h0 += 16) {
+        float av[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) av[i] = tbuf[(h0 + i) * 33 + lane];
+        if (interior) {
+          float hv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) hv[i] = epi.compute(cc, av[i], pre[h0 + i]);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int o = ctx[32 + h0 + i];
+            epi.store(cc, RowCtx{ctx[h0 + i], o, o >= 0}, mrow0 + h0 + i, n, hv[i], av[i], pre[h0 + i]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (col_ok && h0 + i < nrows) {
+              const int o = ctx[32 + h0 + i];
+              epi.apply(cc, RowCtx{ctx[h0 + i], o, o >= 0}, mrow0 + h0 + i, n, av[i], pre[h0 + i]);
+            }
+          }
+        }
       }
       __syncwarp();
     }
@@ -403,6 +437,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_con
   }
   __syncthreads();
   if (threadIdx.x == 0) tc_stamp(trace, 7);
+  if (tl_idx < 4096) g_tc_timeline[2 * tl_idx + 1] = globaltimer_ns();
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)(BN * Cfg::kAccs)));

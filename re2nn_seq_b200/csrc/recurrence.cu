@@ -308,6 +308,13 @@ int re2nn_debug_set_tc_trace(unsigned long long* device_buf) {
   return 0;
 }
 
+int re2nn_debug_set_tc_timeline(unsigned long long* device_buf) {
+  unsigned int zero = 0;
+  RE2NN_CUDA(cudaMemcpyToSymbol(g_tc_timeline_ctr, &zero, sizeof(zero)));
+  RE2NN_CUDA(cudaMemcpyToSymbol(g_tc_timeline, &device_buf, sizeof(device_buf)));
+  return 0;
+}
+
 int re2nn_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof_on = on != 0;

@@ -148,14 +148,71 @@ class _DecomposeBase(nn.Module):
         _, order = torch.sort(lengths, descending=True, stable=True)
         return order, exclusive_offsets(lengths).index_select(0, order)
 
+    # ---- CUDA-graph replay of the inference path --------------------------------------------------------
+    # One forward_local is ~80-110 small dependent launches; on the host that is 10+ us per launch, more than
+    # the kernels take.  Inference calls (no grad, no KD) are therefore captured once per (shape, precision,
+    # parameter version) with static buffers and replayed: one graph launch per batch.
+    def _graph_key(self, B, Lpad, L, tag):
+        vers = tuple((q.data_ptr(), q._version) for q in self.parameters())
+        return (tag, B, Lpad, L, self.precision, bool(getattr(self, 'sort_by_length', True)), vers)
+
+    def _infer_body(self, inp, label, lengths, L):
+        """Sync-free inference body: every shape is a function of (B, Lpad, L) only."""
+        B = lengths.shape[0]
+        nmax = B * L
+        offs0 = exclusive_offsets(lengths)
+        true = ops.flatten_i64(label.contiguous(), lengths, offs0, L, nmax)
+        order, offsets = self._length_order(lengths, None)
+        if order is not None:
+            lengths = lengths.index_select(0, order)
+            inp = inp.index_select(0, order)
+        else:
+            offsets = offs0
+        scores = self._scores_from(inp, lengths, (L, nmax))
+        pred = self.decode(scores, None, None, lengths, _shape=(L, nmax), _offsets=offsets)
+        return pred, true
+
+    def _infer_graphed(self, inp, label, lengths, shape, tag):
+        L, N = shape
+        B, Lpad = lengths.shape[0], inp.shape[1]
+        if not hasattr(self, '_graphs'):
+            self._graphs = {}
+        key = self._graph_key(B, Lpad, L, tag)
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= 8:                      # parameter updates / new shapes: drop stale captures
+                self._graphs.clear()
+            sx, sy, sl = inp.clone(), label.contiguous().clone(), lengths.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                   # warm-up outside capture (lazy init, caches)
+                self._infer_body(sx, sy, sl, L)
+            torch.cuda.current_stream().wait_stream(side)
+            l0 = ops.launches()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                pred, true = self._infer_body(sx, sy, sl, L)
+            ent = dict(g=g, x=sx, y=sy, l=sl, pred=pred, true=true, launches=ops.launches() - l0)
+            self._graphs[key] = ent
+        ent['x'].copy_(inp, non_blocking=True)
+        ent['y'].copy_(label, non_blocking=True)
+        ent['l'].copy_(lengths, non_blocking=True)
+        ent['g'].replay()
+        ops._count(ent['launches'])
+        return None, ent['pred'][:N].clone(), ent['true'][:N].clone()
+
+    def _can_graph(self, train, re_tags):
+        return (not train) and re_tags is None and not torch.is_grad_enabled() and getattr(self, 'use_cuda_graph', True) \
+            and self.args.marryup_type not in ('kd', 'pr') and not getattr(self, 'full_pad', False)
+
     def _finish(self, all_scores, label, lengths, train, re_tags, shape, order=None, offsets=None, orig=None):
         L, N = shape
         dev = all_scores.device
         label = label.to(dev)
         if order is None:
-            flattened_true_labels = flatten(label[:, :L], lengths)
+            flattened_true_labels = ops.flatten_i64(label.contiguous(), lengths, exclusive_offsets(lengths), L, N)
         else:
-            flattened_true_labels = flatten(label[:, :L], orig)
+            flattened_true_labels = ops.flatten_i64(label.contiguous(), orig, exclusive_offsets(orig), L, N)
             label = label.index_select(0, order)
         loss = None
         if train:
@@ -261,10 +318,15 @@ class FARNN_S_D_W_I_S(_DecomposeBase):
         return autograd_fns.decompose_scores(self._recurrence_consts(), names, tensors, pr, x, None, lengths, shape[0],
                                              cache=self._cache)
 
+    def _scores_from(self, inp, lengths, shape):
+        return self.forward_scores(inp, lengths, shape)
+
     def forward_local(self, input, label, lengths, train=True, re_tags=None):
         dev = self._device()
         lengths = lengths.to(dev).contiguous()
         shape = self._host_shape(lengths)
+        if self._can_graph(train, re_tags):
+            return self._infer_graphed(input.to(dev).contiguous(), label.to(dev), lengths, shape, 'tok')
         order, offsets = self._length_order(lengths, re_tags)
         if order is None:
             all_scores = self.forward_scores(input, lengths, shape)
@@ -328,11 +390,16 @@ class FARNN_S_SF(_DecomposeBase):
         pr = (self.priority_layer.priority_mat, self.priority_layer.priority_bias)
         return autograd_fns.decompose_scores(self._recurrence_consts(), names, tensors, pr, None, v, lengths, shape[0])
 
+    def _scores_from(self, inp, lengths, shape):
+        return self.forward_scores(inp, lengths, shape)
+
     def forward(self, input, label, lengths, train=True, re_tags=None):
         """input: pre-computed rank factors B x L x R (model_decompose_single.py:483-580)."""
         dev = self._device()
         lengths = lengths.to(dev).contiguous()
         shape = self._host_shape(lengths)
+        if self._can_graph(train, re_tags):
+            return self._infer_graphed(input.to(dev).float().contiguous(), label.to(dev), lengths, shape, 'sf')
         order, offsets = self._length_order(lengths, re_tags)
         if order is None:
             all_scores = self.forward_scores(input, lengths, shape)

@@ -361,3 +361,13 @@ def onehot_backward(x, lengths, L, language, W, o, h0, hT, alpha, beta, dscores,
     check(fn['re2nn_onehot_backward'](C.byref(a), _stream()), 'onehot_backward')
     _count(3 if pr_mat is not None else 2)
     return dlang
+
+
+def flatten_i64(padded, lengths, offsets, L, n_flat):
+    """Valid prefixes of an int64 B x Lrow tensor, batch-major (no host sync)."""
+    B, Lrow = padded.shape
+    flat = torch.empty((n_flat,), dtype=torch.int64, device=padded.device)
+    check(fn['re2nn_flatten_i64'](_i64(padded), _i64(lengths), _i64(offsets), B, Lrow, L, _i64(flat), _stream()),
+          'flatten_i64')
+    _count(1)
+    return flat
