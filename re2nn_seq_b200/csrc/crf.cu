@@ -18,7 +18,7 @@ __device__ __forceinline__ float clamped_feat(const float* f, int j, int clamp_c
 }
 
 // dynamic smem: [TS ? T*T : 0] transitions, then kCrfWarps * 2 * Tp partitions
-template <bool TS>
+template <bool TS, int NJ>
 __global__ void __launch_bounds__(kCrfWarps * 32) crf_viterbi_kernel(
     const float* __restrict__ feats, const float* __restrict__ trans_g, const int64_t* __restrict__ len,
     const int64_t* __restrict__ offsets, int B, int L, int T, int clamp_col, float thr, int64_t o_idx,
@@ -43,21 +43,60 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_viterbi_kernel(
 
   for (int j = lane; j < T; j += 32) pa[j] = clamped_feat(fb, j, clamp_col, thr) + tr[(T - 2) * T + j];
   __syncwarp();
-  for (int t = 1; t < n; ++t) {
-    const float* ft = fb + (size_t)t * T;
-    for (int j = lane; j < T; j += 32) {
-      const float f = clamped_feat(ft, j, clamp_col, thr);
-      float best = -INFINITY;
-      int bi = 0;
-      for (int i = 0; i < T; ++i) {
-        float v = (f + tr[i * T + j]) + pa[i];
-        if (v > best) { best = v; bi = i; }
+  if (NJ > 0) {
+    // register-blocked: lane owns target tags j = lane + 32*q (q < NJ); one pass over the source tags i shares the
+    // partition load and keeps NJ independent max/argmax chains in flight
+    for (int t = 1; t < n; ++t) {
+      const float* ft = fb + (size_t)t * T;
+      float f[NJ > 0 ? NJ : 1], best[NJ > 0 ? NJ : 1];
+      int bi[NJ > 0 ? NJ : 1];
+#pragma unroll
+      for (int q = 0; q < NJ; ++q) {
+        const int j = lane + 32 * q;
+        f[q] = j < T ? clamped_feat(ft, j, clamp_col, thr) : 0.f;
+        best[q] = -INFINITY;
+        bi[q] = 0;
       }
-      pb[j] = best;
-      bpb[(size_t)t * T + j] = (uint16_t)bi;
+      // lanes whose last slot falls past T read (and ignore) the following shared-memory words: the loop stays
+      // warp-uniform and the transitions are followed by the partition buffers, so the reads are in bounds
+#pragma unroll 5
+      for (int i = 0; i < T; ++i) {
+        const float p = pa[i];
+        const float* tri = tr + i * T + lane;
+#pragma unroll
+        for (int q = 0; q < NJ; ++q) {
+          const float v = (f[q] + tri[32 * q]) + p;
+          if (v > best[q]) { best[q] = v; bi[q] = i; }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NJ; ++q) {
+        const int j = lane + 32 * q;
+        if (j < T) {
+          pb[j] = best[q];
+          bpb[(size_t)t * T + j] = (uint16_t)bi[q];
+        }
+      }
+      __syncwarp();
+      float* tmp = pa; pa = pb; pb = tmp;
     }
-    __syncwarp();
-    float* tmp = pa; pa = pb; pb = tmp;
+  } else {
+    for (int t = 1; t < n; ++t) {
+      const float* ft = fb + (size_t)t * T;
+      for (int j = lane; j < T; j += 32) {
+        const float f = clamped_feat(ft, j, clamp_col, thr);
+        float best = -INFINITY;
+        int bi = 0;
+        for (int i = 0; i < T; ++i) {
+          float v = (f + tr[i * T + j]) + pa[i];
+          if (v > best) { best = v; bi = i; }
+        }
+        pb[j] = best;
+        bpb[(size_t)t * T + j] = (uint16_t)bi;
+      }
+      __syncwarp();
+      float* tmp = pa; pa = pb; pb = tmp;
+    }
   }
   // transition into STOP: pointer = argmax_i (part_i + trans[i][STOP])
   float best = -INFINITY;
@@ -384,16 +423,29 @@ int re2nn_crf_viterbi(const float* feats, const float* transitions, const int64_
   const size_t with_tr = part + (size_t)T * T * 4;
   const int grid = cdiv(B, kCrfWarps);
   cudaStream_t st = (cudaStream_t)stream;
+#define RE2NN_VIT(NJ)                                                                                              \
+  do {                                                                                                             \
+    RE2NN_CUDA(cudaFuncSetAttribute(crf_viterbi_kernel<true, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                    (int)with_tr));                                                                \
+    crf_viterbi_kernel<true, NJ><<<grid, kCrfWarps * 32, with_tr, st>>>(feats, transitions, lengths, offsets, B, L, \
+                                                                        T, clamp_col, threshold, o_idx,            \
+                                                                        padded_path, flat_pred, bp_ws);            \
+  } while (0)
   if (with_tr <= kSmemLimit) {
-    RE2NN_CUDA(cudaFuncSetAttribute(crf_viterbi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_tr));
-    crf_viterbi_kernel<true><<<grid, kCrfWarps * 32, with_tr, st>>>(feats, transitions, lengths, offsets, B, L, T,
-                                                                    clamp_col, threshold, o_idx, padded_path,
-                                                                    flat_pred, bp_ws);
+    switch (cdiv(T, 32)) {
+      case 1: RE2NN_VIT(1); break;
+      case 2: RE2NN_VIT(2); break;
+      case 3: RE2NN_VIT(3); break;
+      case 4: RE2NN_VIT(4); break;
+      case 5: RE2NN_VIT(5); break;
+      default: RE2NN_VIT(0); break;
+    }
   } else {
-    crf_viterbi_kernel<false><<<grid, kCrfWarps * 32, part, st>>>(feats, transitions, lengths, offsets, B, L, T,
-                                                                  clamp_col, threshold, o_idx, padded_path, flat_pred,
-                                                                  bp_ws);
+    crf_viterbi_kernel<false, 0><<<grid, kCrfWarps * 32, part, st>>>(feats, transitions, lengths, offsets, B, L, T,
+                                                                     clamp_col, threshold, o_idx, padded_path,
+                                                                     flat_pred, bp_ws);
   }
+#undef RE2NN_VIT
   RE2NN_LAUNCH_CHECK();
   return 0;
 }
