@@ -205,9 +205,9 @@ def main():
     m = r.FARNN_S_D_W_I_S(args=args, o_idx=0, **f)
     with torch.no_grad():
         m.crf.transitions.copy_(torch.from_numpy(synth.crf_transitions(0, m.C)))
-    prec = a.precision
-    if prec == 'auto':      # parity-grade tensor-core mode when the device has tcgen05, else the fp32 CUDA-core path
-        prec = 'tf32x3' if ops.has_tcgen05() else 'fp32'
+    m.precision = a.precision      # 'auto': parity-grade tensor-core mode (split fp16 / 3xTF32), fp32 without tcgen05
+    with torch.no_grad():
+        prec = m._resolved_precision()
     m.precision = prec
     p_oracle = oracle_params_from_module(m) if rank == 0 else None
     m = m.cuda().eval()
@@ -286,6 +286,7 @@ def main():
 
     # ---- roofline pass: the same K steps again, every step-GEMM launch bracketed by CUDA events recorded
     # inside the library on the launching stream (kept out of region 1 so the events do not perturb `value`)
+    m.use_cuda_graph = False               # events are recorded around direct launches, not inside a graph replay
     ops.profile_enable(True)
     ops.profile_read()
     barrier()
@@ -299,6 +300,7 @@ def main():
     clocks = sampler.stop()
     prof_ms, prof_n = ops.profile_read()
     ops.profile_enable(False)
+    m.use_cuda_graph = True
     prof_step_ms = sum(s.elapsed_time(e) for s, e in evp) / a.steps
 
     # ---- timed region 2: end to end from pinned host buffers --------------------------------------------
@@ -336,6 +338,11 @@ def main():
         peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside the step)' if peaks else \
             'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'
         # dominant kernel: GEMM2 (+ state epilogue), both directions per launch: 2 dirs * 2*B*S*(R+S) flops
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json'))).get(prec)
+        except Exception:
+            pass
         g2_flops = 2 * 2.0 * c['B'] * S * (R + S)
         g2_ms = prof_ms[2] / max(prof_n[2], 1)
         achieved = g2_flops / (g2_ms * 1e-3) / 1e12 if g2_ms > 0 else 0.0
@@ -351,9 +358,10 @@ def main():
                        'farnn': a.farnn, 'precision': prec, 'tokens_per_step_per_gpu': n_tok,
                        'tag_mismatches_vs_fp32_path': mismatch,
                        'l2': 'flushed between timed iterations (256 MB write)',
+                       'cuda_graph': a.mode == 'infer',
                        'whole_step_tflops': value * flops_per_position(S, R, D, Cp, a.farnn) / 1e12},
             'roofline': {'bound': 'tensor', 'kernel': 'step GEMM2 + state epilogue (%s)' % prec, 'achieved': achieved,
-                         'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': None,
+                         'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': traffic,
                          'peak_source': peak_src, 'launches_timed': prof_n[2], 'avg_launch_ms': g2_ms,
                          'kernel_share_of_step': (prof_ms[2] / a.steps) / prof_step_ms if prof_step_ms > 0 else None,
                          'profiled_ms_per_step': prof_step_ms,

@@ -88,6 +88,19 @@ class _DecomposeBase(nn.Module):
                 for w in (self.Wss1, self.Wrs1, self.Wss2, self.Wrs2):
                     nn.init.xavier_normal_(w)
 
+    def _resolved_precision(self):
+        """'auto' picks the fastest parity-grade mode the device has: split-fp16 tensor cores when the state is
+        bounded by the update nonlinearity (fp16 planes need |operand| < 65504), 3xTF32 otherwise, fp32 CUDA
+        cores without tcgen05.  Training always runs the fp32 path."""
+        prec = self.precision
+        if prec != 'auto':
+            return prec
+        if torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters()):
+            return 'fp32'
+        if not ops.has_tcgen05():
+            return 'fp32'
+        return 'fp16x3' if self.args.update_nonlinear in ('tanh', 'relutanh') else 'tf32x3'
+
     # ---- launch-time constants -----------------------------------------------------------------
     @property
     def _S_full(self):
@@ -154,7 +167,7 @@ class _DecomposeBase(nn.Module):
     # parameter version) with static buffers and replayed: one graph launch per batch.
     def _graph_key(self, B, Lpad, L, tag):
         vers = tuple((q.data_ptr(), q._version) for q in self.parameters())
-        return (tag, B, Lpad, L, self.precision, bool(getattr(self, 'sort_by_length', True)), vers)
+        return (tag, B, Lpad, L, self._resolved_precision(), bool(getattr(self, 'sort_by_length', True)), vers)
 
     def _infer_body(self, inp, label, lengths, L):
         """Sync-free inference body: every shape is a function of (B, Lpad, L) only."""
@@ -241,7 +254,7 @@ class _DecomposeBase(nn.Module):
     def _recurrence_consts(self):
         a = self.args
         return dict(farnn=a.farnn, max_semiring=(a.train_mode == 'max'), update_nonlinear=_nl_name(a.update_nonlinear, _UPDATE_NL),
-                    sigmoid_exponent=float(a.sigmoid_exponent), precision=self.precision,
+                    sigmoid_exponent=float(a.sigmoid_exponent), precision=self._resolved_precision(),
                     ce1=(a.local_loss_func == 'CE1'), use_priority=bool(a.use_priority),
                     additional_nonlinear=_nl_name(a.additional_nonlinear, _ADD_NL),
                     full_pad=bool(getattr(self, 'full_pad', False)) or a.marryup_type in ('kd', 'pr'))
