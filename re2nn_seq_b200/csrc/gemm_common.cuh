@@ -29,11 +29,22 @@ template <int PREC> struct OperandFmt;
 template <> struct OperandFmt<RE2NN_PREC_FP32> {
   static constexpr int kElemBytes = 4, kPlanes = 1, kLdAlign = 1;
   __device__ static __forceinline__ void store(void* base, size_t idx, size_t, float v) { ((float*)base)[idx] = v; }
+  // four consecutive elements, idx % 4 == 0 and the row pitch 16-byte aligned
+  __device__ static __forceinline__ void store4(void* base, size_t idx, size_t, float4 v) {
+    *reinterpret_cast<float4*>((float*)base + idx) = v;
+  }
 };
 template <> struct OperandFmt<RE2NN_PREC_BF16> {
   static constexpr int kElemBytes = 2, kPlanes = 1, kLdAlign = 8;
   __device__ static __forceinline__ void store(void* base, size_t idx, size_t, float v) {
     ((__nv_bfloat16*)base)[idx] = __float2bfloat16_rn(v);
+  }
+  __device__ static __forceinline__ void store4(void* base, size_t idx, size_t, float4 v) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&lo);
+    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>((__nv_bfloat16*)base + idx) = u;
   }
 };
 __device__ __forceinline__ float tf32_hi(float v) {   // round-to-nearest onto the 10-bit tf32 mantissa
@@ -48,6 +59,12 @@ template <> struct OperandFmt<RE2NN_PREC_TF32X3> {
     ((float*)base)[idx] = hi;
     ((float*)base)[idx + plane] = tf32_hi(v - hi);
   }
+  __device__ static __forceinline__ void store4(void* base, size_t idx, size_t plane, float4 v) {
+    float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    float4 l = make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));
+    *reinterpret_cast<float4*>((float*)base + idx) = h;
+    *reinterpret_cast<float4*>((float*)base + idx + plane) = l;
+  }
 };
 // fp16 split: v = hi + lo * 2^-11 with hi = fp16(v), lo = fp16((v - hi) * 2^11): 22 mantissa bits in 4 bytes.
 // The residual is kept scaled so it stays a normal fp16 number; its products go to a second accumulator that
@@ -59,6 +76,17 @@ template <> struct OperandFmt<RE2NN_PREC_FP16X3> {
     const __half hi = __float2half_rn(v);
     ((__half*)base)[idx] = hi;
     ((__half*)base)[idx + plane] = __float2half_rn((v - __half2float(hi)) * kFp16LoScale);
+  }
+  __device__ static __forceinline__ void store4(void* base, size_t idx, size_t plane, float4 v) {
+    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn((v.x - f0.x) * kFp16LoScale, (v.y - f0.y) * kFp16LoScale);
+    const __half2 l1 = __floats2half2_rn((v.z - f1.x) * kFp16LoScale, (v.w - f1.y) * kFp16LoScale);
+    uint2 uh, ul;
+    uh.x = *reinterpret_cast<const uint32_t*>(&h0); uh.y = *reinterpret_cast<const uint32_t*>(&h1);
+    ul.x = *reinterpret_cast<const uint32_t*>(&l0); ul.y = *reinterpret_cast<const uint32_t*>(&l1);
+    *reinterpret_cast<uint2*>((__half*)base + idx) = uh;
+    *reinterpret_cast<uint2*>((__half*)base + idx + plane) = ul;
   }
 };
 inline bool prec_is_16bit(int prec) { return prec == RE2NN_PREC_BF16 || prec == RE2NN_PREC_FP16X3; }

@@ -237,19 +237,33 @@ using namespace re2nn;
 
 extern "C" int re2nn_has_tcgen05(void);
 
-// (alpha * beta) in operand format for the tcgen05 score GEMM; rows past the length are zero
+// (alpha * beta) in operand format for the tcgen05 score GEMM; rows past the length are zero.
+// One warp per (sequence, position) row: the row index math happens once per warp, lanes sweep the S columns
+// with 16-byte loads when the row pitch allows it.
 template <int PREC>
-__global__ void ab_operand_kernel(const float* __restrict__ alpha, const float* __restrict__ beta,
-                                  const int64_t* __restrict__ len, int B, int L, int S, int ld, int full_pad,
-                                  void* __restrict__ dst, size_t plane) {
-  const size_t total = (size_t)B * L * ld;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t m = i / ld;
-    const int s = (int)(i - m * ld);
-    const int b = (int)(m / L), t = (int)(m - (size_t)b * L);
-    float v = 0.f;
-    if (s < S && (full_pad || t < (int)len[b])) v = __ldg(alpha + m * S + s) * __ldg(beta + m * S + s);
-    OperandFmt<PREC>::store(dst, i, plane, v);
+__global__ void __launch_bounds__(256) ab_operand_kernel(const float* __restrict__ alpha, const float* __restrict__ beta,
+                                                         const int64_t* __restrict__ len, int B, int L, int S, int ld,
+                                                         int full_pad, void* __restrict__ dst, size_t plane) {
+  const size_t m = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (m >= (size_t)B * L) return;
+  const int b = (int)(m / L), t = (int)(m - (size_t)b * L);
+  const bool valid = full_pad || t < (int)len[b];
+  const size_t row = m * (size_t)ld;
+  if (valid && (S & 3) == 0) {
+    const float4* a4 = reinterpret_cast<const float4*>(alpha + m * S);
+    const float4* b4 = reinterpret_cast<const float4*>(beta + m * S);
+    for (int c = lane; c < (S >> 2); c += 32) {
+      const float4 x = __ldg(a4 + c), y = __ldg(b4 + c);
+      OperandFmt<PREC>::store4(dst, row + 4 * c, plane, make_float4(x.x * y.x, x.y * y.y, x.z * y.z, x.w * y.w));
+    }
+    for (int s = S + lane; s < ld; s += 32) OperandFmt<PREC>::store(dst, row + s, plane, 0.f);
+  } else {
+    for (int s = lane; s < ld; s += 32) {
+      float v = 0.f;
+      if (valid && s < S) v = __ldg(alpha + m * S + s) * __ldg(beta + m * S + s);
+      OperandFmt<PREC>::store(dst, row + s, plane, v);
+    }
   }
 }
 
@@ -262,9 +276,7 @@ static int label_scores_tc(const float* alpha, const float* beta, const int64_t*
   void* Bop = ws + operand_bytes(PREC, M, S);
   const size_t pa = M * ld, pb = (size_t)C * ld;
   {
-    size_t total = M * ld;
-    int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 32);
-    ab_operand_kernel<PREC><<<blocks, 256, 0, st>>>(alpha, beta, lengths, B, L, S, ld, full_pad, Aop, pa);
+    ab_operand_kernel<PREC><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(alpha, beta, lengths, B, L, S, ld, full_pad, Aop, pa);
     RE2NN_LAUNCH_CHECK();
     convert_weight_kernel<PREC><<<(unsigned)(((size_t)C * ld + 255) / 256), 256, 0, st>>>(C_mat, C, S, S, 0, Bop, ld, pb, 0);
     RE2NN_LAUNCH_CHECK();
