@@ -25,7 +25,7 @@ struct EpiStore2 {          // C_z = acc (per direction output pointers)
   int ldc;
   int accumulate;           // C += acc
   __device__ __forceinline__ EpiStore2 for_dir(int z) const { EpiStore2 e = *this; e.C[0] = C[z]; return e; }
-  __device__ __forceinline__ bool tile_alive(int, int, int) const { return true; }
+  __device__ __forceinline__ bool tile_alive(int, int) const { return true; }
   __device__ __forceinline__ RowCtx row(int) const { return RowCtx{0, 0, true}; }
   __device__ __forceinline__ Col col(int) const { return Col{0.f, 0.f}; }
   __device__ __forceinline__ Pre prefetch(const RowCtx&, int m, int n) const {
@@ -42,7 +42,7 @@ struct EpiDAB {
   float* dalpha; float* dbeta;
   int L, S, full_pad;
   __device__ __forceinline__ EpiDAB for_dir(int) const { return *this; }
-  __device__ __forceinline__ bool tile_alive(int, int, int) const { return true; }
+  __device__ __forceinline__ bool tile_alive(int, int) const { return true; }
   __device__ __forceinline__ RowCtx row(int m) const {
     int b = m / L, t = m - b * L;
     return RowCtx{0, (full_pad || t < (int)len[b]) ? 0 : -1, true};
@@ -355,7 +355,7 @@ struct EpiTokenBwd {
   float* dV; float* dbeta_prod; float* dGpre;
   int R, nl;
   __device__ __forceinline__ EpiTokenBwd for_dir(int) const { return *this; }
-  __device__ __forceinline__ bool tile_alive(int, int, int) const { return true; }
+  __device__ __forceinline__ bool tile_alive(int, int) const { return true; }
   __device__ __forceinline__ RowCtx row(int) const { return RowCtx{0, 0, true}; }
   __device__ __forceinline__ Col col(int n) const { return Col{__ldg(beta_vec + n), 0.f}; }
   __device__ __forceinline__ Pre prefetch(const RowCtx&, int m, int n) const {

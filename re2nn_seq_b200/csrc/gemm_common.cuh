@@ -109,6 +109,7 @@ struct StepParams {
   float sig_k;
   const int64_t* x;
   const int64_t* len;
+  const int* tile_last[2];   // per direction, per 128-row tile: last step at which a row of the tile is alive
   const float* vtab;
   const float* gtab;
   int ldg;
@@ -150,16 +151,9 @@ __device__ __forceinline__ RowCtx make_row(const StepParams& p, int z, int m) {
   return r;
 }
 
-// is any row of [m0, m0+rows) still alive at this step?  (block-uniform; all threads must call)
-__device__ __forceinline__ bool tile_alive(const StepParams& p, int z, int m0, int rows) {
-  bool a = false;
-  for (int i = threadIdx.x; i < rows; i += blockDim.x) {
-    int tpos, orow;
-    bool alive;
-    step_pos(z, p.k, (int)p.len[m0 + i], p.full_pad, tpos, orow, alive);
-    a |= alive;
-  }
-  return __syncthreads_or(a) != 0;
+// is any row of 128-row tile `mt` still alive at this step?  (one load; every warp role can ask independently)
+__device__ __forceinline__ bool tile_alive(const StepParams& p, int z, int mt) {
+  return p.full_pad || p.k <= __ldg(p.tile_last[z] + mt);
 }
 
 // Every epilogue functor is split so the mainloops can (a) hoist per-column constants, (b) put all of a
@@ -175,7 +169,7 @@ struct Col { float a, b; };
 template <int PREC> struct EpiQ {
   StepParams p;
   __device__ __forceinline__ EpiQ for_dir(int z) const { EpiQ e = *this; e.p.bind(z); return e; }
-  __device__ __forceinline__ bool tile_alive(int z, int m0, int rows) const { return re2nn::tile_alive(p, z, m0, rows); }
+  __device__ __forceinline__ bool tile_alive(int z, int mt) const { return re2nn::tile_alive(p, z, mt); }
   __device__ __forceinline__ RowCtx row(int m) const { return make_row(p, p.dir, m); }
   __device__ __forceinline__ Col col(int) const { return Col{0.f, 0.f}; }
   __device__ __forceinline__ Pre prefetch(const RowCtx& r, int, int n) const {
@@ -200,7 +194,7 @@ template <int PREC, int NL = -1, int FARNN = -1> struct EpiH {
   static constexpr bool kFast = PREC == RE2NN_PREC_BF16;
   StepParams p;
   __device__ __forceinline__ EpiH for_dir(int z) const { EpiH e = *this; e.p.bind(z); return e; }
-  __device__ __forceinline__ bool tile_alive(int z, int m0, int rows) const { return re2nn::tile_alive(p, z, m0, rows); }
+  __device__ __forceinline__ bool tile_alive(int z, int mt) const { return re2nn::tile_alive(p, z, mt); }
   __device__ __forceinline__ RowCtx row(int m) const { return make_row(p, p.dir, m); }
   __device__ __forceinline__ int farnn() const { return FARNN >= 0 ? FARNN : p.farnn; }
   __device__ __forceinline__ int nl() const { return NL >= 0 ? NL : p.nl; }
@@ -249,7 +243,7 @@ template <int PREC> struct EpiGate {
   static constexpr bool kFast = PREC == RE2NN_PREC_BF16;
   StepParams p;
   __device__ __forceinline__ EpiGate for_dir(int z) const { EpiGate e = *this; e.p.bind(z); return e; }
-  __device__ __forceinline__ bool tile_alive(int z, int m0, int rows) const { return re2nn::tile_alive(p, z, m0, rows); }
+  __device__ __forceinline__ bool tile_alive(int z, int mt) const { return re2nn::tile_alive(p, z, mt); }
   __device__ __forceinline__ RowCtx row(int m) const { return make_row(p, p.dir, m); }
   __device__ __forceinline__ Col col(int n) const {
     if (n < p.S) return Col{0.f, 0.f};
@@ -287,7 +281,7 @@ struct EpiStore {
   int ldc;
   const float* bias;      // per-column or NULL
   __device__ __forceinline__ EpiStore for_dir(int) const { return *this; }
-  __device__ __forceinline__ bool tile_alive(int, int, int) const { return true; }
+  __device__ __forceinline__ bool tile_alive(int, int) const { return true; }
   __device__ __forceinline__ RowCtx row(int) const { return RowCtx{0, 0, true}; }
   __device__ __forceinline__ Col col(int n) const { return Col{bias ? __ldg(bias + n) : 0.f, 0.f}; }
   __device__ __forceinline__ Pre prefetch(const RowCtx&, int, int) const { return Pre{0.f, 0.f}; }
@@ -307,7 +301,7 @@ struct EpiTokenTable {
   const float* beta_vec;
   int R, nl;
   __device__ __forceinline__ EpiTokenTable for_dir(int) const { return *this; }
-  __device__ __forceinline__ bool tile_alive(int, int, int) const { return true; }
+  __device__ __forceinline__ bool tile_alive(int, int) const { return true; }
   __device__ __forceinline__ RowCtx row(int) const { return RowCtx{0, 0, true}; }
   __device__ __forceinline__ Col col(int n) const { return Col{__ldg(beta_vec + n), 0.f}; }
   __device__ __forceinline__ Pre prefetch(const RowCtx&, int m, int n) const {

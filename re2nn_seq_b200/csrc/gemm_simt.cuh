@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const GemmProblem prob, 
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int M = prob.M, N = prob.N;
   const int rows = min(BM, M - m0);
-  if (!epi_in.tile_alive(z, m0, rows)) return;
+  if (!epi_in.tile_alive(z, blockIdx.x)) return;   // BM == 128 == liveness tile
   const Epi epi = epi_in.for_dir(z);
 
   __shared__ __align__(16) float As[BK][BM + 4];

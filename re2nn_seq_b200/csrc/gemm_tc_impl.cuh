@@ -79,7 +79,8 @@ inline void tc_pick_bn(int M, int N, int ndir, int planes, int* bn_out, int* BN_
     if (bn > 256) continue;
     if (nt > 1 && bn * (nt - 1) >= N) continue;            // a narrower split already covers N
     const int cls = bn <= 64 ? 64 : (bn <= 128 ? 128 : 256);
-    const int per_sm = (cls == 256 || (planes == 2 && cls == 128)) ? 1 : 2;   // CTAs resident per SM (smem / registers)
+    const int per_sm = 1;                                   // persistent kernel: one CTA per SM
+    (void)cls;
     const long ctas = mt * nt;
     const double waves = (double)((ctas + 148L * per_sm - 1) / (148L * per_sm));
     const double conc = (double)std::min<long>(per_sm, (ctas + 147) / 148);   // CTAs sharing one SM's ingest
@@ -196,9 +197,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// One pipeline stage holds, per 128-byte k-block: the A tile (128 rows) and the B tile (BN rows); the 3xTF32
-// path keeps the residual ("lo") planes next to them so each operand byte is fetched once and feeds
-// three MMAs (hi*hi, lo*hi, hi*lo).
+constexpr int kTcEpiWarps = 8;                       // two warps per TMEM lane quarter
+constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;
+constexpr int kTcTbufBytes = kTcEpiWarps * 32 * 33 * 4;   // per-warp 32x33 fp32 transpose buffers
+constexpr int kTcSmemLimit = 227 * 1024;
+
+// One pipeline stage holds, per 128-byte k-block: the A tile (128 rows) and the B tile (BN rows); the split
+// formats keep the residual ("lo") planes next to them so each operand byte is fetched once and feeds three MMAs
+// (hi*hi, lo*hi, hi*lo).  When TMEM has room for two accumulator sets the kernel double-buffers them: the
+// epilogue of tile i overlaps the mainloop of tile i+1 (kOverlap); otherwise tiles run back to back and the
+// transpose buffers alias the (then idle) pipeline stages.
 template <int PREC, int BN> struct TcCfg {
   static constexpr int kPlanes = OperandFmt<PREC>::kPlanes;
   static constexpr int kAccs = PREC == RE2NN_PREC_FP16X3 ? 2 : 1;   // fp16 split keeps the residual products apart
@@ -207,8 +215,17 @@ template <int PREC, int BN> struct TcCfg {
   static constexpr int kABytes = kATile * kPlanes;
   static constexpr int kBBytes = kBTile * kPlanes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = kPlanes == 1 ? (BN == 128 ? 3 : 4) : (BN == 128 ? 3 : 2);
-  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 128 /*barriers*/ + 2048 /*row ctx*/;
+  static constexpr int kFixedBase = 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*row ctx*/;
+  static constexpr bool kOverlap = BN * kAccs * 2 <= 512 &&                                  // two accumulator sets in TMEM
+                                   (kTcSmemLimit - kFixedBase - kTcTbufBytes) / kStageBytes >= 2;   // + private transpose buffers
+  static constexpr int kAccCols = BN * kAccs;                      // TMEM columns of one accumulator set
+  static constexpr int kTmemCols = kAccCols * (kOverlap ? 2 : 1);
+  static constexpr int kFixed = kFixedBase + (kOverlap ? kTcTbufBytes : 0);
+  static constexpr int kFit = (kTcSmemLimit - kFixed) / kStageBytes;
+  static constexpr int kStages = kFit > 4 ? 4 : kFit;
+  static constexpr int kSmem = kStages * kStageBytes + kFixed;
+  static_assert(kStages >= 2, "pipeline needs two stages");
+  static_assert(kOverlap || kStages * kStageBytes >= kTcTbufBytes, "aliased transpose buffers do not fit");
 };
 
 // optional per-CTA phase trace (debug): 8 clock64 stamps per CTA when a buffer is installed
@@ -224,223 +241,274 @@ __device__ __forceinline__ void tc_stamp(unsigned long long* t, int slot) {
   if (t) t[slot] = clock64();
 }
 
-constexpr int kTcEpiWarps = 8;                       // two warps per TMEM lane quarter
-constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;
-
+// Persistent kernel: CTA c works on tiles c, c + gridDim.x, ...; tile id -> (direction z, m-tile, n-tile) with the
+// n-tile fastest so concurrently running CTAs share A tiles in L2.
 template <int PREC, int BN, class Epi>
-__global__ void __launch_bounds__(kTcThreads, 2) tc_gemm_kernel(const __grid_constant__ TcLaunch L, const Epi epi_in) {
+__global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_constant__ TcLaunch L, const Epi epi_in) {
   using Cfg = TcCfg<PREC, BN>;
   constexpr bool TF32 = PREC == RE2NN_PREC_TF32X3;
   constexpr bool SPLIT = Cfg::kPlanes == 2;
   constexpr bool TWOACC = Cfg::kAccs == 2;
-  const int z = blockIdx.z;
+  constexpr bool OVERLAP = Cfg::kOverlap;
+  constexpr int kpb = 128 / OperandFmt<PREC>::kElemBytes;
   const int bn = L.bn;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * bn;
-  const int rows = min(128, L.M - m0);
+  const int m_tiles = (L.M + 127) / 128, n_tiles = (L.N + bn - 1) / bn;
+  const int tiles_per_dir = m_tiles * n_tiles, total_tiles = tiles_per_dir * L.ndir;
   unsigned long long* trace = nullptr;
-  if (g_tc_trace) trace = g_tc_trace + 32ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+  if (g_tc_trace) trace = g_tc_trace + 32ull * blockIdx.x;
   if (threadIdx.x == 0) tc_stamp(trace, 0);
   unsigned int tl_idx = 0xffffffffu;
-  if (g_tc_timeline && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+  if (g_tc_timeline && threadIdx.x == 0 && blockIdx.x == 0) {
     tl_idx = atomicAdd(&g_tc_timeline_ctr, 1u);
     if (tl_idx < 4096) g_tc_timeline[2 * tl_idx] = globaltimer_ns();
   }
-  if (!epi_in.tile_alive(z, m0, rows)) return;
-  if (threadIdx.x == 0) tc_stamp(trace, 1);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = base + Cfg::kStages * Cfg::kStageBytes;     // full[S], empty[S], tmem_full, tmem_ptr
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  constexpr int kStageRegion = Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t bars = base + kStageRegion;     // full[S], empty[S], tmem_full[2], tmem_empty[2], tmem_slot
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (Cfg::kStages + s); };
-  const uint32_t tmem_full = bars + 8u * (2 * Cfg::kStages);
-  const uint32_t tmem_slot = tmem_full + 8u;
-  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_p = (volatile uint32_t*)(gen_base + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 1));
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * Cfg::kStages + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * Cfg::kStages + 2 + s); };
+  const uint32_t tmem_slot = bars + 8u * (2 * Cfg::kStages + 4);
+  volatile uint32_t* tmem_slot_p = (volatile uint32_t*)(gen_base + kStageRegion + 8 * (2 * Cfg::kStages + 4));
+  int* ctx_base = reinterpret_cast<int*>(gen_base + kStageRegion + 256);
+  float* tbuf_base = reinterpret_cast<float*>(OVERLAP ? gen_base + kStageRegion + 256 + 2048 : gen_base);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nseg = L.nseg;
-  int total_kb = 0;
-  for (int s = 0; s < nseg; ++s) total_kb += L.seg[z][s].kblocks;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < nseg; ++s) {
-      tma_prefetch_desc(&L.maps[L.seg[z][s].a_map]);
-      tma_prefetch_desc(&L.maps[L.seg[z][s].b_map]);
-      if (SPLIT) {
-        tma_prefetch_desc(&L.maps[L.seg[z][s].a_lo]);
-        tma_prefetch_desc(&L.maps[L.seg[z][s].b_lo]);
+    for (int z = 0; z < L.ndir; ++z)
+      for (int s = 0; s < nseg; ++s) {
+        tma_prefetch_desc(&L.maps[L.seg[z][s].a_map]);
+        tma_prefetch_desc(&L.maps[L.seg[z][s].b_map]);
+        if (SPLIT) {
+          tma_prefetch_desc(&L.maps[L.seg[z][s].a_lo]);
+          tma_prefetch_desc(&L.maps[L.seg[z][s].b_lo]);
+        }
       }
-    }
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), kTcEpiWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                 "r"((uint32_t)(BN * Cfg::kAccs)));
+                 "r"((uint32_t)Cfg::kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_acc = *tmem_slot_p;
+  const uint32_t tmem_base = *tmem_slot_p;
   if (threadIdx.x == 0) tc_stamp(trace, 2);
 
+  // Every role walks the same tile sequence and skips the same dead tiles (tile_alive is a pure function of
+  // the tile), so the pipeline counters stay in lock-step without any cross-role communication.
   if (warp == 0) {
-    if (lane == 0) {
-      int it = 0;
-      for (int s = 0; s < nseg; ++s) {
-        const TcSeg sg = L.seg[z][s];
-        const CUtensorMap* ma = &L.maps[sg.a_map];
-        const CUtensorMap* mb = &L.maps[sg.b_map];
-        constexpr int kpb = 128 / OperandFmt<PREC>::kElemBytes;
-        for (int kb = 0; kb < sg.kblocks; ++kb, ++it) {
-          const int st = it % Cfg::kStages;
-          const uint32_t ph = (it / Cfg::kStages) & 1;
-          mbar_wait(empty_bar(st), ph ^ 1);
-          const uint32_t sa = base + st * Cfg::kStageBytes;
-          mbar_expect_tx(full_bar(st), (uint32_t)(Cfg::kPlanes * (Cfg::kATile + bn * 128)));
-          tma_load_2d(sa, ma, full_bar(st), kb * kpb, m0);
-          tma_load_2d(sa + Cfg::kABytes, mb, full_bar(st), kb * kpb, n0);
-          if (SPLIT) {
-            tma_load_2d(sa + Cfg::kATile, &L.maps[sg.a_lo], full_bar(st), kb * kpb, m0);
-            tma_load_2d(sa + Cfg::kABytes + Cfg::kBTile, &L.maps[sg.b_lo], full_bar(st), kb * kpb, n0);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A/B = bf16 (1) or tf32 (2), both K-major, N>>3, M>>4
-      const uint32_t fmt = TF32 ? 2u : (PREC == RE2NN_PREC_FP16X3 ? 0u : 1u);   // 0 = f16, 1 = bf16, 2 = tf32
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((128u >> 4) << 24);
-      for (int it = 0; it < total_kb; ++it) {
-        const int st = it % Cfg::kStages;
-        const uint32_t ph = (it / Cfg::kStages) & 1;
-        mbar_wait(full_bar(st), ph);
-        if (it < 24) tc_stamp(trace, 8 + it);   // debug: when did k-block `it` land?
-        tc_fence_after();
-        const uint32_t sa = base + st * Cfg::kStageBytes;
-        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + Cfg::kABytes);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)   // 4 x 32-byte K steps per 128-byte block (16 bf16 / 8 tf32 each)
-          tc_mma<TF32>(tmem_acc, da + 2u * k, db + 2u * k, idesc, (it | k) != 0 ? 1u : 0u);
-        if (SPLIT) {   // residual terms: lo*hi and hi*lo (lo*lo is below fp32 resolution)
-          const uint64_t dal = make_smem_desc(sa + Cfg::kATile), dbl = make_smem_desc(sa + Cfg::kABytes + Cfg::kBTile);
-          const uint32_t acc_lo = TWOACC ? tmem_acc + (uint32_t)BN : tmem_acc;   // fp16 split: scaled residual accumulator
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            tc_mma<TF32>(acc_lo, dal + 2u * k, db + 2u * k, idesc, TWOACC ? ((it | k) != 0 ? 1u : 0u) : 1u);
-            tc_mma<TF32>(acc_lo, da + 2u * k, dbl + 2u * k, idesc, 1u);
-          }
-        }
-        tc_commit(empty_bar(st));     // frees the smem slot once these MMAs have read it
-      }
-      tc_commit(tmem_full);           // accumulator complete
-      tc_stamp(trace, 3);             // all MMAs issued
-    }
-  } else {
-    // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31.  tcgen05.ld hands lane i the 32 columns of
-    // row i; a 32x33 shared-memory transpose turns that into "lane = column" so that every global access
-    // of the epilogue functor is a full contiguous row segment (128 B fp32 / 64 B bf16 per warp request).
-    const Epi epi = epi_in.for_dir(z);       // direction-bound copy: plain members, no per-element z indexing
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int ew = warp - 2;                // epilogue warp index 0..7
-    const int half = ew >> 2;               // which interleaved set of 32-column chunks this warp takes
-    const int mrow0 = m0 + q * 32;
-    // all pipeline stages are drained once tmem_full fires: stage memory doubles as the transpose buffer;
-    // the row contexts live behind the barriers (never touched by TMA)
-    float* tbuf = reinterpret_cast<float*>(gen_base) + ew * (32 * 33);
-    int* ctx = reinterpret_cast<int*>(gen_base + Cfg::kStages * Cfg::kStageBytes + 128) + ew * 64;   // [vrow x32 | orow x32]
-    {
-      RowCtx mine{0, -1, false};
-      if (mrow0 + lane < L.M) mine = epi.row(mrow0 + lane);
-      ctx[lane] = mine.vrow;
-      ctx[32 + lane] = mine.orow;   // (alive is only consumed by the fp32 training path; here alive <=> orow >= 0 or unused)
-    }
-    __syncwarp();
-    const int nrows = min(32, L.M - mrow0);
-    bool acc_ready = false;
-#pragma unroll 1
-    for (int c0 = half * 32; c0 < bn; c0 += 32 * (kTcEpiWarps / 4)) {
-      if (n0 + c0 >= L.N) break;     // warp-uniform
-      const int n = n0 + c0 + lane;
-      const bool col_ok = n < L.N && c0 + lane < bn;
-      const Col cc = col_ok ? epi.col(n) : Col{0.f, 0.f};
-      // phase 1: every dependent global load of this 32x32 block in flight at once
-      Pre pre[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        pre[i] = Pre{0.f, 0.f};
-        if (col_ok && i < nrows) pre[i] = epi.prefetch(RowCtx{ctx[i], ctx[32 + i], ctx[32 + i] >= 0}, mrow0 + i, n);
-      }
-      if (!acc_ready) {
-        if (ew == 0 && lane == 0) tc_stamp(trace, 4);   // first prefetch batch issued
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        acc_ready = true;
-        if (ew == 0 && lane == 0) tc_stamp(trace, 5);   // accumulator ready
-      }
-      uint32_t r[32];
-      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      if (TWOACC) {
-        uint32_t r2[32];
-        tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), r2);
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          tbuf[lane * 33 + j] = fmaf(__uint_as_float(r2[j]), 1.f / kFp16LoScale, __uint_as_float(r[j]));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
-      }
-      __syncwarp();
-      // phase 2: lane = column, rows in batches of 16: all accumulator reads first, then 16 independent
-      // epilogue evaluations (the compiler interleaves their MUFU / convert / store chains), unguarded when the
-      // 32x32 block is interior
-      const bool interior = nrows == 32 && n0 + c0 + 32 <= L.N && c0 + 32 <= bn;   // warp-uniform
-#pragma unroll
-      for (int h0 = 0; h0 < 32; h0 += 16) {
-        float av[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) av[i] = tbuf[(h0 + i) * 33 + lane];
-        if (interior) {
-          float hv[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) hv[i] = epi.compute(cc, av[i], pre[h0 + i]);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int o = ctx[32 + h0 + i];
-            epi.store(cc, RowCtx{ctx[h0 + i], o, o >= 0}, mrow0 + h0 + i, n, hv[i], av[i], pre[h0 + i]);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (col_ok && h0 + i < nrows) {
-              const int o = ctx[32 + h0 + i];
-              epi.apply(cc, RowCtx{ctx[h0 + i], o, o >= 0}, mrow0 + h0 + i, n, av[i], pre[h0 + i]);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int z = tile / tiles_per_dir, rem = tile - z * tiles_per_dir;
+      const int mt = rem / n_tiles, nt = rem - mt * n_tiles;
+      if (!epi_in.tile_alive(z, mt)) continue;
+      const int m0 = mt * 128, n0 = nt * bn;
+      if (lane == 0) {
+        for (int s = 0; s < nseg; ++s) {
+          const TcSeg sg = L.seg[z][s];
+          const CUtensorMap* ma = &L.maps[sg.a_map];
+          const CUtensorMap* mb = &L.maps[sg.b_map];
+          for (int kb = 0; kb < sg.kblocks; ++kb, ++it) {
+            const int st = it % Cfg::kStages;
+            const uint32_t ph = (it / Cfg::kStages) & 1;
+            mbar_wait(empty_bar(st), ph ^ 1);
+            const uint32_t sa = base + st * Cfg::kStageBytes;
+            mbar_expect_tx(full_bar(st), (uint32_t)(Cfg::kPlanes * (Cfg::kATile + bn * 128)));
+            tma_load_2d(sa, ma, full_bar(st), kb * kpb, m0);
+            tma_load_2d(sa + Cfg::kABytes, mb, full_bar(st), kb * kpb, n0);
+            if (SPLIT) {
+              tma_load_2d(sa + Cfg::kATile, &L.maps[sg.a_lo], full_bar(st), kb * kpb, m0);
+              tma_load_2d(sa + Cfg::kABytes + Cfg::kBTile, &L.maps[sg.b_lo], full_bar(st), kb * kpb, n0);
             }
           }
         }
       }
       __syncwarp();
+      if (!OVERLAP) {   // transpose buffers alias the stages: wait until this tile's epilogue is done with them
+        asm volatile("bar.sync 1, %0;" ::"r"(kTcThreads) : "memory");
+      }
     }
-    if (!acc_ready) {
-      mbar_wait(tmem_full, 0);
-      tc_fence_after();
+  } else if (warp == 1) {
+    // instruction descriptor: D=f32, A/B = f16 (0) / bf16 (1) / tf32 (2), both K-major, N>>3, M>>4
+    const uint32_t fmt = TF32 ? 2u : (PREC == RE2NN_PREC_FP16X3 ? 0u : 1u);
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((128u >> 4) << 24);
+    int it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int z = tile / tiles_per_dir, rem = tile - z * tiles_per_dir;
+      const int mt = rem / n_tiles;
+      if (!epi_in.tile_alive(z, mt)) continue;
+      if (lane == 0) {
+        int total_kb = 0;
+        for (int s = 0; s < nseg; ++s) total_kb += L.seg[z][s].kblocks;
+        const int as = OVERLAP ? (tcount & 1) : 0;
+        const uint32_t aph = OVERLAP ? ((tcount >> 1) & 1) : (tcount & 1);
+        mbar_wait(tempty_bar(as), aph ^ 1);          // epilogue has drained this accumulator set
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(as * Cfg::kAccCols);
+        for (int j = 0; j < total_kb; ++j, ++it) {
+          const int st = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait(full_bar(st), ph);
+          if (tcount == 0 && j < 24) tc_stamp(trace, 8 + j);   // debug: when did k-block j of the first tile land?
+          tc_fence_after();
+          const uint32_t sa = base + st * Cfg::kStageBytes;
+          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // 4 x 32-byte K steps per 128-byte block (16 x 16-bit / 8 x tf32 each)
+            tc_mma<TF32>(tmem_acc, da + 2u * k, db + 2u * k, idesc, (j | k) != 0 ? 1u : 0u);
+          if (SPLIT) {   // residual terms: lo*hi and hi*lo (lo*lo is below fp32 resolution)
+            const uint64_t dal = make_smem_desc(sa + Cfg::kATile), dbl = make_smem_desc(sa + Cfg::kABytes + Cfg::kBTile);
+            const uint32_t acc_lo = TWOACC ? tmem_acc + (uint32_t)BN : tmem_acc;   // fp16 split: scaled residual accumulator
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              tc_mma<TF32>(acc_lo, dal + 2u * k, db + 2u * k, idesc, TWOACC ? ((j | k) != 0 ? 1u : 0u) : 1u);
+              tc_mma<TF32>(acc_lo, da + 2u * k, dbl + 2u * k, idesc, 1u);
+            }
+          }
+          tc_commit(empty_bar(st));     // frees the smem slot once these MMAs have read it
+        }
+        tc_commit(tfull_bar(as));       // accumulator complete
+        if (tcount == 0) tc_stamp(trace, 3);
+      }
+      ++tcount;
+      __syncwarp();
+      if (!OVERLAP) {
+        asm volatile("bar.sync 1, %0;" ::"r"(kTcThreads) : "memory");
+      }
     }
-    tc_fence_before();
-    if (ew == 0 && lane == 0) tc_stamp(trace, 6);       // epilogue of warp 2 done
+  } else {
+    // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31.  tcgen05.ld hands lane i the 32 columns of
+    // row i; a 32x33 shared-memory transpose turns that into "lane = column" so that every global access
+    // of the epilogue functor is a full contiguous row segment (128 B fp32 / 64 B 16-bit per warp request).
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int ew = warp - 2;                // epilogue warp index 0..7
+    const int half = ew >> 2;               // which interleaved set of 32-column chunks this warp takes
+    float* tbuf = tbuf_base + ew * (32 * 33);
+    int* ctx = ctx_base + ew * 64;          // [vrow x32 | orow x32]
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int z = tile / tiles_per_dir, rem = tile - z * tiles_per_dir;
+      const int mt = rem / n_tiles, nt = rem - mt * n_tiles;
+      if (!epi_in.tile_alive(z, mt)) continue;
+      const int m0 = mt * 128, n0 = nt * bn;
+      const Epi epi = epi_in.for_dir(z);    // direction-bound copy: plain members, no per-element z indexing
+      const int mrow0 = m0 + q * 32;
+      const int as = OVERLAP ? (tcount & 1) : 0;
+      const uint32_t aph = OVERLAP ? ((tcount >> 1) & 1) : (tcount & 1);
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(as * Cfg::kAccCols);
+      {
+        RowCtx mine{0, -1, false};
+        if (mrow0 + lane < L.M) mine = epi.row(mrow0 + lane);
+        ctx[lane] = mine.vrow;
+        ctx[32 + lane] = mine.orow;
+      }
+      __syncwarp();
+      const int nrows = min(32, L.M - mrow0);
+      bool acc_ready = false;
+#pragma unroll 1
+      for (int c0 = half * 32; c0 < bn; c0 += 32 * (kTcEpiWarps / 4)) {
+        if (n0 + c0 >= L.N) break;     // warp-uniform
+        const int n = n0 + c0 + lane;
+        const bool col_ok = n < L.N && c0 + lane < bn;
+        const Col cc = col_ok ? epi.col(n) : Col{0.f, 0.f};
+        // phase 1: every dependent global load of this 32x32 block in flight at once
+        Pre pre[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          pre[i] = Pre{0.f, 0.f};
+          if (col_ok && i < nrows) pre[i] = epi.prefetch(RowCtx{ctx[i], ctx[32 + i], ctx[32 + i] >= 0}, mrow0 + i, n);
+        }
+        if (!acc_ready) {
+          if (tcount == 0 && ew == 0 && lane == 0) tc_stamp(trace, 4);   // first prefetch batch issued
+          mbar_wait(tfull_bar(as), aph);
+          tc_fence_after();
+          acc_ready = true;
+          if (tcount == 0 && ew == 0 && lane == 0) tc_stamp(trace, 5);   // accumulator ready
+        }
+        uint32_t r[32];
+        tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        if (TWOACC) {
+          uint32_t r2[32];
+          tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), r2);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            tbuf[lane * 33 + j] = fmaf(__uint_as_float(r2[j]), 1.f / kFp16LoScale, __uint_as_float(r[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
+        }
+        __syncwarp();
+        // phase 2: lane = column, rows in batches of 16: all accumulator reads first, then 16 independent
+        // epilogue evaluations (their MUFU / convert chains interleave), then the stores; unguarded when the
+        // 32x32 block is interior
+        const bool interior = nrows == 32 && n0 + c0 + 32 <= L.N && c0 + 32 <= bn;   // warp-uniform
+#pragma unroll
+        for (int h0 = 0; h0 < 32; h0 += 16) {
+          float av[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) av[i] = tbuf[(h0 + i) * 33 + lane];
+          if (interior) {
+            float hv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) hv[i] = epi.compute(cc, av[i], pre[h0 + i]);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int o = ctx[32 + h0 + i];
+              epi.store(cc, RowCtx{ctx[h0 + i], o, o >= 0}, mrow0 + h0 + i, n, hv[i], av[i], pre[h0 + i]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (col_ok && h0 + i < nrows) {
+                const int o = ctx[32 + h0 + i];
+                epi.apply(cc, RowCtx{ctx[h0 + i], o, o >= 0}, mrow0 + h0 + i, n, av[i], pre[h0 + i]);
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (!acc_ready) {
+        mbar_wait(tfull_bar(as), aph);
+        tc_fence_after();
+      }
+      // this warp is done reading the accumulator set: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(as)) : "memory");
+      }
+      if (tcount == 0 && ew == 0 && lane == 0) tc_stamp(trace, 6);       // epilogue of the first tile done
+      ++tcount;
+      if (!OVERLAP) {
+        asm volatile("bar.sync 1, %0;" ::"r"(kTcThreads) : "memory");
+      }
+    }
   }
+  tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) tc_stamp(trace, 7);
   if (tl_idx < 4096) g_tc_timeline[2 * tl_idx + 1] = globaltimer_ns();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)(BN * Cfg::kAccs)));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols));
   }
 }
 
@@ -453,7 +521,8 @@ inline cudaError_t launch_tc_bn(const TcLaunch& L, const Epi& epi, cudaStream_t 
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  dim3 grid(cdiv(L.M, 128), cdiv(L.N, L.bn), L.ndir);
+  const long tiles = (long)cdiv(L.M, 128) * cdiv(L.N, L.bn) * L.ndir;
+  const int grid = (int)std::min<long>(tiles, 148);          // one persistent CTA per SM
   tc_gemm_kernel<PREC, BN, Epi><<<grid, kTcThreads, Cfg::kSmem, st>>>(L, epi);
   return cudaGetLastError();
 }

@@ -23,6 +23,7 @@ int set_error(const char* fmt, ...) {
 
 // ---- workspace ----------------------------------------------------------------------------------
 struct RecWs {
+  int* tile_last[2];
   void* Q[2];
   void* Hbar[2][2];   // [parity][dir]
   void* Hst[2];
@@ -43,6 +44,7 @@ static size_t carve(const re2nn_recurrence_args& a, char* base, RecWs* ws) {
   RecWs w;
   memset(&w, 0, sizeof(w));
   for (int z = 0; z < 2; ++z) {
+    w.tile_last[z] = (int*)take((size_t)cdiv(a.B, 128) * sizeof(int));
     w.Q[z] = take(operand_bytes(prec, a.B, a.R));
     w.Hbar[0][z] = take(operand_bytes(prec, a.B, a.S));
     w.Hbar[1][z] = take(operand_bytes(prec, a.B, a.S));
@@ -55,6 +57,22 @@ static size_t carve(const re2nn_recurrence_args& a, char* base, RecWs* ws) {
   off += weight_prep_carve(prec, a.S, a.R, a.farnn, base ? base + off : nullptr, &w.wp);
   if (ws) *ws = w;
   return off;
+}
+
+// last step at which any row of a 128-row tile is alive: fwd k < n, bwd k < n-1  (one warp-reduced max per tile)
+__global__ void __launch_bounds__(128) tile_last_kernel(const int64_t* __restrict__ len, int B, int* __restrict__ fwd,
+                                                        int* __restrict__ bwd) {
+  const int m = blockIdx.x * 128 + threadIdx.x;
+  int n = m < B ? (int)len[m] : 0;
+  n = __reduce_max_sync(0xffffffffu, n);
+  __shared__ int sh[4];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    n = max(max(sh[0], sh[1]), max(sh[2], sh[3]));
+    fwd[blockIdx.x] = n - 1;
+    bwd[blockIdx.x] = n - 2;
+  }
 }
 
 // ---- init: step "-1" ------------------------------------------------------------------------------
@@ -133,6 +151,8 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
   const size_t h_plane = (size_t)B * ldh, q_plane = (size_t)B * ldq;
 
   if (int rc = weight_prep_run<PREC>(a, w.wp, st)) return rc;
+  tile_last_kernel<<<cdiv(B, 128), 128, 0, st>>>(a.lengths, B, w.tile_last[0], w.tile_last[1]);
+  RE2NN_LAUNCH_CHECK();
   {
     size_t total = (size_t)2 * B * S;
     int blocks = (int)((total + 255) / 256);
@@ -178,7 +198,7 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
   p.B = B; p.Lpad = a.Lpad; p.L = L; p.S = S; p.R = R;
   p.farnn = a.farnn; p.nl = a.update_nonlinear; p.v_mode = a.v_mode; p.full_pad = a.full_pad;
   p.sig_k = a.sigmoid_exponent;
-  p.x = a.x; p.len = a.lengths; p.vtab = a.vtab; p.gtab = a.gtab; p.ldg = S * a.farnn;
+  p.x = a.x; p.len = a.lengths; p.tile_last[0] = w.tile_last[0]; p.tile_last[1] = w.tile_last[1]; p.vtab = a.vtab; p.gtab = a.gtab; p.ldg = S * a.farnn;
   p.o = a.o; p.hinit[0] = a.h0; p.hinit[1] = a.hT;
   p.ldq = ldq; p.q_plane = q_plane; p.ldh = ldh; p.h_plane = h_plane;
   p.out[0] = a.alpha; p.out[1] = a.beta;
