@@ -1,0 +1,94 @@
+"""GPU: ragged / degenerate shapes through every arithmetic mode (tile tails, single tokens, odd dimensions)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import oracle_params, rel_err
+from oracle import re2nn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+class _Z(dict):
+    files = property(lambda self: list(self.keys()))
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+CASES = [
+    # V, S, R, C, D, B, Lmax, lengths override
+    (11, 5, 3, 2, 4, 1, 1, None),                 # one sequence, one token
+    (11, 5, 3, 2, 4, 3, 6, [1, 6, 1]),            # single-token sequences next to a full one
+    (40, 17, 9, 3, 7, 130, 5, None),              # batch tile tail (128 + 2), odd S / R / C
+    (40, 33, 20, 6, 5, 257, 9, None),             # two full tiles + 1 row
+    (40, 64, 40, 4, 8, 64, 3, [3] * 64),          # all sequences the same length
+]
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'tf32x3', 'fp16x3', 'bf16'])
+@pytest.mark.parametrize('case', range(len(CASES)))
+@pytest.mark.parametrize('farnn,crf', [(0, 1), (2, 0)])
+def test_edge_shapes(case, prec, farnn, crf):
+    import re2nn_seq_b200 as r
+    from re2nn_seq_b200 import ops, synth
+    if prec != 'fp32' and not ops.has_tcgen05():
+        pytest.skip('no tcgen05')
+    V, S, R, C, D, B, Lmax, lens_override = CASES[case]
+    args = synth.make_args(farnn=farnn, use_crf=crf, update_nonlinear='tanh', beta=0.2)
+    f = synth.make_decompose_factors(case, V, S, R, C, D, lang_frac=0.5, dtype=np.float32)
+    x, lens, lab = synth.make_batch(case + 1, B, Lmax, V, C)
+    if lens_override is not None:
+        lens = np.asarray(lens_override, np.int64)
+        pad = np.arange(Lmax)[None, :] >= lens[:, None]
+        x[pad] = V
+    torch.manual_seed(case)
+    m = r.FARNN_S_D_W_I_S(args=args, o_idx=0, **f)
+    with torch.no_grad():
+        if farnn:
+            for n in ('Wss1', 'Wrs1', 'Wss2', 'Wrs2'):
+                getattr(m, n).mul_(0.2)
+            m.bs1.fill_(0.1)
+            m.bs2.fill_(-0.1)
+        if crf:
+            m.crf.transitions.copy_(torch.from_numpy(synth.crf_transitions(case, m.C)))
+    m = m.cuda()
+    m.precision = prec
+    with torch.no_grad():
+        sc = m.forward_scores(_t(x), _t(lens)).cpu().numpy()
+        loss, pred, true = m.forward_local(_t(x), _t(lab), _t(lens), train=True)
+        _, pred_g, _ = m.forward_local(_t(x), _t(lab), _t(lens), train=False)          # CUDA-graph path
+    z = _Z({'p.' + k: v.detach().cpu().numpy() for k, v in m.state_dict().items()})
+    L = int(lens.max())
+    truth, _, _ = orc.decompose_scores(oracle_params(z, np.float64), x, lens, args)
+    mask = orc.length_mask(lens, L)
+    tol = 3e-2 if prec == 'bf16' else 1e-5
+    assert rel_err(sc[mask], truth[mask]) < tol
+    assert (sc[~mask] == 0).all()                                   # rows past the length are written as zeros
+    assert torch.equal(pred, pred_g)
+    assert pred.shape[0] == int(lens.sum()) == true.shape[0]
+    if prec != 'bf16':
+        o_loss, o_pred, o_true, _ = orc.decompose_forward_local(oracle_params(z, np.float32), x, lab, lens, args, 0, True)
+        np.testing.assert_array_equal(pred.cpu().numpy(), o_pred)
+        np.testing.assert_array_equal(true.cpu().numpy(), o_true)
+        assert rel_err(loss.item(), o_loss) < 1e-5
+
+
+def test_argument_errors_are_reported_not_fatal():
+    """Bad arguments come back as RuntimeError with a message (the reference raises Python exceptions too)."""
+    import re2nn_seq_b200 as r
+    from re2nn_seq_b200 import synth
+    args = synth.make_args(farnn=0, use_crf=1, update_nonlinear='tanh')
+    f = synth.make_decompose_factors(0, 11, 5, 3, 2, 4, dtype=np.float32)
+    m = r.FARNN_S_D_W_I_S(args=args, o_idx=0, **f).cuda()
+    x, lens, lab = synth.make_batch(1, 2, 4, 11, 2)
+    with pytest.raises(RuntimeError, match='float32|int64|contiguous|expected'):
+        with torch.no_grad():
+            m.forward_scores(_t(x).int(), _t(lens))                  # wrong index dtype
+    with pytest.raises(AssertionError):
+        m.crf.neg_log_likelihood_loss(torch.zeros(2, 4, 3, device='cuda'), None, _t(lab), lengths=_t(lens))   # crf.py:58
+    m.precision = 'no-such-mode'
+    with pytest.raises(KeyError):
+        with torch.no_grad():
+            m.forward_scores(_t(x), _t(lens))
