@@ -6,6 +6,8 @@
 // the running partition is exchanged through a per-warp shared buffer.  Arithmetic order follows the
 // reference exactly where it decides an argmax: cur = (feat_j + trans_ij) + part_i, strict ">" keeps
 // the first maximal index like torch.max(dim).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace re2nn {
@@ -198,25 +200,30 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_nll_kernel(
 
 // CRF backward: marginals by the backward recursion, reusing the saved forward partitions.
 //   dfeats[b,t,j] = gs * (P(y_t=j) - [tag_t=j]);  dtrans[i,j] += gs * (sum_t P(y_{t-1}=i,y_t=j) - gold counts)
+// Every warp owns a private T x T accumulator in shared memory (row pitch padded to an odd number of words:
+// lanes own rows, so the pitch decides the bank) => plain read-modify-write, no shared atomics; the CTA folds
+// its warps' copies together and issues one global atomicAdd per element.
 template <bool TS>
-__global__ void __launch_bounds__(kCrfWarps * 32) crf_nll_backward_kernel(
+__global__ void crf_nll_backward_kernel(
     const float* __restrict__ feats, const float* __restrict__ trans_g, const int64_t* __restrict__ len,
     const int64_t* __restrict__ tags, const float* __restrict__ part_save, const float* __restrict__ gscale, int B,
     int L, int Ltags, int T, float* __restrict__ dfeats, float* __restrict__ dtrans) {
   extern __shared__ float smem[];
+  const int nw = blockDim.x >> 5;
   const int Tp = (T + 31) & ~31;
-  float* s_trans = smem;                        // T*T (if TS)
-  float* s_dtr = smem + (TS ? T * T : 0);       // T*T accumulator for this CTA
-  float* s_beta = s_dtr + T * T;                // kCrfWarps * 2 * Tp
+  const int Tq = T | 1;                          // odd pitch of the private accumulators
+  float* s_trans = smem;                         // T*T (if TS)
+  float* s_dtr = smem + (TS ? T * T : 0);        // nw * T * Tq
+  float* s_beta = s_dtr + (size_t)nw * T * Tq;   // nw * 2 * Tp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
-    if (TS) s_trans[i] = trans_g[i];
-    s_dtr[i] = 0.f;
-  }
+  if (TS)
+    for (int i = threadIdx.x; i < T * T; i += blockDim.x) s_trans[i] = trans_g[i];
+  for (int i = threadIdx.x; i < nw * T * Tq; i += blockDim.x) s_dtr[i] = 0.f;
   __syncthreads();
   const float* tr = TS ? s_trans : trans_g;
   const float gs = gscale ? *gscale : 1.f;
-  const int b = blockIdx.x * kCrfWarps + warp;
+  float* dw = s_dtr + (size_t)warp * T * Tq;
+  const int b = blockIdx.x * nw + warp;
   if (b < B) {
     const int n = (int)len[b];
     float* ba = s_beta + warp * 2 * Tp;   // beta_t
@@ -239,15 +246,18 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_nll_backward_kernel(
     for (int t = n - 1; t >= 0; --t) {
       const float* pt = ps + (size_t)t * T;
       const int gold = (int)tg[t];
-      // unary marginal at t  (+ STOP column / START row of dtrans)
+      // unary marginal at t  (+ STOP column / START row of dtrans); lane owns j => distinct addresses
       for (int j = lane; j < T; j += 32) {
-        float mg = expf(pt[j] + ba[j] - logZ);
-        df[(size_t)t * T + j] = gs * (mg - (j == gold ? 1.f : 0.f));
-        if (t == n - 1) atomicAdd(&s_dtr[j * T + (T - 1)], gs * (mg - (j == gold ? 1.f : 0.f)));
-        if (t == 0) atomicAdd(&s_dtr[(T - 2) * T + j], gs * (mg - (j == gold ? 1.f : 0.f)));
+        const float d = gs * (expf(pt[j] + ba[j] - logZ) - (j == gold ? 1.f : 0.f));
+        df[(size_t)t * T + j] = d;
+        if (t == n - 1) dw[j * Tq + (T - 1)] += d;
       }
-      if (t == 0) break;
-      // pairwise marginals (t-1 -> t) and beta_{t-1}
+      __syncwarp();
+      if (t == 0) {
+        for (int j = lane; j < T; j += 32) dw[(T - 2) * Tq + j] += df[j];
+        break;
+      }
+      // pairwise marginals (t-1 -> t) and beta_{t-1}; lane owns source rows i
       const float* pp = ps + (size_t)(t - 1) * T;
       const float* ft = fb + (size_t)t * T;
       const int gprev = (int)tg[t - 1];
@@ -255,14 +265,14 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_nll_backward_kernel(
         float mx = -INFINITY;
         for (int j = 0; j < T; ++j) mx = fmaxf(mx, (tr[i * T + j] + __ldg(ft + j)) + ba[j]);
         float sm = 0.f;
-        const float pi = pp[i];
+        const float pi = pp[i] - logZ;
+        float* dwi = dw + i * Tq;
         for (int j = 0; j < T; ++j) {
-          float e = (tr[i * T + j] + __ldg(ft + j)) + ba[j];
+          const float e = (tr[i * T + j] + __ldg(ft + j)) + ba[j];
           sm += expf(e - mx);
-          float pw = expf(pi + e - logZ);
-          float d = pw - ((i == gprev && j == gold) ? 1.f : 0.f);
-          if (d != 0.f) atomicAdd(&s_dtr[i * T + j], gs * d);
+          dwi[j] += gs * expf(pi + e);
         }
+        if (i == gprev) dwi[gold] -= gs;
         bb[i] = mx + logf(sm);
       }
       __syncwarp();
@@ -273,7 +283,9 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_nll_backward_kernel(
   }
   __syncthreads();
   for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
-    float v = s_dtr[i];
+    const int r = i / T, c = i - r * T;
+    float v = 0.f;
+    for (int w = 0; w < nw; ++w) v += s_dtr[(size_t)w * T * Tq + r * Tq + c];
     if (v != 0.f) atomicAdd(dtrans + i, v);
   }
 }
@@ -479,21 +491,26 @@ int re2nn_crf_nll_backward(const float* feats, const float* transitions, const i
                            const float* part_save, const float* gscale, int B, int L, int Ltags, int T, float* dfeats,
                            float* dtrans, void* stream) {
   RE2NN_CHECK(feats && transitions && lengths && tags && part_save && dfeats && dtrans, "crf_nll_backward: null tensor");
-  const int Tp = (T + 31) & ~31;
-  const size_t base = (size_t)kCrfWarps * 2 * Tp * 4 + (size_t)T * T * 4;
-  const size_t with_tr = base + (size_t)T * T * 4;
-  const int grid = cdiv(B, kCrfWarps);
+  const int Tp = (T + 31) & ~31, Tq = T | 1;
+  const size_t per_warp = ((size_t)T * Tq + 2 * Tp) * 4;
+  const size_t tr_bytes = (size_t)T * T * 4;
   cudaStream_t st = (cudaStream_t)stream;
-  RE2NN_CUDA(cudaMemsetAsync(dtrans, 0, (size_t)T * T * 4, st));
-  if (with_tr <= kSmemLimit) {
-    RE2NN_CUDA(cudaFuncSetAttribute(crf_nll_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_tr));
-    crf_nll_backward_kernel<true><<<grid, kCrfWarps * 32, with_tr, st>>>(feats, transitions, lengths, tags, part_save,
-                                                                         gscale, B, L, Ltags, T, dfeats, dtrans);
+  RE2NN_CUDA(cudaMemsetAsync(dtrans, 0, tr_bytes, st));
+  // as many warps (sequences) per CTA as the private accumulators allow, transitions in smem when they still fit
+  bool ts = tr_bytes + per_warp <= kSmemLimit;
+  size_t avail = kSmemLimit - (ts ? tr_bytes : 0);
+  int nw = (int)std::min<size_t>(kCrfWarps, avail / per_warp);
+  RE2NN_CHECK(nw >= 1, "crf_nll_backward: tag set too large (T=%d)", T);
+  const size_t smem = (ts ? tr_bytes : 0) + nw * per_warp;
+  const int grid = cdiv(B, nw);
+  if (ts) {
+    RE2NN_CUDA(cudaFuncSetAttribute(crf_nll_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    crf_nll_backward_kernel<true><<<grid, nw * 32, smem, st>>>(feats, transitions, lengths, tags, part_save, gscale, B,
+                                                               L, Ltags, T, dfeats, dtrans);
   } else {
-    RE2NN_CHECK(base <= kSmemLimit, "crf_nll_backward: tag set too large (T=%d)", T);
-    RE2NN_CUDA(cudaFuncSetAttribute(crf_nll_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base));
-    crf_nll_backward_kernel<false><<<grid, kCrfWarps * 32, base, st>>>(feats, transitions, lengths, tags, part_save,
-                                                                       gscale, B, L, Ltags, T, dfeats, dtrans);
+    RE2NN_CUDA(cudaFuncSetAttribute(crf_nll_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    crf_nll_backward_kernel<false><<<grid, nw * 32, smem, st>>>(feats, transitions, lengths, tags, part_save, gscale,
+                                                                B, L, Ltags, T, dfeats, dtrans);
   }
   RE2NN_LAUNCH_CHECK();
   return 0;
