@@ -26,14 +26,15 @@ struct ALoadAlphaBeta {
   }
 };
 
-template <class Epi, class ALoad>
+// BM = 128 (8x4 micro-tile) for full grids, BM = 64 (4x4) when the 128-row tiling would leave SMs idle.
+template <int BM, class Epi, class ALoad>
 __global__ void __launch_bounds__(256) simt_gemm_kernel(const GemmProblem prob, const Epi epi_in, const ALoad aload) {
-  constexpr int BM = 128, BN = 64, BK = 16, TM = 8, TN = 4;
+  constexpr int BN = 64, BK = 16, TM = BM / 16, TN = 4;
   const int z = blockIdx.z;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int M = prob.M, N = prob.N;
   const int rows = min(BM, M - m0);
-  if (!epi_in.tile_alive(z, blockIdx.x)) return;   // BM == 128 == liveness tile
+  if (!epi_in.tile_alive(z, (int)(blockIdx.x * BM) / 128)) return;   // liveness is tracked per 128 rows
   const Epi epi = epi_in.for_dir(z);
 
   __shared__ __align__(16) float As[BK][BM + 4];
@@ -82,10 +83,12 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const GemmProblem prob, 
       for (int kk = 0; kk < BK; ++kk) {
         float a[TM], b[TN];
         const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * TM]);
-        const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * TM + 4]);
         const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * TN]);
         a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
-        a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+        if constexpr (TM == 8) {
+          const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * TM + 4]);
+          a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+        }
         b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
 #pragma unroll
         for (int i = 0; i < TM; ++i)
@@ -111,8 +114,14 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const GemmProblem prob, 
 
 template <class Epi, class ALoad>
 inline cudaError_t launch_simt_gemm(const GemmProblem& prob, const Epi& epi, const ALoad& aload, cudaStream_t st) {
-  dim3 grid(cdiv(prob.M, 128), cdiv(prob.N, 64), prob.ndir);
-  simt_gemm_kernel<Epi, ALoad><<<grid, 256, 0, st>>>(prob, epi, aload);
+  const long ctas128 = (long)cdiv(prob.M, 128) * cdiv(prob.N, 64) * prob.ndir;
+  if (ctas128 >= 148) {
+    dim3 grid(cdiv(prob.M, 128), cdiv(prob.N, 64), prob.ndir);
+    simt_gemm_kernel<128, Epi, ALoad><<<grid, 256, 0, st>>>(prob, epi, aload);
+  } else {
+    dim3 grid(cdiv(prob.M, 64), cdiv(prob.N, 64), prob.ndir);
+    simt_gemm_kernel<64, Epi, ALoad><<<grid, 256, 0, st>>>(prob, epi, aload);
+  }
   return cudaGetLastError();
 }
 
