@@ -281,7 +281,8 @@ def main():
         step_device()
         ev[i][1].record()
     barrier()
-    launches = (ops.launches() - l0) // a.steps
+    launches_total = ops.launches() - l0
+    launches = launches_total // a.steps
     total_ms = sum(s.elapsed_time(e) for s, e in ev)
 
     # ---- roofline pass: the same K steps again, every step-GEMM launch bracketed by CUDA events recorded
@@ -369,7 +370,7 @@ def main():
                                                'gemm2': prof_ms[2] / a.steps}},
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(xh.numel() * 8 + lh.numel() * 8 + yh.numel() * 8),
                     'd2h_bytes_per_step': int(n_tok * 8)},
-            'gpu_launches': int(launches), 'clocks': clocks,
+            'gpu_launches': int(launches_total), 'gpu_launches_per_step': int(launches), 'clocks': clocks,
         }
         if not a.no_cpu_baseline:
             try:

@@ -11,17 +11,24 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', 
               '--use_fast_math=false', '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 
 
-def _newest_source():
-    t = 0.0
-    for root, _, files in os.walk(CSRC):
-        for f in files:
-            t = max(t, os.path.getmtime(os.path.join(root, f)))
-    t = max(t, os.path.getmtime(os.path.join(HERE, '..', 'include', 're2nn_b200.h')))
-    return t
+def _source_hash():
+    """Content hash of every CUDA source + the public header (mtimes do not survive a snapshot copy)."""
+    import hashlib
+    h = hashlib.sha256()
+    files = [os.path.join(HERE, '..', 'include', 're2nn_b200.h')]
+    for root, _, names in os.walk(CSRC):
+        files += [os.path.join(root, f) for f in names if f.endswith(('.cu', '.cuh', '.h'))]
+    for f in sorted(files):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, 'rb').read())
+    h.update(' '.join(NVCC_FLAGS + SOURCES).encode())
+    return h.hexdigest()
 
 
 def build(force=False, verbose=False):
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source():
+    stamp = LIB + '.hash'
+    digest = _source_hash()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
         return LIB
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
     flags = [f for f in NVCC_FLAGS if not f.startswith('--use_fast_math')]
@@ -44,6 +51,8 @@ def build(force=False, verbose=False):
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError('link failed')
+    with open(stamp, 'w') as f:
+        f.write(digest)
     return LIB
 
 

@@ -27,6 +27,7 @@ struct __align__(64) TcLaunch {
   int bn;   // effective n-tile width (multiple of 16, <= BN): MMA N, TMA box rows of B, grid.y = ceil(N / bn)
 };
 typedef TcLaunch TcStepMaps;
+static bool g_tc_use_pdl = true;     // programmatic dependent launch between consecutive tcgen05 step kernels
 struct TcRecurrenceMaps { TcLaunch gate, g1[2], g2[2]; };
 
 // ---- host: tensor maps ---------------------------------------------------------------------------------
@@ -153,6 +154,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
+// Programmatic dependent launch: a step kernel may start (prologue: barrier init, TMEM alloc, descriptor
+// prefetch, row contexts) while the previous step kernel is still draining; griddep_wait() blocks until the
+// previous grid has completed and its writes are visible.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -310,11 +316,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_p;
   if (threadIdx.x == 0) tc_stamp(trace, 2);
+  griddep_launch_dependents();      // the next step kernel may begin its prologue as SMs free up
 
   // Every role walks the same tile sequence and skips the same dead tiles (tile_alive is a pure function of
   // the tile), so the pipeline counters stay in lock-step without any cross-role communication.
   if (warp == 0) {
     int it = 0;
+    griddep_wait();                 // A operands are written by the previous kernel
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int z = tile / tiles_per_dir, rem = tile - z * tiles_per_dir;
       const int mt = rem / n_tiles, nt = rem - mt * n_tiles;
@@ -350,6 +358,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
     const uint32_t fmt = TF32 ? 2u : (PREC == RE2NN_PREC_FP16X3 ? 0u : 1u);
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((128u >> 4) << 24);
     int it = 0, tcount = 0;
+    griddep_wait();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int z = tile / tiles_per_dir, rem = tile - z * tiles_per_dir;
       const int mt = rem / n_tiles;
@@ -403,6 +412,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
     float* tbuf = tbuf_base + ew * (32 * 33);
     int* ctx = ctx_base + ew * 64;          // [vrow x32 | orow x32]
     int tcount = 0;
+    griddep_wait();                         // state / gate buffers are written by the previous kernel
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int z = tile / tiles_per_dir, rem = tile - z * tiles_per_dir;
       const int mt = rem / n_tiles, nt = rem - mt * n_tiles;
@@ -523,8 +533,18 @@ inline cudaError_t launch_tc_bn(const TcLaunch& L, const Epi& epi, cudaStream_t 
   }
   const long tiles = (long)cdiv(L.M, 128) * cdiv(L.N, L.bn) * L.ndir;
   const int grid = (int)std::min<long>(tiles, 148);          // one persistent CTA per SM
-  tc_gemm_kernel<PREC, BN, Epi><<<grid, kTcThreads, Cfg::kSmem, st>>>(L, epi);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_tc_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, tc_gemm_kernel<PREC, BN, Epi>, L, epi);
 }
 
 template <int PREC, class Epi>
