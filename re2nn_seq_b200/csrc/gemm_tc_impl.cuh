@@ -203,9 +203,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-constexpr int kTcEpiWarps = 8;                       // two warps per TMEM lane quarter
+constexpr int kTcEpiWarps = 8;                       // two warps per TMEM lane quarter (16 measured slower: spills, fewer stages)
 constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;
 constexpr int kTcTbufBytes = kTcEpiWarps * 32 * 33 * 4;   // per-warp 32x33 fp32 transpose buffers
+constexpr int kTcCtxBytes = kTcEpiWarps * 64 * 4;         // per-warp row contexts [vrow x32 | orow x32]
 constexpr int kTcSmemLimit = 227 * 1024;
 
 // One pipeline stage holds, per 128-byte k-block: the A tile (128 rows) and the B tile (BN rows); the split
@@ -221,7 +222,7 @@ template <int PREC, int BN> struct TcCfg {
   static constexpr int kABytes = kATile * kPlanes;
   static constexpr int kBBytes = kBTile * kPlanes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kFixedBase = 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*row ctx*/;
+  static constexpr int kFixedBase = 1024 /*align slack*/ + 256 /*barriers*/ + kTcCtxBytes;
   static constexpr bool kOverlap = BN * kAccs * 2 <= 512 &&                                  // two accumulator sets in TMEM
                                    (kTcSmemLimit - kFixedBase - kTcTbufBytes) / kStageBytes >= 2;   // + private transpose buffers
   static constexpr int kAccCols = BN * kAccs;                      // TMEM columns of one accumulator set
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
   const uint32_t tmem_slot = bars + 8u * (2 * Cfg::kStages + 4);
   volatile uint32_t* tmem_slot_p = (volatile uint32_t*)(gen_base + kStageRegion + 8 * (2 * Cfg::kStages + 4));
   int* ctx_base = reinterpret_cast<int*>(gen_base + kStageRegion + 256);
-  float* tbuf_base = reinterpret_cast<float*>(OVERLAP ? gen_base + kStageRegion + 256 + 2048 : gen_base);
+  float* tbuf_base = reinterpret_cast<float*>(OVERLAP ? gen_base + kStageRegion + 256 + kTcCtxBytes : gen_base);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nseg = L.nseg;
