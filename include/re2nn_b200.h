@@ -189,8 +189,8 @@ typedef struct re2nn_onehot_args {
   int32_t full_pad;
   const int64_t* x;
   const int64_t* lengths;
-  const float* language;       /* (V+1) x S x S */
-  const float* W;              /* S x S */
+  const float* language;       /* (V+1) x S x S; with W == NULL: the pre-summed language + W (re2nn_onehot_sum_tensor) */
+  const float* W;              /* S x S, or NULL */
   const float* o;              /* S */
   const float* h0;
   const float* hT;
@@ -198,6 +198,9 @@ typedef struct re2nn_onehot_args {
   float* beta;                 /* B x L x S */
 } re2nn_onehot_args;
 int re2nn_onehot_recurrence(const re2nn_onehot_args* a, void* stream);
+/* out[v] = language[v] + W  (model_onehot.py:366 `sum_tensor`): the reference redoes this V*S*S add on every
+ * forward; here it is done once per parameter version and the recurrence then streams a single tensor. */
+int re2nn_onehot_sum_tensor(const float* language, const float* W, int V1, int S, float* out, void* stream);
 
 /* ---- onehot i-FST backward (sum semiring) ----------------------------------------------------------------
  * replaces torch.autograd over FARNN_S_O_I_S.forward_score (train_onehot.py:179-181): the only trained

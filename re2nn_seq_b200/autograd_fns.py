@@ -102,13 +102,23 @@ class _OnehotScores(torch.autograd.Function):
     def forward(ctx, consts, pr, x, lengths, L, h0, hT, language, W, output_mat, out_wild):
         need_grad = consts['grad_on'] and any(ctx.needs_input_grad[5:])
         o = ops.output_vector_sum(output_mat, None if consts['ce1'] else out_wild)
-        alpha, beta = ops.onehot_recurrence(x, lengths, L, language, W, o, h0, hT, consts['update_nonlinear'],
-                                            consts['max_semiring'], consts['full_pad'])
+        # language + W once per parameter version (the reference redoes this V*S*S add every forward)
+        cache = consts.get('cache')
+        key = (language.data_ptr(), language._version, W.data_ptr(), W._version)
+        if cache is not None and cache.get('key') == key:
+            summed = cache['sum']
+        else:
+            summed = ops.onehot_sum_tensor(language, W)
+            if cache is not None:
+                cache.clear()
+                cache.update(key=key, sum=summed)
+        alpha, beta = ops.onehot_recurrence(x, lengths, L, summed, None, o, h0, hT, consts['update_nonlinear'],
+                                            consts['max_semiring'], consts['full_pad'], presummed=True)
         pm, pb = (pr if consts['use_priority'] else (None, None))
         scores = ops.label_scores(alpha, beta, lengths, output_mat, pm, pb, full_pad=consts['full_pad'])
         if need_grad:
             ctx.consts, ctx.pr, ctx.L = consts, pr, L
-            ctx.saved = (x, lengths, h0, hT, language, W, output_mat, o, alpha, beta)
+            ctx.saved = (x, lengths, h0, hT, summed, W, output_mat, o, alpha, beta)
         return scores
 
     @staticmethod

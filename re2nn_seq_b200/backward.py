@@ -37,4 +37,4 @@ def onehot_backward(ctx, dscores):
     x, lengths, h0, hT, language, W, output_mat, o, alpha, beta = ctx.saved
     pr_mat = ctx.pr[0].detach() if consts['use_priority'] else None
     return ops.onehot_backward(x, lengths, ctx.L, language, W, o, h0, hT, alpha, beta, dscores, output_mat, pr_mat,
-                               consts['update_nonlinear'], consts['full_pad'])
+                               consts['update_nonlinear'], consts['full_pad'], presummed=True)   # `language` = language + W

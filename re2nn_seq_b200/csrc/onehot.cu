@@ -13,6 +13,18 @@ namespace re2nn {
 constexpr int kOhThreads = 512;
 constexpr int kOhWarps = kOhThreads / 32;
 
+// T[s][j] (+ W[s][j] unless the caller passes a pre-summed tensor, W == nullptr)
+__device__ __forceinline__ float tw(const float* __restrict__ T, const float* __restrict__ W, size_t i) {
+  return W ? __ldg(T + i) + __ldg(W + i) : __ldg(T + i);
+}
+
+// sum[v][s][j] = language[v][s][j] + W[s][j]   (model_onehot.py:366, hoisted: once per parameter version)
+__global__ void onehot_sum_kernel(const float* __restrict__ lang, const float* __restrict__ W, size_t n_slice,
+                                  size_t total, float* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = lang[i] + W[i % n_slice];
+}
+
 template <bool MAXP>
 __device__ __forceinline__ float comb(float acc, float h, float t) {
   return MAXP ? fmaxf(acc, h * t) : fmaf(h, t, acc);
@@ -57,17 +69,17 @@ __global__ void __launch_bounds__(kOhThreads) onehot_recurrence_kernel(const re2
         if (j < S) {
           int s = warp;
           for (; s + 3 * kOhWarps < S; s += 4 * kOhWarps) {
-            float t0 = __ldg(T + (size_t)s * S + j) + __ldg(W + (size_t)s * S + j);
-            float t1 = __ldg(T + (size_t)(s + kOhWarps) * S + j) + __ldg(W + (size_t)(s + kOhWarps) * S + j);
-            float t2 = __ldg(T + (size_t)(s + 2 * kOhWarps) * S + j) + __ldg(W + (size_t)(s + 2 * kOhWarps) * S + j);
-            float t3 = __ldg(T + (size_t)(s + 3 * kOhWarps) * S + j) + __ldg(W + (size_t)(s + 3 * kOhWarps) * S + j);
+            float t0 = tw(T, W, (size_t)s * S + j);
+            float t1 = tw(T, W, (size_t)(s + kOhWarps) * S + j);
+            float t2 = tw(T, W, (size_t)(s + 2 * kOhWarps) * S + j);
+            float t3 = tw(T, W, (size_t)(s + 3 * kOhWarps) * S + j);
             acc = comb<MAXP>(acc, h[s], t0);
             acc = comb<MAXP>(acc, h[s + kOhWarps], t1);
             acc = comb<MAXP>(acc, h[s + 2 * kOhWarps], t2);
             acc = comb<MAXP>(acc, h[s + 3 * kOhWarps], t3);
           }
           for (; s < S; s += kOhWarps)
-            acc = comb<MAXP>(acc, h[s], __ldg(T + (size_t)s * S + j) + __ldg(W + (size_t)s * S + j));
+            acc = comb<MAXP>(acc, h[s], tw(T, W, (size_t)s * S + j));
           part[warp * S + j] = acc;
         }
       }
@@ -86,20 +98,20 @@ __global__ void __launch_bounds__(kOhThreads) onehot_recurrence_kernel(const re2
       float* hn = part;   // S
       for (int s = warp; s < S; s += kOhWarps) {
         const float* __restrict__ Tr = T + (size_t)s * S;
-        const float* __restrict__ Wr = W + (size_t)s * S;
+        const float* __restrict__ Wr = W ? W + (size_t)s * S : nullptr;
         float acc = init;
         int j = lane;
         for (; j + 96 < S; j += 128) {
-          float t0 = __ldg(Tr + j) + __ldg(Wr + j);
-          float t1 = __ldg(Tr + j + 32) + __ldg(Wr + j + 32);
-          float t2 = __ldg(Tr + j + 64) + __ldg(Wr + j + 64);
-          float t3 = __ldg(Tr + j + 96) + __ldg(Wr + j + 96);
+          float t0 = tw(Tr, Wr, j);
+          float t1 = tw(Tr, Wr, j + 32);
+          float t2 = tw(Tr, Wr, j + 64);
+          float t3 = tw(Tr, Wr, j + 96);
           acc = comb<MAXP>(acc, h[j], t0);
           acc = comb<MAXP>(acc, h[j + 32], t1);
           acc = comb<MAXP>(acc, h[j + 64], t2);
           acc = comb<MAXP>(acc, h[j + 96], t3);
         }
-        for (; j < S; j += 32) acc = comb<MAXP>(acc, h[j], __ldg(Tr + j) + __ldg(Wr + j));
+        for (; j < S; j += 32) acc = comb<MAXP>(acc, h[j], tw(Tr, Wr, j));
         acc = MAXP ? warp_max(acc) : warp_sum(acc);
         if (lane == 0) hn[s] = acc;
       }
@@ -163,7 +175,7 @@ __global__ void __launch_bounds__(kOhThreads) onehot_backward_kernel(const re2nn
         float acc = 0.f;
         for (int j = lane; j < S; j += 32) {
           const float dj = dacc[j];
-          acc = fmaf(__ldg(T + (size_t)s * S + j) + __ldg(W + (size_t)s * S + j), dj, acc);
+          acc = fmaf(tw(T, W, (size_t)s * S + j), dj, acc);
           const float v = hs * dj;
           if (v != 0.f) atomicAdd(dT + (size_t)s * S + j, v);
         }
@@ -182,7 +194,7 @@ __global__ void __launch_bounds__(kOhThreads) onehot_backward_kernel(const re2nn
           const float hj = hprev[j];
           for (int s = warp; s < S; s += kOhWarps) {
             const float ds = dacc[s];
-            acc = fmaf(__ldg(T + (size_t)s * S + j) + __ldg(W + (size_t)s * S + j), ds, acc);
+            acc = fmaf(tw(T, W, (size_t)s * S + j), ds, acc);
             const float v = ds * hj;
             if (v != 0.f) atomicAdd(dT + (size_t)s * S + j, v);
           }
@@ -205,9 +217,17 @@ __global__ void __launch_bounds__(kOhThreads) onehot_backward_kernel(const re2nn
 
 using namespace re2nn;
 
+extern "C" int re2nn_onehot_sum_tensor(const float* language, const float* W, int V1, int S, float* out, void* stream) {
+  RE2NN_CHECK(language && W && out && V1 > 0 && S > 0, "onehot_sum_tensor: bad arguments");
+  const size_t total = (size_t)V1 * S * S;
+  onehot_sum_kernel<<<148 * 16, 256, 0, (cudaStream_t)stream>>>(language, W, (size_t)S * S, total, out);
+  RE2NN_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int re2nn_onehot_backward(const re2nn_onehot_backward_args* a, void* stream) {
   RE2NN_CHECK(a != nullptr, "onehot_backward: null args");
-  RE2NN_CHECK(a->x && a->lengths && a->language && a->W && a->o && a->h0 && a->hT && a->alpha && a->beta &&
+  RE2NN_CHECK(a->x && a->lengths && a->language && a->o && a->h0 && a->hT && a->alpha && a->beta &&
                   a->dalpha && a->dbeta && a->dlanguage, "onehot_backward: null tensor");
   const size_t smem = (size_t)(3 + kOhWarps) * a->S * sizeof(float);
   RE2NN_CHECK(smem <= 220 * 1024, "onehot_backward: S=%d too large", a->S);
@@ -220,7 +240,7 @@ extern "C" int re2nn_onehot_backward(const re2nn_onehot_backward_args* a, void* 
 extern "C" int re2nn_onehot_recurrence(const re2nn_onehot_args* a, void* stream) {
   RE2NN_CHECK(a != nullptr, "onehot_recurrence: null args");
   RE2NN_CHECK(a->B > 0 && a->L > 0 && a->S > 0 && a->L <= a->Lpad, "onehot_recurrence: bad dims");
-  RE2NN_CHECK(a->x && a->lengths && a->language && a->W && a->o && a->h0 && a->hT && a->alpha && a->beta,
+  RE2NN_CHECK(a->x && a->lengths && a->language && a->o && a->h0 && a->hT && a->alpha && a->beta,
               "onehot_recurrence: null tensor");
   RE2NN_CHECK(a->update_nonlinear >= RE2NN_NL_NONE && a->update_nonlinear <= RE2NN_NL_RELUTANH,
               "onehot_recurrence: unsupported update_nonlinear %d", a->update_nonlinear);

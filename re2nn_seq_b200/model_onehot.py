@@ -62,8 +62,10 @@ class FARNN_S_O_I_S(nn.Module):
     def _consts(self, full_pad):
         a = self.args
         nl = a.update_nonlinear if a.update_nonlinear in _UPDATE_NL else 'none'
+        if not hasattr(self, '_sum_cache'):
+            self._sum_cache = {}
         return dict(update_nonlinear=nl, max_semiring=(a.train_mode == 'max'), ce1=(a.local_loss_func == 'CE1'),
-                    use_priority=bool(a.use_priority), full_pad=bool(full_pad))
+                    use_priority=bool(a.use_priority), full_pad=bool(full_pad), cache=self._sum_cache)
 
     def _scores(self, input, lengths, L, full_pad):
         dev = self._device()

@@ -130,16 +130,17 @@ def decompose_recurrence(x, lengths, L, vtab, gtab, S1, S2, W, o, h0, hT, Wss1, 
     return alpha, beta, saves
 
 
-def onehot_recurrence(x, lengths, L, language, W, o, h0, hT, update_nonlinear, max_semiring=False, full_pad=False):
+def onehot_recurrence(x, lengths, L, language, W, o, h0, hT, update_nonlinear, max_semiring=False, full_pad=False,
+                      presummed=False):
     B, Lpad = x.shape
-    S = W.shape[0]
+    S = language.shape[1]
     a = OnehotArgs()
     a.B, a.Lpad, a.L, a.S = B, Lpad, L, S
     a.update_nonlinear, a.max_semiring, a.full_pad = NL[update_nonlinear], int(max_semiring), int(full_pad)
-    alpha = torch.zeros((B, L, S), dtype=torch.float32, device=W.device)
-    beta = torch.zeros((B, L, S), dtype=torch.float32, device=W.device)
+    alpha = torch.zeros((B, L, S), dtype=torch.float32, device=language.device)
+    beta = torch.zeros((B, L, S), dtype=torch.float32, device=language.device)
     a.x, a.lengths = _i64(x), _i64(lengths)
-    a.language, a.W, a.o, a.h0, a.hT = _f32(language), _f32(W), _f32(o), _f32(h0), _f32(hT)
+    a.language, a.W, a.o, a.h0, a.hT = _f32(language), (_f32(W) if not presummed else None), _f32(o), _f32(h0), _f32(hT)
     a.alpha, a.beta = _f32(alpha), _f32(beta)
     check(fn['re2nn_onehot_recurrence'](C.byref(a), _stream()), 'onehot_recurrence')
     _count(1)
@@ -338,12 +339,12 @@ def token_table_backward(dvtab, V_embed, E, G, beta_vec, additional_nonlinear, w
 
 
 def onehot_backward(x, lengths, L, language, W, o, h0, hT, alpha, beta, dscores, C_mat, pr_mat, update_nonlinear,
-                    full_pad):
+                    full_pad, presummed=False):
     """d loss / d language_tensor for the sum-semiring onehot recurrence."""
     B, Lpad = x.shape
-    S = W.shape[0]
+    S = language.shape[1]
     Cn = C_mat.shape[0]
-    dev = W.device
+    dev = language.device
     dalpha = torch.empty_like(alpha)
     dbeta = torch.empty_like(beta)
     ws = torch.empty((B, L, Cn), dtype=torch.float32, device=dev) if pr_mat is not None else None
@@ -356,7 +357,7 @@ def onehot_backward(x, lengths, L, language, W, o, h0, hT, alpha, beta, dscores,
     a.B, a.Lpad, a.L, a.S = B, Lpad, L, S
     a.update_nonlinear, a.full_pad = NL[update_nonlinear], int(full_pad)
     a.x, a.lengths = _i64(x), _i64(lengths)
-    a.language, a.W, a.o, a.h0, a.hT = _f32(language), _f32(W), _f32(o), _f32(h0), _f32(hT)
+    a.language, a.W, a.o, a.h0, a.hT = _f32(language), (_f32(W) if not presummed else None), _f32(o), _f32(h0), _f32(hT)
     a.alpha, a.beta, a.dalpha, a.dbeta, a.dlanguage = _f32(alpha), _f32(beta), _f32(dalpha), _f32(dbeta), _f32(dlang)
     check(fn['re2nn_onehot_backward'](C.byref(a), _stream()), 'onehot_backward')
     _count(3 if pr_mat is not None else 2)
@@ -371,3 +372,11 @@ def flatten_i64(padded, lengths, offsets, L, n_flat):
           'flatten_i64')
     _count(1)
     return flat
+
+
+def onehot_sum_tensor(language, W):
+    out = torch.empty_like(language)
+    V1, S = language.shape[0], language.shape[1]
+    check(fn['re2nn_onehot_sum_tensor'](_f32(language), _f32(W), V1, S, _f32(out), _stream()), 'onehot_sum_tensor')
+    _count(1)
+    return out
