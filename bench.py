@@ -38,6 +38,7 @@ def parse():
     ap.add_argument('--farnn', type=int, default=0)
     ap.add_argument('--mode', default='infer', choices=['infer', 'train'],
                     help="infer = BASELINE configs[1] (headline); train = configs[2]: fwd+bwd+grad all-reduce, B=1024/GPU")
+    ap.add_argument('--train-precision', default='auto', help='forward GEMMs of --mode train: auto|fp32|tf32x3|fp16x3')
     ap.add_argument('--cpu-sample', type=int, default=256, help='sequences in the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
@@ -215,7 +216,8 @@ def main():
     if a.mode == 'train':
         from re2nn_seq_b200 import dist as rd
         m.train()
-        m.precision = prec = 'fp32'
+        m.train_precision = a.train_precision
+        prec = m._resolved_precision()          # grad mode is on here: resolves the training precision
         bucket = rd.GradBucket(m)
 
     n_tok = int(lens.sum())

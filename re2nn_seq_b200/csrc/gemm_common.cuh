@@ -126,6 +126,8 @@ struct StepParams {
   float* Usave[2];                                // training: u = hbar @ S1|S2          (B x R slab of this step)
   float* Asave[2];                                // training: pre-activation a          (B x S slab of this step)
   float* HstNext[2];                              // training: state before step k+1     (B x S slab)
+  float* HbarSaveNext[2];                         // training on tensor cores: fp32 copy of the next operand
+  float* HbarSaveCur[2];                          // training on tensor cores, farnn==2: fp32 copy of this step's operand
   int dir;                                        // set by bind(): the direction this CTA works on
   // Move direction z into slot 0 so the epilogue addresses plain members (registers after inlining)
   // instead of indexing the constant bank with a run-time z for every element.
@@ -134,6 +136,7 @@ struct StepParams {
     hinit[0] = hinit[z]; Q[0] = Q[z]; Hbar_next[0] = Hbar_next[z]; Hbar_cur[0] = Hbar_cur[z];
     Hst[0] = Hst[z]; H[0] = H[z]; Z[0] = Z[z]; Rg[0] = Rg[z]; out[0] = out[z];
     Usave[0] = Usave[z]; Asave[0] = Asave[z]; HstNext[0] = HstNext[z];
+    HbarSaveNext[0] = HbarSaveNext[z]; HbarSaveCur[0] = HbarSaveCur[z];
   }
 };
 
@@ -166,7 +169,8 @@ struct Pre { float a, b; };
 struct Col { float a, b; };
 
 // E1: Q = (Hbar @ S1|S2) * v_t            (model_decompose_single.py:170-171 / 175-176)
-template <int PREC> struct EpiQ {
+// TRAIN: also keep what BPTT needs (fp32 step-major slabs; rows that are finished hold exact zeros)
+template <int PREC, bool TRAIN = false> struct EpiQ {
   StepParams p;
   __device__ __forceinline__ EpiQ for_dir(int z) const { EpiQ e = *this; e.p.bind(z); return e; }
   __device__ __forceinline__ bool tile_alive(int z, int mt) const { return re2nn::tile_alive(p, z, mt); }
@@ -181,8 +185,9 @@ template <int PREC> struct EpiQ {
   }
   __device__ __forceinline__ void store(const Col&, const RowCtx& r, int m, int n, float q, float acc, const Pre&) const {
     OperandFmt<PREC>::store(p.Q[0], (uint32_t)m * (uint32_t)p.ldq + (uint32_t)n, p.q_plane, q);
-    if constexpr (PREC == RE2NN_PREC_FP32) {     // training saves exist on the fp32 path only
-      if (p.Usave[0]) p.Usave[0][(uint32_t)m * (uint32_t)p.R + (uint32_t)n] = r.alive ? acc : 0.f;
+    if constexpr (TRAIN) {
+      const bool live = p.full_pad || r.orow >= 0;
+      p.Usave[0][(uint32_t)m * (uint32_t)p.R + (uint32_t)n] = live ? acc : 0.f;
     }
   }
 };
@@ -190,7 +195,7 @@ template <int PREC> struct EpiQ {
 // E2: h_next = phi((Q @ S2^T + Hbar @ W) [* o]) ; gate blend ; write alpha/beta + next operands
 // (model_decompose_single.py:172-173,177-199).  NL / FARNN >= 0 fix update_nonlinear / farnn at compile
 // time (the hot configurations), -1 reads them from StepParams.
-template <int PREC, int NL = -1, int FARNN = -1> struct EpiH {
+template <int PREC, int NL = -1, int FARNN = -1, bool TRAIN = false> struct EpiH {
   static constexpr bool kFast = PREC == RE2NN_PREC_BF16;
   StepParams p;
   __device__ __forceinline__ EpiH for_dir(int z) const { EpiH e = *this; e.p.bind(z); return e; }
@@ -220,12 +225,14 @@ template <int PREC, int NL = -1, int FARNN = -1> struct EpiH {
   __device__ __forceinline__ void store(const Col& c, const RowCtx& r, int m, int n, float hnew, float acc, const Pre&) const {
     const uint32_t hi = (uint32_t)m * (uint32_t)p.ldh + (uint32_t)n;
     const uint32_t si = (uint32_t)m * (uint32_t)p.S + (uint32_t)n;
-    if constexpr (PREC == RE2NN_PREC_FP32) {     // training saves exist on the fp32 path only
-      if (p.Asave[0]) {   // keep what BPTT needs; rows that are finished hold exact zeros
-        const bool live = r.alive;          // note: a live row may have no output row (backward direction, beta_0)
-        p.Asave[0][si] = live ? acc : 0.f;
-        if (!live) hnew = 0.f;
-        p.HstNext[0][si] = hnew;
+    if constexpr (TRAIN) {
+      // note: with full_pad a live row may have no output row (backward direction, beta_0)
+      const bool live = p.full_pad || r.orow >= 0;
+      p.Asave[0][si] = live ? acc : 0.f;
+      if (!live) hnew = 0.f;
+      p.HstNext[0][si] = hnew;
+      if constexpr (PREC != RE2NN_PREC_FP32) {     // fp32: the operand buffer already is the fp32 slab
+        if (farnn() <= 1) p.HbarSaveNext[0][si] = p.dir == 1 ? hnew * c.a : hnew;
       }
     }
     if (farnn() >= 1) {
@@ -239,7 +246,7 @@ template <int PREC, int NL = -1, int FARNN = -1> struct EpiH {
 
 // EG: zt / rt gates and the reset-blended operand (model_decompose_single.py:147-157)
 // columns [0,S) = update gate pre-activation, [S,2S) = reset gate pre-activation (farnn==2)
-template <int PREC> struct EpiGate {
+template <int PREC, bool TRAIN = false> struct EpiGate {
   static constexpr bool kFast = PREC == RE2NN_PREC_BF16;
   StepParams p;
   __device__ __forceinline__ EpiGate for_dir(int z) const { EpiGate e = *this; e.p.bind(z); return e; }
@@ -268,8 +275,9 @@ template <int PREC> struct EpiGate {
       float hb = (1.f - g) * c.a + g * pre.b;
       if (p.dir == 1) hb *= c.b;
       OperandFmt<PREC>::store(p.Hbar_cur[0], (uint32_t)m * (uint32_t)p.ldh + (uint32_t)s, p.h_plane, hb);
-      if constexpr (PREC == RE2NN_PREC_FP32) {
-        if (p.Rg[0]) p.Rg[0][(uint32_t)m * (uint32_t)p.S + (uint32_t)s] = g;
+      if constexpr (TRAIN) {
+        p.Rg[0][(uint32_t)m * (uint32_t)p.S + (uint32_t)s] = g;
+        if constexpr (PREC != RE2NN_PREC_FP32) p.HbarSaveCur[0][(uint32_t)m * (uint32_t)p.S + (uint32_t)s] = hb;
       }
     }
   }

@@ -214,22 +214,36 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
       p.Hbar_next[z] = w.Hbar[par ^ 1][z];
       p.Z[z] = w.Z[z];
       p.Rg[z] = nullptr;
-      if (saving) {   // fp32 only: operands live in the step-major save slabs instead of the ping-pong buffers
+      if (saving) {
         const size_t sS = (size_t)B * S, sR = (size_t)B * R;
         float* hb_k = a.hbar_save + ((size_t)z * (L + 1) + k) * sS;
         float* hs_k = a.hst_save + ((size_t)z * (L + 1) + k) * sS;
-        p.Hbar_cur[z] = hb_k;
-        p.Hbar_next[z] = hb_k + sS;
         p.HstNext[z] = hs_k + sS;
-        p.Hst[z] = hs_k + sS;
         p.Usave[z] = a.u_save + ((size_t)z * L + k) * sR;
         p.Asave[z] = a.a_save + ((size_t)z * L + k) * sS;
         if (a.farnn >= 1) p.Z[z] = a.zsave + ((size_t)z * L + k) * sS;
-        if (a.farnn == 2) p.Rg[z] = a.rsave + ((size_t)z * L + k) * sS;
-        gg.seg[z][0].A = hs_k;
-        g1.seg[z][0].A = hb_k;
-        g2.seg[z][1].A = hb_k;
+        p.Rg[z] = a.farnn == 2 ? a.rsave + ((size_t)z * L + k) * sS : nullptr;
+        if (PREC == RE2NN_PREC_FP32) {
+          // fp32: the operands themselves live in the step-major save slabs instead of the ping-pong buffers
+          p.Hbar_cur[z] = hb_k;
+          p.Hbar_next[z] = hb_k + sS;
+          p.Hst[z] = hs_k + sS;
+          gg.seg[z][0].A = hs_k;
+          g1.seg[z][0].A = hb_k;
+          g2.seg[z][1].A = hb_k;
+        } else {
+          // tensor cores: operands stay in their (ping-pong) operand-format buffers, the epilogues add fp32 copies
+          p.HbarSaveNext[z] = hb_k + sS;
+          p.HbarSaveCur[z] = hb_k;
+        }
       }
+    }
+    if (saving) {   // training: generic functors with the save stores compiled in
+      if (a.farnn >= 1)
+        RE2NN_CUDA((launch_gemm<PREC>(0, gg, EpiGate<PREC, true>{p}, tm ? &tm->gate : nullptr, st)));
+      RE2NN_CUDA((launch_gemm<PREC>(1, g1, EpiQ<PREC, true>{p}, tm ? &tm->g1[par] : nullptr, st)));
+      RE2NN_CUDA((launch_gemm<PREC>(2, g2, EpiH<PREC, -1, -1, true>{p}, tm ? &tm->g2[par] : nullptr, st)));
+      continue;
     }
     if (a.farnn >= 1)
       RE2NN_CUDA((launch_gemm<PREC>(0, gg, EpiGate<PREC>{p}, tm ? &tm->gate : nullptr, st)));
@@ -392,7 +406,7 @@ int re2nn_decompose_recurrence(const re2nn_recurrence_args* a, void* stream) {
   RE2NN_CHECK(a->farnn == 0 || (a->gtab && a->Wss1), "decompose_recurrence: farnn>=1 needs gtab and Wss1");
   RE2NN_CHECK(a->farnn < 2 || a->Wss2, "decompose_recurrence: farnn==2 needs Wss2");
   if (a->save_for_backward) {
-    RE2NN_CHECK(a->precision == RE2NN_PREC_FP32, "decompose_recurrence: save_for_backward needs precision fp32");
+    RE2NN_CHECK(a->precision != RE2NN_PREC_BF16, "decompose_recurrence: training needs a parity-grade precision");
     RE2NN_CHECK(a->hbar_save && a->hst_save && a->u_save && a->a_save, "decompose_recurrence: missing save slabs");
     RE2NN_CHECK(a->farnn == 0 || a->zsave, "decompose_recurrence: farnn>=1 training needs zsave");
     RE2NN_CHECK(a->farnn < 2 || a->rsave, "decompose_recurrence: farnn==2 training needs rsave");

@@ -91,12 +91,12 @@ class _DecomposeBase(nn.Module):
     def _resolved_precision(self):
         """'auto' picks the fastest parity-grade mode the device has: split-fp16 tensor cores when the state is
         bounded by the update nonlinearity (fp16 planes need |operand| < 65504), 3xTF32 otherwise, fp32 CUDA
-        cores without tcgen05.  Training always runs the fp32 path."""
-        prec = self.precision
+        cores without tcgen05.  Training (grad enabled) uses `train_precision` (default fp32; 'auto', 'tf32x3' or
+        'fp16x3' run the forward GEMMs on tensor cores, the backward stays fp32)."""
+        training = torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters())
+        prec = getattr(self, 'train_precision', 'fp32') if training else self.precision
         if prec != 'auto':
             return prec
-        if torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters()):
-            return 'fp32'
         if not ops.has_tcgen05():
             return 'fp32'
         return 'fp16x3' if self.args.update_nonlinear in ('tanh', 'relutanh') else 'tf32x3'

@@ -203,3 +203,28 @@ def test_onehot_gradients_golden(name):
     assert list(gold) == ['language_tensor']
     err = rel_err(m.language_tensor.grad.cpu().numpy(), gold['language_tensor'])
     assert err < 2e-4, err
+
+
+@pytest.mark.parametrize('tp', ['tf32x3', 'fp16x3'])
+@pytest.mark.parametrize('farnn,crf', [(0, 1), (2, 1)])
+def test_training_with_tensor_core_forward(farnn, crf, tp):
+    """train_precision: forward GEMMs on tensor cores (parity-grade split formats), backward in fp32."""
+    from re2nn_seq_b200 import ops
+    from oracle import re2nn_oracle_torch as ot
+    if not ops.has_tcgen05():
+        pytest.skip('no tcgen05')
+    m, args, x, lens, lab = _random_decompose(9, 500, 300, 200, 72, 100, 40, 20, farnn=farnn, use_crf=crf,
+                                              update_nonlinear='tanh', beta=0.1, train_h0=1, train_hT=1)
+    m.train_precision = tp
+    loss, _, _ = m.forward_local(_t(x), _t(lab), _t(lens), train=True)
+    loss.backward()
+    rename = {'embedding.weight': 'embedding', 'crf.transitions': 'crf_transitions',
+              'priority_layer.priority_mat': 'priority_mat', 'priority_layer.priority_bias': 'priority_bias'}
+    p64 = {rename.get(k, k): v.detach().cpu().numpy().astype(np.float64) for k, v in m.state_dict().items()}
+    names = [rename.get(k, k) for k, v in m.named_parameters() if v.requires_grad]
+    o_loss, g64 = ot.grads(p64, x, lab, lens, args, names=names)
+    assert rel_err(loss.item(), o_loss) < TOL
+    for k, v in m.named_parameters():
+        if v.requires_grad:
+            err = rel_err(v.grad.cpu().numpy(), g64[rename.get(k, k)])
+            assert err < 1e-4, '%s: rel err %.3e' % (k, err)
