@@ -61,11 +61,15 @@ int re2nn_has_tcgen05(void);
 int re2nn_profile_enable(int on);
 /* debug: install (or clear with NULL) a device buffer receiving 32 clock64 stamps per CTA of every
  * tcgen05 step-GEMM launch (entry, alive-check, setup, MMAs issued, prefetch issued, accumulator ready,
- * epilogue done, exit, then arrival time of the first 24 k-blocks); slot = 32 * linear CTA id. */
+ * epilogue done, exit, then arrival time of the first 24 k-blocks); slot = 32 * (256 * launch index + linear CTA id)
+ * for the first 256 launches after the call, so the buffer must hold 32 * 65536 entries. */
 int re2nn_debug_set_tc_trace(unsigned long long* device_buf);
 /* debug: per-launch timeline: buf[2*i], buf[2*i+1] = %globaltimer (ns) at entry / exit of CTA (0,0,0) of the i-th
  * tcgen05 step-GEMM launch since the call (up to 4096 launches); NULL clears. */
 int re2nn_debug_set_tc_timeline(unsigned long long* device_buf);
+/* debug / calibration: CTA-group size of the tcgen05 step GEMMs built after the call: 0 = the cost model
+ * picks per GEMM shape (default), 1 = single-CTA tiles (128 x bn), 2 = CTA pairs (cta_group::2, 256 x bn). */
+int re2nn_debug_set_tc_cta_group(int cta_group);
 int re2nn_profile_read(double* ms_out_host, int64_t* count_out_host);
 
 /* ---- stand-alone GEMM through the step-GEMM mainloops (unit-test / calibration entry) -------------------

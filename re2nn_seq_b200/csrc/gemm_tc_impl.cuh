@@ -5,6 +5,10 @@
 //   warps 2..5  epilogue: each warp owns the 32 TMEM lanes (rows) its warp-id quarter may access
 // Both operands are K-major (A: M x K, B: N x K, K contiguous), bf16 (kind::f16) or tf32 (kind::tf32);
 // TF32X3 runs three (A_hi,B_hi) / (A_lo,B_hi) / (A_hi,B_lo) segment passes into the same accumulator.
+// CG = 2 runs the same kernel on CTA pairs (thread-block clusters of two, cta_group::2): one 256 x bn tile per
+// pair, each CTA stages its own 128 A rows and HALF of the B rows, the leader CTA issues the MMAs for both and
+// every CTA keeps the accumulator of its own 128 rows in its own TMEM.  The L2 -> SM operand stream is what
+// bounds these GEMMs (~43 B/clk/SM chip-wide), and pairing removes half of the B bytes per SM.
 #pragma once
 #include <cuda.h>
 
@@ -25,8 +29,12 @@ struct __align__(64) TcLaunch {
   TcSeg seg[2][kTcMaxSeg];
   int nseg, nmaps, M, N, BN, ndir;
   int bn;   // effective n-tile width (multiple of 16, <= BN): MMA N, TMA box rows of B, grid.y = ceil(N / bn)
+  int cg;   // 1: one CTA per 128 x bn tile; 2: CTA pair per 256 x bn tile (B box rows = bn / 2)
+  int launch_id;   // debug trace: index of this launch since tracing was switched on
 };
 typedef TcLaunch TcStepMaps;
+static int g_tc_trace_launches = -1;  // debug: >= 0 while a phase-trace buffer is installed (next launch index)
+static int g_tc_force_cg = 0;        // debug: 0 = cost model picks, 1 / 2 = force the CTA-group size
 static bool g_tc_use_pdl = true;     // programmatic dependent launch between consecutive tcgen05 step kernels
 struct TcRecurrenceMaps { TcLaunch gate, g1[2], g2[2]; };
 
@@ -69,27 +77,31 @@ inline int make_operand_map(CUtensorMap* m, const void* base, size_t elem_off, i
   return 0;
 }
 
-// n-tile width: the step GEMMs are bound by shared-memory ingest (~64 B/clk/SM), so pick the split of N that
-// minimises bytes per SM: waves(m_tiles * nt CTAs over 148 SMs) * (A tile 16 KB + B tile bn * 128 B) per k-block.
-inline void tc_pick_bn(int M, int N, int ndir, int planes, int* bn_out, int* BN_out) {
-  const long mt = (long)cdiv(M, 128) * ndir;
+// Tile shape: the step GEMMs are bound by the L2 -> shared-memory operand stream (measured 43-58 B/clk/SM), so
+// pick the CTA-group size and the split of N that minimise the bytes one SM has to ingest over its waves:
+//   per k-block and plane: A tile 16 KB + B tile (bn / cg) * 128 B;  MMA floor bn / 2 clk per 32-byte K step.
+inline void tc_pick_shape(int M, int N, int ndir, int planes, int mmas, int* bn_out, int* BN_out, int* cg_out) {
   double best = 1e30;
-  int best_bn = 64;
-  for (int nt = 1; nt <= cdiv(N, 16); ++nt) {
-    int bn = ((cdiv(N, nt) + 15) / 16) * 16;
-    if (bn > 256) continue;
-    if (nt > 1 && bn * (nt - 1) >= N) continue;            // a narrower split already covers N
-    const int cls = bn <= 64 ? 64 : (bn <= 128 ? 128 : 256);
-    const int per_sm = 1;                                   // persistent kernel: one CTA per SM
-    (void)cls;
-    const long ctas = mt * nt;
-    const double waves = (double)((ctas + 148L * per_sm - 1) / (148L * per_sm));
-    const double conc = (double)std::min<long>(per_sm, (ctas + 147) / 148);   // CTAs sharing one SM's ingest
-    const double cost = waves * conc * planes * (16384.0 + bn * 128.0) + 2000.0 * waves;
-    if (cost < best - 1e-9) { best = cost; best_bn = bn; }
+  int best_bn = 64, best_cg = 1;
+  for (int cg = 1; cg <= 2; ++cg) {
+    if (g_tc_force_cg && cg != g_tc_force_cg) continue;
+    const long mt = (long)cdiv(M, 128 * cg) * ndir;
+    const long slots = 148 / cg;
+    for (int nt = 1; nt <= cdiv(N, 16); ++nt) {
+      int bn = ((cdiv(N, nt) + 15) / 16) * 16;
+      if (bn > 256) continue;
+      if (nt > 1 && bn * (nt - 1) >= N) continue;            // a narrower split already covers N
+      const long tiles = mt * nt;
+      const double waves = (double)((tiles + slots - 1) / slots);
+      const double ingest = planes * (16384.0 + (bn / cg) * 128.0) / 45.0;   // clk per k-block
+      const double mma = mmas * 4.0 * (bn / 2.0);                            // clk per k-block
+      const double cost = waves * std::max(ingest, mma) + 150.0 * waves + (cg == 2 ? 10.0 : 0.0);
+      if (cost < best - 1e-9) { best = cost; best_bn = bn; best_cg = cg; }
+    }
   }
   *bn_out = best_bn;
   *BN_out = best_bn <= 64 ? 64 : (best_bn <= 128 ? 128 : 256);
+  *cg_out = best_cg;
 }
 
 // Expand a GemmProblem (operands already in the PREC operand format, all B operands K-major) into maps.
@@ -97,7 +109,9 @@ template <int PREC>
 inline int tc_make_launch(const GemmProblem& g, TcLaunch* out) {
   memset(out, 0, sizeof(*out));
   out->M = g.M; out->N = g.N; out->ndir = g.ndir;
-  tc_pick_bn(g.M, g.N, g.ndir, OperandFmt<PREC>::kPlanes, &out->bn, &out->BN);
+  tc_pick_shape(g.M, g.N, g.ndir, OperandFmt<PREC>::kPlanes, OperandFmt<PREC>::kPlanes == 2 ? 3 : 1, &out->bn, &out->BN,
+                &out->cg);
+  const int b_box = out->bn / out->cg;
   constexpr int kpb = 128 / OperandFmt<PREC>::kElemBytes;   // K elements per 128-byte block
   int nm = 0;
   for (int z = 0; z < g.ndir; ++z) {
@@ -110,13 +124,13 @@ inline int tc_make_launch(const GemmProblem& g, TcLaunch* out) {
       const int a_hi = nm++;
       if (int rc = make_operand_map<PREC>(&out->maps[a_hi], sg.A, 0, g.M, sg.K, sg.lda, 128)) return rc;
       const int b_hi = nm++;
-      if (int rc = make_operand_map<PREC>(&out->maps[b_hi], sg.B, 0, g.N, sg.K, sg.ldb, out->bn)) return rc;
+      if (int rc = make_operand_map<PREC>(&out->maps[b_hi], sg.B, 0, g.N, sg.K, sg.ldb, b_box)) return rc;
       int a_lo = -1, b_lo = -1;
       if (OperandFmt<PREC>::kPlanes == 2) {
         a_lo = nm++;
         if (int rc = make_operand_map<PREC>(&out->maps[a_lo], sg.A, sg.a_plane, g.M, sg.K, sg.lda, 128)) return rc;
         b_lo = nm++;
-        if (int rc = make_operand_map<PREC>(&out->maps[b_lo], sg.B, sg.b_plane, g.N, sg.K, sg.ldb, out->bn)) return rc;
+        if (int rc = make_operand_map<PREC>(&out->maps[b_lo], sg.B, sg.b_plane, g.N, sg.K, sg.ldb, b_box)) return rc;
       }
       out->seg[z][ns++] = TcSeg{a_hi, b_hi, a_lo, b_lo, kb};
     }
@@ -151,6 +165,29 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
                : "memory");
 }
+// CTA-pair variants: the transaction bytes of both CTAs' loads are credited to the LEADER's full barrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {   // same offset in CTA `rank` of the cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -163,6 +200,29 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// commit on behalf of the pair: arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask)
+               : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void tc_mma_pair(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  if (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+  }
 }
 template <bool TF32>
 __device__ __forceinline__ void tc_mma(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
@@ -214,11 +274,11 @@ constexpr int kTcSmemLimit = 227 * 1024;
 // (hi*hi, lo*hi, hi*lo).  When TMEM has room for two accumulator sets the kernel double-buffers them: the
 // epilogue of tile i overlaps the mainloop of tile i+1 (kOverlap); otherwise tiles run back to back and the
 // transpose buffers alias the (then idle) pipeline stages.
-template <int PREC, int BN> struct TcCfg {
+template <int PREC, int BN, int CG = 1> struct TcCfg {
   static constexpr int kPlanes = OperandFmt<PREC>::kPlanes;
   static constexpr int kAccs = PREC == RE2NN_PREC_FP16X3 ? 2 : 1;   // fp16 split keeps the residual products apart
   static constexpr int kATile = 128 * 128;
-  static constexpr int kBTile = BN * 128;
+  static constexpr int kBTile = (BN / CG) * 128;               // a CTA of a pair stages half of the B rows
   static constexpr int kABytes = kATile * kPlanes;
   static constexpr int kBBytes = kBTile * kPlanes;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -250,19 +310,30 @@ __device__ __forceinline__ void tc_stamp(unsigned long long* t, int slot) {
 
 // Persistent kernel: CTA c works on tiles c, c + gridDim.x, ...; tile id -> (direction z, m-tile, n-tile) with the
 // n-tile fastest so concurrently running CTAs share A tiles in L2.
-template <int PREC, int BN, class Epi>
+template <int PREC, int BN, int CG, class Epi>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_constant__ TcLaunch L, const Epi epi_in) {
-  using Cfg = TcCfg<PREC, BN>;
+  using Cfg = TcCfg<PREC, BN, CG>;
+  constexpr bool PAIR = CG == 2;
   constexpr bool TF32 = PREC == RE2NN_PREC_TF32X3;
   constexpr bool SPLIT = Cfg::kPlanes == 2;
   constexpr bool TWOACC = Cfg::kAccs == 2;
   constexpr bool OVERLAP = Cfg::kOverlap;
   constexpr int kpb = 128 / OperandFmt<PREC>::kElemBytes;
   const int bn = L.bn;
-  const int m_tiles = (L.M + 127) / 128, n_tiles = (L.N + bn - 1) / bn;
+  constexpr int kTileM = 128 * CG;                       // rows of one (pair) tile
+  const int m_tiles = (L.M + kTileM - 1) / kTileM, n_tiles = (L.N + bn - 1) / bn;
   const int tiles_per_dir = m_tiles * n_tiles, total_tiles = tiles_per_dir * L.ndir;
+  const int crank = PAIR ? (int)cluster_ctarank() : 0;   // 0 = leader (issues the MMAs), 1 = peer
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // a 128-row block past the end of M (second half of the last pair tile) is simply dead
+  auto alive = [&](int z, int mt) -> bool {
+    if (!PAIR) return epi_in.tile_alive(z, mt);
+    const int last = (L.M + 127) / 128 - 1;
+    return epi_in.tile_alive(z, 2 * mt) || (2 * mt + 1 <= last && epi_in.tile_alive(z, 2 * mt + 1));
+  };
   unsigned long long* trace = nullptr;
-  if (g_tc_trace) trace = g_tc_trace + 32ull * blockIdx.x;
+  if (g_tc_trace && L.launch_id < 256) trace = g_tc_trace + 32ull * (256u * (unsigned)L.launch_id + blockIdx.x);
   if (threadIdx.x == 0) tc_stamp(trace, 0);
   unsigned int tl_idx = 0xffffffffu;
   if (g_tc_timeline && threadIdx.x == 0 && blockIdx.x == 0) {
@@ -303,17 +374,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), kTcEpiWarps);
+      mbar_init(tempty_bar(s), kTcEpiWarps * CG);    // the leader's MMA warp waits for both CTAs' epilogues
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                 "r"((uint32_t)Cfg::kTmemCols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    if (PAIR) {    // both CTAs of the pair execute the paired allocation (same warp id, same slot offset)
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                   "r"((uint32_t)Cfg::kTmemCols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                   "r"((uint32_t)Cfg::kTmemCols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();     // the peer's barriers must exist before anything arrives on them remotely
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_p;
   if (threadIdx.x == 0) tc_stamp(trace, 2);
@@ -324,11 +402,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
   if (warp == 0) {
     int it = 0;
     griddep_wait();                 // A operands are written by the previous kernel
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const uint32_t bbox = (uint32_t)(bn / CG);                       // B rows this CTA stages
+    const uint32_t cta_bytes = (uint32_t)(Cfg::kPlanes * (Cfg::kATile + bbox * 128));
+    for (int tile = worker; tile < total_tiles; tile += nworkers) {
       const int z = tile / tiles_per_dir, rem = tile - z * tiles_per_dir;
       const int mt = rem / n_tiles, nt = rem - mt * n_tiles;
-      if (!epi_in.tile_alive(z, mt)) continue;
-      const int m0 = mt * 128, n0 = nt * bn;
+      if (!alive(z, mt)) continue;
+      const int m0 = mt * kTileM + crank * 128, n0 = nt * bn + crank * (int)bbox;
       if (lane == 0) {
         for (int s = 0; s < nseg; ++s) {
           const TcSeg sg = L.seg[z][s];
@@ -339,12 +419,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
             const uint32_t ph = (it / Cfg::kStages) & 1;
             mbar_wait(empty_bar(st), ph ^ 1);
             const uint32_t sa = base + st * Cfg::kStageBytes;
-            mbar_expect_tx(full_bar(st), (uint32_t)(Cfg::kPlanes * (Cfg::kATile + bn * 128)));
-            tma_load_2d(sa, ma, full_bar(st), kb * kpb, m0);
-            tma_load_2d(sa + Cfg::kABytes, mb, full_bar(st), kb * kpb, n0);
-            if (SPLIT) {
-              tma_load_2d(sa + Cfg::kATile, &L.maps[sg.a_lo], full_bar(st), kb * kpb, m0);
-              tma_load_2d(sa + Cfg::kABytes + Cfg::kBTile, &L.maps[sg.b_lo], full_bar(st), kb * kpb, n0);
+            if (PAIR) {
+              const uint32_t fb = mapa_shared(full_bar(st), 0);         // the leader's barrier collects both CTAs' bytes
+              if (crank == 0) mbar_expect_tx(full_bar(st), 2u * cta_bytes);
+              tma_load_2d_pair(sa, ma, fb, kb * kpb, m0);
+              tma_load_2d_pair(sa + Cfg::kABytes, mb, fb, kb * kpb, n0);
+              if (SPLIT) {
+                tma_load_2d_pair(sa + Cfg::kATile, &L.maps[sg.a_lo], fb, kb * kpb, m0);
+                tma_load_2d_pair(sa + Cfg::kABytes + Cfg::kBTile, &L.maps[sg.b_lo], fb, kb * kpb, n0);
+              }
+            } else {
+              mbar_expect_tx(full_bar(st), cta_bytes);
+              tma_load_2d(sa, ma, full_bar(st), kb * kpb, m0);
+              tma_load_2d(sa + Cfg::kABytes, mb, full_bar(st), kb * kpb, n0);
+              if (SPLIT) {
+                tma_load_2d(sa + Cfg::kATile, &L.maps[sg.a_lo], full_bar(st), kb * kpb, m0);
+                tma_load_2d(sa + Cfg::kABytes + Cfg::kBTile, &L.maps[sg.b_lo], full_bar(st), kb * kpb, n0);
+              }
             }
           }
         }
@@ -357,14 +448,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
   } else if (warp == 1) {
     // instruction descriptor: D=f32, A/B = f16 (0) / bf16 (1) / tf32 (2), both K-major, N>>3, M>>4
     const uint32_t fmt = TF32 ? 2u : (PREC == RE2NN_PREC_FP16X3 ? 0u : 1u);
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc =
+        (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | (((uint32_t)kTileM >> 4) << 24);
     int it = 0, tcount = 0;
     griddep_wait();
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    if (lane == 0) tc_stamp(trace, 1);   // previous grid complete
+    for (int tile = worker; tile < total_tiles; tile += nworkers) {
       const int z = tile / tiles_per_dir, rem = tile - z * tiles_per_dir;
       const int mt = rem / n_tiles;
-      if (!epi_in.tile_alive(z, mt)) continue;
-      if (lane == 0) {
+      if (!alive(z, mt)) continue;
+      if (lane == 0 && crank == 0) {
         int total_kb = 0;
         for (int s = 0; s < nseg; ++s) total_kb += L.seg[z][s].kblocks;
         const int as = OVERLAP ? (tcount & 1) : 0;
@@ -380,21 +473,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
           tc_fence_after();
           const uint32_t sa = base + st * Cfg::kStageBytes;
           const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + Cfg::kABytes);
+          auto mma = [&](uint32_t acc, uint64_t a, uint64_t b, uint32_t accum) {
+            if (PAIR) tc_mma_pair<TF32>(acc, a, b, idesc, accum);
+            else tc_mma<TF32>(acc, a, b, idesc, accum);
+          };
 #pragma unroll
           for (int k = 0; k < 4; ++k)   // 4 x 32-byte K steps per 128-byte block (16 x 16-bit / 8 x tf32 each)
-            tc_mma<TF32>(tmem_acc, da + 2u * k, db + 2u * k, idesc, (j | k) != 0 ? 1u : 0u);
+            mma(tmem_acc, da + 2u * k, db + 2u * k, (j | k) != 0 ? 1u : 0u);
           if (SPLIT) {   // residual terms: lo*hi and hi*lo (lo*lo is below fp32 resolution)
             const uint64_t dal = make_smem_desc(sa + Cfg::kATile), dbl = make_smem_desc(sa + Cfg::kABytes + Cfg::kBTile);
             const uint32_t acc_lo = TWOACC ? tmem_acc + (uint32_t)BN : tmem_acc;   // fp16 split: scaled residual accumulator
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              tc_mma<TF32>(acc_lo, dal + 2u * k, db + 2u * k, idesc, TWOACC ? ((j | k) != 0 ? 1u : 0u) : 1u);
-              tc_mma<TF32>(acc_lo, da + 2u * k, dbl + 2u * k, idesc, 1u);
+              mma(acc_lo, dal + 2u * k, db + 2u * k, TWOACC ? ((j | k) != 0 ? 1u : 0u) : 1u);
+              mma(acc_lo, da + 2u * k, dbl + 2u * k, 1u);
             }
           }
-          tc_commit(empty_bar(st));     // frees the smem slot once these MMAs have read it
+          if (PAIR) tc_commit_pair(empty_bar(st));   // frees this slot in both CTAs once the MMAs have read it
+          else tc_commit(empty_bar(st));
         }
-        tc_commit(tfull_bar(as));       // accumulator complete
+        if (PAIR) tc_commit_pair(tfull_bar(as));     // accumulator complete (each CTA's epilogue waits on its own)
+        else tc_commit(tfull_bar(as));
         if (tcount == 0) tc_stamp(trace, 3);
       }
       ++tcount;
@@ -414,11 +513,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
     int* ctx = ctx_base + ew * 64;          // [vrow x32 | orow x32]
     int tcount = 0;
     griddep_wait();                         // state / gate buffers are written by the previous kernel
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = worker; tile < total_tiles; tile += nworkers) {
       const int z = tile / tiles_per_dir, rem = tile - z * tiles_per_dir;
       const int mt = rem / n_tiles, nt = rem - mt * n_tiles;
-      if (!epi_in.tile_alive(z, mt)) continue;
-      const int m0 = mt * 128, n0 = nt * bn;
+      if (!alive(z, mt)) continue;
+      const int m0 = mt * kTileM + crank * 128, n0 = nt * bn;
       const Epi epi = epi_in.for_dir(z);    // direction-bound copy: plain members, no per-element z indexing
       const int mrow0 = m0 + q * 32;
       const int as = OVERLAP ? (tcount & 1) : 0;
@@ -453,6 +552,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
           acc_ready = true;
           if (tcount == 0 && ew == 0 && lane == 0) tc_stamp(trace, 5);   // accumulator ready
         }
+        const bool dbg_t = tcount == 0 && ew == 0 && lane == 0 && c0 < 96 * 2;
+        const int dbg_s = 20 + 4 * (c0 / 64);
+        if (dbg_t) tc_stamp(trace, dbg_s);
         uint32_t r[32];
         tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
         if (TWOACC) {
@@ -466,6 +568,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
           for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
         }
         __syncwarp();
+        if (dbg_t) tc_stamp(trace, dbg_s + 1);
         // phase 2: lane = column, rows in batches of 16: all accumulator reads first, then 16 independent
         // epilogue evaluations (their MUFU / convert chains interleave), then the stores; unguarded when the
         // 32x32 block is interior
@@ -484,6 +587,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
               const int o = ctx[32 + h0 + i];
               epi.store(cc, RowCtx{ctx[h0 + i], o, o >= 0}, mrow0 + h0 + i, n, hv[i], av[i], pre[h0 + i]);
             }
+            if (dbg_t) tc_stamp(trace, dbg_s + 2 + (h0 >> 4));
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -504,7 +608,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(as)) : "memory");
+        if (PAIR) mbar_arrive_cluster(mapa_shared(tempty_bar(as), 0));
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(as)) : "memory");
       }
       if (tcount == 0 && ew == 0 && lane == 0) tc_stamp(trace, 6);       // epilogue of the first tile done
       ++tcount;
@@ -514,38 +619,58 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();     // neither CTA may retire while the pair still touches its smem / TMEM
+  else __syncthreads();
   if (threadIdx.x == 0) tc_stamp(trace, 7);
   if (tl_idx < 4096) g_tc_timeline[2 * tl_idx + 1] = globaltimer_ns();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols));
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols));
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols));
   }
 }
 
-template <int PREC, int BN, class Epi>
+template <int PREC, int BN, int CG, class Epi>
 inline cudaError_t launch_tc_bn(const TcLaunch& L, const Epi& epi, cudaStream_t st) {
-  using Cfg = TcCfg<PREC, BN>;
+  using Cfg = TcCfg<PREC, BN, CG>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<PREC, BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<PREC, BN, CG, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const long tiles = (long)cdiv(L.M, 128) * cdiv(L.N, L.bn) * L.ndir;
-  const int grid = (int)std::min<long>(tiles, 148);          // one persistent CTA per SM
+  const long tiles = (long)cdiv(L.M, 128 * CG) * cdiv(L.N, L.bn) * L.ndir;
+  const int grid = (int)std::min<long>(tiles, 148 / CG) * CG;   // one persistent CTA (pair) per SM (pair)
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = Cfg::kSmem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CG == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (g_tc_use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = g_tc_use_pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, tc_gemm_kernel<PREC, BN, Epi>, L, epi);
+  cfg.numAttrs = na;
+  if (g_tc_trace_launches >= 0) {
+    TcLaunch Lt = L;
+    Lt.launch_id = g_tc_trace_launches++;
+    return cudaLaunchKernelEx(&cfg, tc_gemm_kernel<PREC, BN, CG, Epi>, Lt, epi);
+  }
+  return cudaLaunchKernelEx(&cfg, tc_gemm_kernel<PREC, BN, CG, Epi>, L, epi);
 }
 
 template <int PREC, class Epi>
@@ -554,10 +679,17 @@ inline cudaError_t launch_tc_gemm(const GemmProblem&, const Epi& epi, const TcSt
     return cudaErrorNotSupported;
   } else {
     if (L == nullptr) return cudaErrorInvalidValue;
+    if (L->cg == 2) {
+      switch (L->BN) {
+        case 64: return launch_tc_bn<PREC, 64, 2>(*L, epi, st);
+        case 128: return launch_tc_bn<PREC, 128, 2>(*L, epi, st);
+        default: return launch_tc_bn<PREC, 256, 2>(*L, epi, st);
+      }
+    }
     switch (L->BN) {
-      case 64: return launch_tc_bn<PREC, 64>(*L, epi, st);
-      case 128: return launch_tc_bn<PREC, 128>(*L, epi, st);
-      default: return launch_tc_bn<PREC, 256>(*L, epi, st);
+      case 64: return launch_tc_bn<PREC, 64, 1>(*L, epi, st);
+      case 128: return launch_tc_bn<PREC, 128, 1>(*L, epi, st);
+      default: return launch_tc_bn<PREC, 256, 1>(*L, epi, st);
     }
   }
 }

@@ -351,6 +351,7 @@ int re2nn_abi_version(void) { return RE2NN_ABI_VERSION; }
 
 int re2nn_debug_set_tc_trace(unsigned long long* device_buf) {
   RE2NN_CUDA(cudaMemcpyToSymbol(g_tc_trace, &device_buf, sizeof(device_buf)));
+  g_tc_trace_launches = device_buf ? 0 : -1;
   return 0;
 }
 
@@ -358,6 +359,14 @@ int re2nn_debug_set_tc_timeline(unsigned long long* device_buf) {
   unsigned int zero = 0;
   RE2NN_CUDA(cudaMemcpyToSymbol(g_tc_timeline_ctr, &zero, sizeof(zero)));
   RE2NN_CUDA(cudaMemcpyToSymbol(g_tc_timeline, &device_buf, sizeof(device_buf)));
+  return 0;
+}
+
+int re2nn_debug_set_tc_cta_group(int cta_group) {
+  RE2NN_CHECK(cta_group >= 0 && cta_group <= 2, "debug_set_tc_cta_group: expected 0, 1 or 2");
+#ifdef RE2NN_HAVE_TC
+  g_tc_force_cg = cta_group;
+#endif
   return 0;
 }
 

@@ -9,7 +9,7 @@ from oracle import re2nn_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
-SHAPES = [(128, 64, 64), (128, 64, 128), (200, 300, 300), (333, 77, 130), (4096, 200, 300), (1000, 520, 1030),
+SHAPES = [(128, 64, 64), (128, 64, 128), (200, 300, 300), (256, 32, 64), (700, 48, 96), (333, 77, 130), (4096, 200, 300), (1000, 520, 1030),
           (8192, 304, 500), (40000, 512, 264)]
 
 
@@ -19,12 +19,23 @@ def _need_tc():
         pytest.skip('no tcgen05 device')
 
 
+@pytest.fixture(params=[1, 2], ids=['cta1', 'ctapair'])
+def cta_group(request):
+    """Force single-CTA tiles (128 x bn) or CTA pairs (cta_group::2, 256 x bn) for the tcgen05 GEMMs of the test."""
+    from re2nn_seq_b200 import _lib
+    _lib.check(_lib.fn['re2nn_debug_set_tc_cta_group'](request.param), 'cta_group')
+    yield request.param
+    _lib.check(_lib.fn['re2nn_debug_set_tc_cta_group'](0), 'cta_group')
+
+
 @pytest.mark.parametrize('prec,tol', [('fp32', 2e-6), ('tf32x3', 2e-5), ('fp16x3', 2e-5), ('bf16', 1.5e-2)])
 @pytest.mark.parametrize('M,N,K', SHAPES)
-def test_gemm_nt(prec, tol, M, N, K):
+def test_gemm_nt(prec, tol, M, N, K, cta_group):
     from re2nn_seq_b200 import ops
     if prec != 'fp32':
         _need_tc()
+    elif cta_group == 2:
+        pytest.skip('fp32 runs the SIMT mainloop')
     g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
     A = torch.randn((M, K), generator=g).cuda()
     B = torch.randn((N, K), generator=g).cuda()
@@ -34,7 +45,7 @@ def test_gemm_nt(prec, tol, M, N, K):
     assert err < tol, 'rel err %.3e' % err
 
 
-def test_gemm_nt_exact_integers():
+def test_gemm_nt_exact_integers(cta_group):
     """Small-integer operands are exact in bf16 and tf32: any layout / descriptor error shows up as a wrong integer."""
     from re2nn_seq_b200 import ops
     _need_tc()
@@ -64,7 +75,7 @@ def _truth(m, args, x, lens):
 
 @pytest.mark.parametrize('mode', ['tf32x3', 'fp16x3'])
 @pytest.mark.parametrize('farnn', [0, 2])
-def test_recurrence_tf32x3_matches_fp32_tolerance(farnn, mode):
+def test_recurrence_tf32x3_matches_fp32_tolerance(farnn, mode, cta_group):
     _need_tc()
     m, args, x, lens, lab = _model(farnn, 1)
     truth, z = _truth(m, args, x, lens)

@@ -18,6 +18,7 @@ m = r.FARNN_S_D_W_I_S(args=args, o_idx=0, **f)
 with torch.no_grad():
     m.crf.transitions.copy_(torch.from_numpy(synth.crf_transitions(0, m.C)))
 m = m.cuda().train()
+m.train_precision = sys.argv[3] if len(sys.argv) > 3 else 'auto'
 xt, lt, yt = (torch.from_numpy(a).cuda() for a in (x, lens, lab))
 def step():
     for q in m.parameters():
