@@ -70,6 +70,9 @@ int re2nn_debug_set_tc_timeline(unsigned long long* device_buf);
 /* debug / calibration: CTA-group size of the tcgen05 step GEMMs built after the call: 0 = the cost model
  * picks per GEMM shape (default), 1 = single-CTA tiles (128 x bn), 2 = CTA pairs (cta_group::2, 256 x bn). */
 int re2nn_debug_set_tc_cta_group(int cta_group);
+/* debug / calibration: 1 (default) = inference without gates runs the whole recurrence in one resident launch
+ * (a CTA pair per 128-row tile iterates over all steps); 0 = one launch per step GEMM. */
+int re2nn_debug_set_resident(int on);
 int re2nn_profile_read(double* ms_out_host, int64_t* count_out_host);
 
 /* ---- stand-alone GEMM through the step-GEMM mainloops (unit-test / calibration entry) -------------------

@@ -240,7 +240,9 @@ template <int PREC, int NL = -1, int FARNN = -1, bool TRAIN = false> struct EpiH
       OperandFmt<PREC>::store(p.Hst[0], hi, p.h_plane, hnew);
     }
     if (farnn() <= 1) OperandFmt<PREC>::store(p.Hbar_next[0], hi, p.h_plane, p.dir == 1 ? hnew * c.a : hnew);
-    if (r.orow >= 0) p.out[0][(size_t)((uint32_t)m * (uint32_t)p.L + (uint32_t)r.orow) * (uint32_t)p.S + (uint32_t)n] = hnew;
+    // address unconditionally, store conditionally: keeps the 16-row batches of the tcgen05 epilogue branch-free
+    float* dst = p.out[0] + (size_t)((uint32_t)m * (uint32_t)p.L + (uint32_t)(r.orow & 0x7fffffff)) * (uint32_t)p.S + (uint32_t)n;
+    if (r.orow >= 0) *dst = hnew;
   }
 };
 

@@ -9,6 +9,7 @@
 
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "recurrence_resident.cuh"
 
 namespace re2nn {
 
@@ -105,6 +106,7 @@ __global__ void rec_init_kernel(int B, int L, int S, int farnn, const int64_t* l
 
 // ---- optional per-launch timing ------------------------------------------------------------------------
 struct ProfPair { cudaEvent_t a, b; };
+static bool g_resident_on = true;    // inference, farnn = 0: run the whole recurrence in one resident launch
 static bool g_prof_on = false;
 static std::vector<ProfPair> g_prof_pool;        // all event pairs ever created
 static std::vector<int> g_prof_used[3];          // indices into the pool, per kernel class
@@ -148,6 +150,7 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
   const int ldh = operand_ld(PREC, S), ldq = operand_ld(PREC, R);
   RE2NN_CHECK((size_t)B * (size_t)std::max(ldh, ldq) < ((size_t)1 << 31) && (size_t)B * L < ((size_t)1 << 31),
               "decompose_recurrence: batch too large for 32-bit row indexing (B=%d)", B);
+  RE2NN_CHECK(PREC == RE2NN_PREC_FP32 || L < 32768, "decompose_recurrence: tensor-core paths keep output rows in 16 bits (L=%d)", L);
   const size_t h_plane = (size_t)B * ldh, q_plane = (size_t)B * ldq;
 
   if (int rc = weight_prep_run<PREC>(a, w.wp, st)) return rc;
@@ -180,6 +183,50 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
       g_2[par].seg[z][1] = w.wp.seg_g2w(z, w.Hbar[par][z], ldh, h_plane);
     }
   }
+  StepParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.Lpad = a.Lpad; p.L = L; p.S = S; p.R = R;
+  p.farnn = a.farnn; p.nl = a.update_nonlinear; p.v_mode = a.v_mode; p.full_pad = a.full_pad;
+  p.sig_k = a.sigmoid_exponent;
+  p.x = a.x; p.len = a.lengths; p.tile_last[0] = w.tile_last[0]; p.tile_last[1] = w.tile_last[1]; p.vtab = a.vtab; p.gtab = a.gtab; p.ldg = S * a.farnn;
+  p.o = a.o; p.hinit[0] = a.h0; p.hinit[1] = a.hT;
+  p.ldq = ldq; p.q_plane = q_plane; p.ldh = ldh; p.h_plane = h_plane;
+  p.out[0] = a.alpha; p.out[1] = a.beta;
+  for (int z = 0; z < 2; ++z) { p.Q[z] = w.Q[z]; p.Hst[z] = w.Hst[z]; p.H[z] = w.H[z]; }
+
+  if constexpr (PREC != RE2NN_PREC_FP32) {
+    // Inference without gates: one resident launch (a CTA pair per 128-row tile runs all steps; recurrence_resident.cuh)
+    if (g_resident_on && !a.save_for_backward && a.farnn == 0 && resident_supported(OperandFmt<PREC>::kPlanes, S, R)) {
+      std::unique_ptr<ResidentLaunch> rl(new ResidentLaunch);
+      memset(rl.get(), 0, sizeof(ResidentLaunch));
+      const int bn1 = resident_part(R), bn2 = resident_part(S);
+      // The TMEM accumulator truncates, so the summation order is part of the result: the parity-grade split formats
+      // keep the order of the per-step path (Q @ S^T first, measured 2-4x closer to fp32 than W first on cfg4);
+      // bf16 starts G2 with Hbar @ W, whose operands do not wait for this step's Q
+      rl->q_first = PREC == RE2NN_PREC_BF16 ? 0 : 1;
+      for (int par = 0; par < 2; ++par) {
+        GemmProblem r2 = g_2[par];
+        if (!rl->q_first)
+          for (int z = 0; z < 2; ++z) {
+            r2.seg[z][0] = g_2[par].seg[z][1];
+            r2.seg[z][1] = g_2[par].seg[z][0];
+          }
+        if (int rc = tc_make_launch<PREC>(g_1[par], &rl->g1[par], bn1)) return rc;
+        if (int rc = tc_make_launch<PREC>(r2, &rl->g2[par], bn2)) return rc;
+      }
+      rl->steps = L;
+      rl->stage_bytes = resident_stage_bytes(OperandFmt<PREC>::kPlanes, S, R);
+      rl->stages = resident_stages(OperandFmt<PREC>::kPlanes, S, R);
+      for (int z = 0; z < 2; ++z) { p.Hbar_cur[z] = w.Hbar[0][z]; p.Hbar_next[z] = w.Hbar[1][z]; }
+      const int pi = prof_begin(2, st);
+      cudaError_t e = a.update_nonlinear == RE2NN_NL_TANH ? launch_resident<PREC, RE2NN_NL_TANH>(*rl, p, B, st)
+                                                           : launch_resident<PREC, -1>(*rl, p, B, st);
+      prof_end(pi, st);
+      RE2NN_CUDA(e);
+      return 0;
+    }
+  }
+
   TcRecurrenceMaps* tm = nullptr;
   std::unique_ptr<TcRecurrenceMaps> tm_hold;
   if constexpr (PREC != RE2NN_PREC_FP32) {
@@ -193,16 +240,6 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
     }
   }
 
-  StepParams p;
-  memset(&p, 0, sizeof(p));
-  p.B = B; p.Lpad = a.Lpad; p.L = L; p.S = S; p.R = R;
-  p.farnn = a.farnn; p.nl = a.update_nonlinear; p.v_mode = a.v_mode; p.full_pad = a.full_pad;
-  p.sig_k = a.sigmoid_exponent;
-  p.x = a.x; p.len = a.lengths; p.tile_last[0] = w.tile_last[0]; p.tile_last[1] = w.tile_last[1]; p.vtab = a.vtab; p.gtab = a.gtab; p.ldg = S * a.farnn;
-  p.o = a.o; p.hinit[0] = a.h0; p.hinit[1] = a.hT;
-  p.ldq = ldq; p.q_plane = q_plane; p.ldh = ldh; p.h_plane = h_plane;
-  p.out[0] = a.alpha; p.out[1] = a.beta;
-  for (int z = 0; z < 2; ++z) { p.Q[z] = w.Q[z]; p.Hst[z] = w.Hst[z]; p.H[z] = w.H[z]; }
 
   const bool saving = a.save_for_backward != 0;
   for (int k = 0; k < L; ++k) {
@@ -367,6 +404,11 @@ int re2nn_debug_set_tc_cta_group(int cta_group) {
 #ifdef RE2NN_HAVE_TC
   g_tc_force_cg = cta_group;
 #endif
+  return 0;
+}
+
+int re2nn_debug_set_resident(int on) {
+  g_resident_on = on != 0;
   return 0;
 }
 
