@@ -348,15 +348,28 @@ def main():
         peak_tf = peaks.get('bf16_tflops_sustained') or 1400.0
         peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside the step)' if peaks else \
             'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'
-        # dominant kernel: GEMM2 (+ state epilogue), both directions per launch: 2 dirs * 2*B*S*(R+S) flops
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json'))).get(prec)
         except Exception:
             pass
-        g2_flops = 2 * 2.0 * c['B'] * S * (R + S)
-        g2_ms = prof_ms[2] / max(prof_n[2], 1)
-        achieved = g2_flops / (g2_ms * 1e-3) / 1e12 if g2_ms > 0 else 0.0
+        if prof_n[3] > 0:
+            # dominant kernel: the resident recurrence kernel (ALL steps of both directions in one launch).
+            # Algorithmic flops per launch: every valid position, both directions, G1 (2*S*R) + G2 (2*(R+S)*S)
+            dom_name = 'resident recurrence: all steps, G1 + G2 + fused epilogues (%s)' % prec
+            dom_cls = 3
+            dom_flops = 2.0 * n_tok * (2.0 * S * R + 2.0 * (R + S) * S)
+            try:
+                traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json'))).get(prec + '_resident')
+            except Exception:
+                traffic = None
+        else:
+            # dominant kernel: GEMM2 (+ state epilogue), both directions per launch: 2 dirs * 2*B*S*(R+S) flops
+            dom_name = 'step GEMM2 + state epilogue (%s)' % prec
+            dom_cls = 2
+            dom_flops = 2 * 2.0 * c['B'] * S * (R + S)
+        g2_ms = prof_ms[dom_cls] / max(prof_n[dom_cls], 1)
+        achieved = dom_flops / (g2_ms * 1e-3) / 1e12 if g2_ms > 0 else 0.0
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -371,13 +384,13 @@ def main():
                        'l2': 'flushed between timed iterations (256 MB write)',
                        'cuda_graph': a.mode == 'infer',
                        'whole_step_tflops': value * flops_per_position(S, R, D, Cp, a.farnn) / 1e12},
-            'roofline': {'bound': 'tensor', 'kernel': 'step GEMM2 + state epilogue (%s)' % prec, 'achieved': achieved,
+            'roofline': {'bound': 'tensor', 'kernel': dom_name, 'achieved': achieved,
                          'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': traffic,
-                         'peak_source': peak_src, 'launches_timed': prof_n[2], 'avg_launch_ms': g2_ms,
-                         'kernel_share_of_step': (prof_ms[2] / a.steps) / prof_step_ms if prof_step_ms > 0 else None,
+                         'peak_source': peak_src, 'launches_timed': prof_n[dom_cls], 'avg_launch_ms': g2_ms,
+                         'kernel_share_of_step': (prof_ms[dom_cls] / a.steps) / prof_step_ms if prof_step_ms > 0 else None,
                          'profiled_ms_per_step': prof_step_ms,
                          'class_ms_per_step': {'gate': prof_ms[0] / a.steps, 'gemm1': prof_ms[1] / a.steps,
-                                               'gemm2': prof_ms[2] / a.steps}},
+                                               'gemm2': prof_ms[2] / a.steps, 'resident': prof_ms[3] / a.steps}},
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(xh.numel() * 8 + lh.numel() * 8 + yh.numel() * 8),
                     'd2h_bytes_per_step': int(n_tok * 8)},
             'gpu_launches': int(launches_total), 'gpu_launches_per_step': int(launches), 'clocks': clocks,

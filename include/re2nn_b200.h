@@ -56,7 +56,8 @@ int re2nn_has_tcgen05(void);
 /* ---- in-library kernel timing (used by bench.py for the roofline line) --------------------------------
  * When enabled, every step-GEMM launch of re2nn_decompose_recurrence is bracketed by CUDA events on
  * its own stream.  re2nn_profile_read synchronises those events, returns the summed milliseconds and
- * launch counts per kernel class (0 = gate GEMM, 1 = GEMM1 + Q epilogue, 2 = GEMM2 + state epilogue)
+ * launch counts per kernel class (0 = gate GEMM, 1 = GEMM1 + Q epilogue, 2 = GEMM2 + state epilogue,
+ * 3 = resident recurrence kernel: all steps in one launch; both output arrays hold 4 entries)
  * and resets the counters. */
 int re2nn_profile_enable(int on);
 /* debug: install (or clear with NULL) a device buffer receiving 32 clock64 stamps per CTA of every
@@ -145,6 +146,9 @@ typedef struct re2nn_recurrence_args {
 
 size_t re2nn_decompose_recurrence_workspace(const re2nn_recurrence_args* a);
 int re2nn_decompose_recurrence(const re2nn_recurrence_args* a, void* stream);
+/* Number of kernels re2nn_decompose_recurrence launches for this argument block (inference without gates on the
+ * tensor-core paths runs ALL steps in one resident kernel; otherwise 2-3 step GEMMs per step). */
+int re2nn_decompose_recurrence_launches(const re2nn_recurrence_args* a);
 
 /* Same recurrence under the max-product semiring (train_mode == 'max': model_decompose_single.py:159-166,
  * utils.py:192-195).  Takes the same argument block (precision ignored: fp32; save_for_backward must be 0);

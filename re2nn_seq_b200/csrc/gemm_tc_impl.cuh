@@ -331,7 +331,7 @@ __device__ __forceinline__ void tc_stamp(unsigned long long* t, int slot) {
 // 32-column chunk starting at chunk `half`.  tcgen05.ld hands lane i the 32 columns of row i; a 32x33
 // shared-memory transpose turns that into "lane = column" so that every global access of the epilogue functor
 // is a full contiguous row segment (128 B fp32 / 64 B 16-bit per warp request).  ctx = int vrow[32] | short orow[32].
-template <bool TWOACC, class Epi>
+template <bool TWOACC, int PARTS = kTcEpiWarps / 4, class Epi>
 __device__ __forceinline__ void tc_epilogue_chunks(const Epi epi, int M, int N, int mrow0, int n0, int bn,
                                                    uint32_t tmem_rows, uint32_t corr_off, int half, int lane,
                                                    float* tbuf, const int* ctx, uint32_t tfull, uint32_t parity,
@@ -341,7 +341,7 @@ __device__ __forceinline__ void tc_epilogue_chunks(const Epi epi, int M, int N, 
   bool acc_ready = false;
   const bool stamp = trace != nullptr && lane == 0;
 #pragma unroll 1
-  for (int c0 = half * 32; c0 < bn; c0 += 32 * (kTcEpiWarps / 4)) {
+  for (int c0 = half * 32; c0 < bn; c0 += 32 * PARTS) {
     if (n0 + c0 >= N) break;     // warp-uniform
     const int n = n0 + c0 + lane;
     const bool col_ok = n < N && c0 + lane < bn;
@@ -378,9 +378,9 @@ __device__ __forceinline__ void tc_epilogue_chunks(const Epi epi, int M, int N, 
     __syncwarp();
     if (dbg_t) tc_stamp(trace, dbg_s + 1);
     // phase 2: lane = column, rows in batches of 16: all accumulator reads first, then 16 independent
-    // epilogue evaluations (their MUFU / convert chains interleave), then the stores; unguarded when the
-    // 32x32 block is interior
-    const bool interior = nrows == 32 && n0 + c0 + 32 <= N && c0 + 32 <= bn;   // warp-uniform
+    // epilogue evaluations (their MUFU / convert chains interleave), then the stores; row-unguarded when
+    // all 32 rows of the block exist
+    const bool interior = nrows == 32;   // warp-uniform; lanes past the last column only skip their stores
 #pragma unroll
     for (int h0 = 0; h0 < 32; h0 += 16) {
       float av[16];
@@ -390,18 +390,23 @@ __device__ __forceinline__ void tc_epilogue_chunks(const Epi epi, int M, int N, 
         float hv[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) hv[i] = epi.compute(cc, av[i], pre[h0 + i]);
+        if (col_ok) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int o = ctx_o[h0 + i];
-          epi.store(cc, RowCtx{ctx[h0 + i], o, o >= 0}, mrow0 + h0 + i, n, hv[i], av[i], pre[h0 + i]);
+          for (int i = 0; i < 16; ++i) {
+            const int o = ctx_o[h0 + i];
+            epi.store(cc, RowCtx{ctx[h0 + i], o, o >= 0}, mrow0 + h0 + i, n, hv[i], av[i], pre[h0 + i]);
+          }
         }
         if (dbg_t) tc_stamp(trace, dbg_s + 2 + (h0 >> 4));
       } else {
-#pragma unroll
+        // edge blocks are rare: a compact loop (no register arrays indexed at run time) keeps the kernel small --
+        // the fully unrolled version doubled the code and the kernels became instruction-fetch bound
+#pragma unroll 1
         for (int i = 0; i < 16; ++i) {
           if (col_ok && h0 + i < nrows) {
             const int o = ctx_o[h0 + i];
-            epi.apply(cc, RowCtx{ctx[h0 + i], o, o >= 0}, mrow0 + h0 + i, n, av[i], pre[h0 + i]);
+            const RowCtx rc{ctx[h0 + i], o, o >= 0};
+            epi.apply(cc, rc, mrow0 + h0 + i, n, tbuf[(h0 + i) * 33 + lane], epi.prefetch(rc, mrow0 + h0 + i, n));
           }
         }
       }

@@ -109,7 +109,7 @@ struct ProfPair { cudaEvent_t a, b; };
 static bool g_resident_on = true;    // inference, farnn = 0: run the whole recurrence in one resident launch
 static bool g_prof_on = false;
 static std::vector<ProfPair> g_prof_pool;        // all event pairs ever created
-static std::vector<int> g_prof_used[3];          // indices into the pool, per kernel class
+static std::vector<int> g_prof_used[4];          // indices into the pool, per kernel class (3 = resident recurrence)          // indices into the pool, per kernel class
 static size_t g_prof_next = 0;
 static std::mutex g_prof_mu;
 
@@ -218,7 +218,7 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
       rl->stage_bytes = resident_stage_bytes(OperandFmt<PREC>::kPlanes, S, R);
       rl->stages = resident_stages(OperandFmt<PREC>::kPlanes, S, R);
       for (int z = 0; z < 2; ++z) { p.Hbar_cur[z] = w.Hbar[0][z]; p.Hbar_next[z] = w.Hbar[1][z]; }
-      const int pi = prof_begin(2, st);
+      const int pi = prof_begin(3, st);
       cudaError_t e = a.update_nonlinear == RE2NN_NL_TANH ? launch_resident<PREC, RE2NN_NL_TANH>(*rl, p, B, st)
                                                            : launch_resident<PREC, -1>(*rl, p, B, st);
       prof_end(pi, st);
@@ -421,7 +421,7 @@ int re2nn_profile_enable(int on) {
 int re2nn_profile_read(double* ms_out_host, int64_t* count_out_host) {
   RE2NN_CHECK(ms_out_host && count_out_host, "profile_read: null output");
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  for (int c = 0; c < 3; ++c) {
+  for (int c = 0; c < 4; ++c) {
     double tot = 0.0;
     for (int idx : g_prof_used[c]) {
       float ms = 0.f;
@@ -441,6 +441,22 @@ const char* re2nn_last_error(void) { return re2nn::g_err; }
 size_t re2nn_decompose_recurrence_workspace(const re2nn_recurrence_args* a) {
   if (!a) return 0;
   return carve(*a, nullptr, nullptr);
+}
+
+// does this call take the resident single-launch path?  (mirrors the test in run_recurrence)
+static bool takes_resident_path(const re2nn_recurrence_args& a) {
+  if (a.precision == RE2NN_PREC_FP32 || !g_resident_on || a.save_for_backward || a.farnn != 0) return false;
+  const int planes = a.precision == RE2NN_PREC_BF16 ? 1 : 2;
+  return resident_supported(planes, a.S, a.R);
+}
+
+int re2nn_decompose_recurrence_launches(const re2nn_recurrence_args* a) {
+  if (!a) return -1;
+  int n = 2;                                                     // tile_last + rec_init
+  if (a->precision == RE2NN_PREC_FP32) n += a->farnn == 2 ? 1 : 0;   // [Wss1 | Wss2] concat
+  else n += 6 + a->farnn;                                        // operand-format copies of the weights
+  n += takes_resident_path(*a) ? 1 : a->L * (2 + (a->farnn >= 1 ? 1 : 0));
+  return n;
 }
 
 int re2nn_decompose_recurrence(const re2nn_recurrence_args* a, void* stream) {

@@ -11,7 +11,7 @@
 //     G2:  H'[:, part j of S] = phi((Hbar @ W + Q @ S2^T|S1^T) [* o])      (EpiH: alpha/beta rows + next Hbar operand)
 //   through the same TMA -> swizzled smem -> tcgen05.mma -> TMEM -> fused-epilogue pipeline as tc_gemm_kernel.
 //   Q and Hbar travel between the two CTAs through L2 (operand-format buffers, read back by TMA); an mbarrier
-//   per CTA ("ready", 16 arrivals = the epilogue warps of both CTAs, remote arrives over DSMEM) tells the TMA
+//   per CTA ("ready", one arrival per epilogue warp of both CTAs, remote arrives over DSMEM) tells the TMA
 //   producer when the rows it is about to load have been published.  Weight (B) tiles never wait for that
 //   barrier, and G2 starts with its Hbar @ W segment, whose operands are already there while the G1 epilogue
 //   is still running.
@@ -30,10 +30,14 @@ struct __align__(64) ResidentLaunch {
   int q_first;               // G2 segment order: 0 = [Hbar @ W, Q @ S^T] (W overlaps the G1 epilogue), 1 = [Q, W]
 };
 
+constexpr int kResEpiWarps = 8;         // epilogue warps (12 measured: bf16 3 % faster, fp16x3 7 % slower)
+constexpr int kResThreads = 64 + 32 * kResEpiWarps;
+constexpr int kResTbufBytes = kResEpiWarps * 32 * 33 * 4;
+constexpr int kResCtxBytes = kResEpiWarps * kTcCtxWords * 4;
 constexpr uint32_t kResCorrOff = 256;   // TMEM column of the second (residual) accumulator of the fp16 split
 
 template <int PREC, int NL>
-__global__ void __launch_bounds__(kTcThreads, 1) tc_resident_kernel(const __grid_constant__ ResidentLaunch RL,
+__global__ void __launch_bounds__(kResThreads, 1) tc_resident_kernel(const __grid_constant__ ResidentLaunch RL,
                                                                     const StepParams p_in) {
   constexpr bool TF32 = PREC == RE2NN_PREC_TF32X3;
   constexpr int kPlanes = OperandFmt<PREC>::kPlanes;
@@ -68,7 +72,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_resident_kernel(const __grid
   const uint32_t tfull_bar = bars + 64, tempty_bar = bars + 72, ready_bar = bars + 80, tmem_slot = bars + 88;
   volatile uint32_t* tmem_slot_p = (volatile uint32_t*)(gen_base + stage_region + 88);
   int* ctx_base = reinterpret_cast<int*>(gen_base + stage_region + 256);
-  float* tbuf_base = reinterpret_cast<float*>(gen_base + stage_region + 256 + kTcCtxBytes);
+  float* tbuf_base = reinterpret_cast<float*>(gen_base + stage_region + 256 + kResCtxBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -89,8 +93,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_resident_kernel(const __grid
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tfull_bar, 1);
-    mbar_init(tempty_bar, kTcEpiWarps);
-    mbar_init(ready_bar, 2 * kTcEpiWarps);       // the epilogue warps of both CTAs
+    mbar_init(tempty_bar, kResEpiWarps);
+    mbar_init(ready_bar, 2 * kResEpiWarps);       // the epilogue warps of both CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -228,8 +232,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_resident_kernel(const __grid
       __syncwarp();
       if (lane == 0) {
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar) : "memory");
-        mbar_arrive_cluster(ready_mine);
-        mbar_arrive_cluster(ready_peer);
+        asm volatile("fence.acq_rel.cluster;" ::: "memory");      // one release for both arrives
+        asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(ready_mine) : "memory");
+        asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(ready_peer) : "memory");
       }
       ++acc;
     };
@@ -254,12 +259,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_resident_kernel(const __grid
         }
         __syncwarp();
         const bool tr = tile == worker && k == 2 && ew == 0 && lane == 0;
-        tc_epilogue_chunks<TWOACC>(e1, M, R, mrow0, crank * bn1, bn1, tmem_rows, kResCorrOff, half, lane, tbuf, ctx,
+        tc_epilogue_chunks<TWOACC, kResEpiWarps / 4>(e1, M, R, mrow0, crank * bn1, bn1, tmem_rows, kResCorrOff, half, lane, tbuf, ctx,
                                    tfull_bar, acc & 1u, nullptr);
         if (tr) tc_stamp(trace, 18);
         release_and_publish();
         const EpiH<PREC, NL, 0> e2{ps};
-        tc_epilogue_chunks<TWOACC>(e2, M, S, mrow0, crank * bn2, bn2, tmem_rows, kResCorrOff, half, lane, tbuf, ctx,
+        tc_epilogue_chunks<TWOACC, kResEpiWarps / 4>(e2, M, S, mrow0, crank * bn2, bn2, tmem_rows, kResCorrOff, half, lane, tbuf, ctx,
                                    tfull_bar, acc & 1u, nullptr);
         if (tr) tc_stamp(trace, 19);
         release_and_publish();
@@ -276,7 +281,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_resident_kernel(const __grid
 }
 
 inline int resident_smem_bytes(int stages, int stage_bytes) {
-  return stages * stage_bytes + 256 + kTcCtxBytes + kTcTbufBytes;
+  return stages * stage_bytes + 256 + kResCtxBytes + kResTbufBytes;
 }
 
 inline int resident_part(int n) { return ((cdiv(n, 2) + 15) / 16) * 16; }      // columns of one CTA of the pair
@@ -284,7 +289,7 @@ inline int resident_stage_bytes(int planes, int S, int R) {
   return planes * (128 * 128 + std::max(resident_part(S), resident_part(R)) * 128);
 }
 inline int resident_stages(int planes, int S, int R) {
-  return std::min(4, (kTcSmemLimit - 256 - kTcCtxBytes - kTcTbufBytes) / resident_stage_bytes(planes, S, R));
+  return std::min(4, (kTcSmemLimit - 256 - kResCtxBytes - kResTbufBytes) / resident_stage_bytes(planes, S, R));
 }
 // Can the resident kernel run this problem?  Each CTA of a pair takes half of R and half of S as ONE MMA tile
 // and needs a two-stage operand pipeline.
@@ -305,7 +310,7 @@ inline cudaError_t launch_resident(const ResidentLaunch& RL, const StepParams& p
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(std::min<long>(tiles, 74) * 2));   // one CTA pair per SM pair
-  cfg.blockDim = dim3(kTcThreads);
+  cfg.blockDim = dim3(kResThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

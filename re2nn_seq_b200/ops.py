@@ -126,7 +126,7 @@ def decompose_recurrence(x, lengths, L, vtab, gtab, S1, S2, W, o, h0, hT, Wss1, 
     ws = torch.empty((need,), dtype=torch.uint8, device=dev)
     a.ws, a.ws_bytes = C.c_void_p(ws.data_ptr()), need
     check(fn['re2nn_decompose_recurrence'](C.byref(a), _stream()), 'decompose_recurrence')
-    _count(1 + (1 if farnn == 2 or precision != 'fp32' else 0) + L * (2 + (1 if farnn else 0)))
+    _count(fn['re2nn_decompose_recurrence_launches'](C.byref(a)))
     return alpha, beta, saves
 
 
@@ -240,9 +240,9 @@ def profile_enable(on):
 
 
 def profile_read():
-    """-> ([ms_gate, ms_gemm1, ms_gemm2], [n_gate, n_gemm1, n_gemm2]) summed since the last read."""
-    ms = (C.c_double * 3)()
-    cnt = (C.c_int64 * 3)()
+    """-> ([ms_gate, ms_gemm1, ms_gemm2, ms_resident], [n_gate, n_gemm1, n_gemm2, n_resident]) since the last read."""
+    ms = (C.c_double * 4)()
+    cnt = (C.c_int64 * 4)()
     check(fn['re2nn_profile_read'](ms, cnt), 'profile_read')
     return list(ms), list(cnt)
 
