@@ -30,7 +30,7 @@ struct __align__(64) ResidentLaunch {
   int q_first;               // G2 segment order: 0 = [Hbar @ W, Q @ S^T] (W overlaps the G1 epilogue), 1 = [Q, W]
 };
 
-constexpr int kResEpiWarps = 8;         // epilogue warps (12 measured: bf16 3 % faster, fp16x3 7 % slower)
+constexpr int kResEpiWarps = 12;        // three epilogue warps per TMEM lane quarter
 constexpr int kResThreads = 64 + 32 * kResEpiWarps;
 constexpr int kResTbufBytes = kResEpiWarps * 32 * 33 * 4;
 constexpr int kResCtxBytes = kResEpiWarps * kTcCtxWords * 4;

@@ -1,0 +1,118 @@
+"""GPU: the resident recurrence kernel (one launch for all steps, a CTA pair per 128-row tile) against the
+one-launch-per-step path and the float64 oracle: more tiles than SM pairs (a pair walks several tiles), ragged
+lengths (tiles stop at their own last step), batches that are not a multiple of 128, pad semantics (full_pad),
+pre-computed rank factors (FARNN_S_SF), every tensor-core precision."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import oracle_params, rel_err
+from oracle import re2nn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _need_tc():
+    from re2nn_seq_b200 import ops
+    if not ops.has_tcgen05():
+        pytest.skip('no tcgen05 device')
+
+
+def _set_resident(on):
+    from re2nn_seq_b200 import _lib
+    _lib.check(_lib.fn['re2nn_debug_set_resident'](1 if on else 0), 'resident')
+
+
+def _launches(m, xt, lt):
+    from re2nn_seq_b200 import ops
+    l0 = ops.launches()
+    with torch.no_grad():
+        s = m.forward_scores(xt, lt)
+    return s, ops.launches() - l0
+
+
+class _Z(dict):
+    files = property(lambda self: list(self.keys()))
+
+
+def _truth(m, args, x, lens):
+    z = _Z({'p.' + k: v.detach().cpu().numpy() for k, v in m.state_dict().items()})
+    sc, _, _ = orc.decompose_scores(oracle_params(z, np.float64), x, lens, args)
+    return sc
+
+
+@pytest.mark.parametrize('prec,tol', [('fp16x3', 1e-5), ('tf32x3', 1e-5), ('bf16', 3e-2)])
+@pytest.mark.parametrize('B,S,R,L,nl', [(5000, 96, 48, 9, 'tanh'), (333, 300, 200, 12, 'tanh'), (130, 64, 40, 7, 'relu')])
+def test_resident_matches_per_step_and_oracle(B, S, R, L, nl, prec, tol):
+    from test_gpu_parity import _random_decompose
+    _need_tc()
+    m, args, x, lens, lab = _random_decompose(11, 500, S, R, 20, 50, B, L, farnn=0, use_crf=0, update_nonlinear=nl,
+                                              beta=0.1)
+    m.precision = prec
+    m.use_cuda_graph = False
+    xt, lt = _t(x), _t(lens)
+    try:
+        _set_resident(True)
+        s_res, n_res = _launches(m, xt, lt)
+        _set_resident(False)
+        s_step, n_step = _launches(m, xt, lt)
+    finally:
+        _set_resident(True)
+    Lmax = int(lens.max())
+    assert n_res < n_step and (n_step - n_res) % 2 == 1   # one resident launch replaces two step GEMMs per step
+    mask = orc.length_mask(lens, Lmax)
+    a, b = s_res.cpu().numpy()[mask], s_step.cpu().numpy()[mask]
+    if prec != 'bf16':
+        assert np.array_equal(a, b)                  # same summation order as the per-step path: same bits
+    truth = _truth(m, args, x, lens)[mask]
+    assert rel_err(a, truth) < tol
+    assert rel_err(b, truth) < tol
+
+
+def test_resident_full_pad_positions():
+    """KD / PR read the scores at pad positions: with full_pad every tile runs all L steps (reference semantics)."""
+    from test_gpu_parity import _random_decompose
+    _need_tc()
+    m, args, x, lens, lab = _random_decompose(3, 400, 80, 48, 12, 50, 300, 10, farnn=0, use_crf=0, update_nonlinear='tanh',
+                                              beta=0.1)
+    m.use_cuda_graph = False
+    m.full_pad = True
+    xt, lt = _t(x), _t(lens)
+    out = {}
+    try:
+        for prec in ('fp32', 'fp16x3'):
+            m.precision = prec
+            with torch.no_grad():
+                out[prec] = m.forward_scores(xt, lt).cpu().numpy()
+    finally:
+        m.full_pad = False
+    assert rel_err(out['fp16x3'], out['fp32']) < 1e-5            # every position, pads included
+
+
+def test_resident_precomputed_factors():
+    """FARNN_S_SF (v_t supplied as B x L x R floats) through the resident kernel."""
+    import re2nn_seq_b200 as r
+    from re2nn_seq_b200 import synth
+    _need_tc()
+    S, R, C, B, L = 120, 72, 15, 700, 8
+    args = synth.make_args(farnn=0, use_crf=0, update_nonlinear='tanh', beta=0.1)
+    f = synth.make_decompose_factors(2, 300, S, R, C, 50, dtype=np.float32)
+    keep = ('S1', 'S2', 'C_output_mat', 'wildcard_mat', 'wildcard_output_vector', 'final_vector', 'start_vector')
+    m = r.FARNN_S_SF(args=args, o_idx=0, is_cuda=True, priority_mat=None, **{k: f[k] for k in keep}).cuda()
+    m.use_cuda_graph = False
+    rs = np.random.RandomState(5)
+    v = (rs.randn(B, L, R) * 0.3).astype(np.float32)
+    lens = rs.randint(3, L + 1, size=B).astype(np.int64)
+    lens[0] = L
+    vt, lt = _t(v), _t(lens)
+    out = {}
+    for prec in ('fp32', 'fp16x3'):
+        m.precision = prec
+        with torch.no_grad():
+            out[prec] = m.forward_scores(vt, lt).cpu().numpy()
+    mask = orc.length_mask(lens, L)
+    assert rel_err(out['fp16x3'][mask], out['fp32'][mask]) < 1e-5
