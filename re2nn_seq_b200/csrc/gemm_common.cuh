@@ -29,6 +29,10 @@ template <int PREC> struct OperandFmt;
 template <> struct OperandFmt<RE2NN_PREC_FP32> {
   static constexpr int kElemBytes = 4, kPlanes = 1, kLdAlign = 1;
   __device__ static __forceinline__ void store(void* base, size_t idx, size_t, float v) { ((float*)base)[idx] = v; }
+  // conversion unconditional, stores predicated: keeps unrolled epilogue batches branch-free
+  __device__ static __forceinline__ void store_if(bool on, void* base, size_t idx, size_t, float v) {
+    if (on) ((float*)base)[idx] = v;
+  }
   // four consecutive elements, idx % 4 == 0 and the row pitch 16-byte aligned
   __device__ static __forceinline__ void store4(void* base, size_t idx, size_t, float4 v) {
     *reinterpret_cast<float4*>((float*)base + idx) = v;
@@ -38,6 +42,10 @@ template <> struct OperandFmt<RE2NN_PREC_BF16> {
   static constexpr int kElemBytes = 2, kPlanes = 1, kLdAlign = 8;
   __device__ static __forceinline__ void store(void* base, size_t idx, size_t, float v) {
     ((__nv_bfloat16*)base)[idx] = __float2bfloat16_rn(v);
+  }
+  __device__ static __forceinline__ void store_if(bool on, void* base, size_t idx, size_t, float v) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    if (on) ((__nv_bfloat16*)base)[idx] = h;
   }
   __device__ static __forceinline__ void store4(void* base, size_t idx, size_t, float4 v) {
     __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
@@ -59,6 +67,12 @@ template <> struct OperandFmt<RE2NN_PREC_TF32X3> {
     ((float*)base)[idx] = hi;
     ((float*)base)[idx + plane] = tf32_hi(v - hi);
   }
+  __device__ static __forceinline__ void store_if(bool on, void* base, size_t idx, size_t plane, float v) {
+    const float hi = tf32_hi(v), lo = tf32_hi(v - hi);
+    float* d = (float*)base + idx;
+    if (on) d[0] = hi;
+    if (on) d[plane] = lo;
+  }
   __device__ static __forceinline__ void store4(void* base, size_t idx, size_t plane, float4 v) {
     float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
     float4 l = make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));
@@ -76,6 +90,13 @@ template <> struct OperandFmt<RE2NN_PREC_FP16X3> {
     const __half hi = __float2half_rn(v);
     ((__half*)base)[idx] = hi;
     ((__half*)base)[idx + plane] = __float2half_rn((v - __half2float(hi)) * kFp16LoScale);
+  }
+  __device__ static __forceinline__ void store_if(bool on, void* base, size_t idx, size_t plane, float v) {
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn((v - __half2float(hi)) * kFp16LoScale);
+    __half* d = (__half*)base + idx;
+    if (on) d[0] = hi;
+    if (on) d[plane] = lo;
   }
   __device__ static __forceinline__ void store4(void* base, size_t idx, size_t plane, float4 v) {
     const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
@@ -270,16 +291,20 @@ template <int PREC, bool TRAIN = false> struct EpiGate {
     store(c, r, m, n, compute(c, acc, pre), acc, pre);
   }
   __device__ __forceinline__ void store(const Col& c, const RowCtx&, int m, int n, float g, float, const Pre& pre) const {
-    if (n < p.S) {
-      p.Z[0][(uint32_t)m * (uint32_t)p.S + (uint32_t)n] = g;
-    } else {
-      const int s = n - p.S;
-      float hb = (1.f - g) * c.a + g * pre.b;
-      if (p.dir == 1) hb *= c.b;
-      OperandFmt<PREC>::store(p.Hbar_cur[0], (uint32_t)m * (uint32_t)p.ldh + (uint32_t)s, p.h_plane, hb);
-      if constexpr (TRAIN) {
-        p.Rg[0][(uint32_t)m * (uint32_t)p.S + (uint32_t)s] = g;
-        if constexpr (PREC != RE2NN_PREC_FP32) p.HbarSaveCur[0][(uint32_t)m * (uint32_t)p.S + (uint32_t)s] = hb;
+    // update-gate columns [0,S) store z; reset-gate columns [S,2S) store the blended operand.  Both forms are
+    // evaluated and only the stores are predicated, so the unrolled 16-row batches of the tcgen05 epilogue stay
+    // branch-free (the branchy form ran 3x slower).
+    const bool is_r = n >= p.S;
+    const uint32_t s = (uint32_t)(is_r ? n - p.S : n);
+    const uint32_t si = (uint32_t)m * (uint32_t)p.S + s;
+    if (!is_r) p.Z[0][si] = g;
+    float hb = (1.f - g) * c.a + g * pre.b;
+    if (p.dir == 1) hb *= c.b;
+    OperandFmt<PREC>::store_if(is_r, p.Hbar_cur[0], (uint32_t)m * (uint32_t)p.ldh + s, p.h_plane, hb);
+    if constexpr (TRAIN) {
+      if (is_r) p.Rg[0][si] = g;
+      if constexpr (PREC != RE2NN_PREC_FP32) {
+        if (is_r) p.HbarSaveCur[0][si] = hb;
       }
     }
   }

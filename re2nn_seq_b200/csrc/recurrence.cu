@@ -292,8 +292,10 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
         e = launch_gemm<PREC>(2, g2, EpiH<PREC, RE2NN_NL_TANH, 0>{p}, m2, st);
       else if (a.farnn == 0)
         e = launch_gemm<PREC>(2, g2, EpiH<PREC, -1, 0>{p}, m2, st);
-      else if (a.update_nonlinear == RE2NN_NL_TANH)
-        e = launch_gemm<PREC>(2, g2, EpiH<PREC, RE2NN_NL_TANH, -1>{p}, m2, st);
+      else if (a.farnn == 2 && a.update_nonlinear == RE2NN_NL_TANH)
+        e = launch_gemm<PREC>(2, g2, EpiH<PREC, RE2NN_NL_TANH, 2>{p}, m2, st);
+      else if (a.farnn == 1 && a.update_nonlinear == RE2NN_NL_TANH)
+        e = launch_gemm<PREC>(2, g2, EpiH<PREC, RE2NN_NL_TANH, 1>{p}, m2, st);
       else
         e = launch_gemm<PREC>(2, g2, EpiH<PREC, -1, -1>{p}, m2, st);
       RE2NN_CUDA(e);

@@ -13,7 +13,8 @@ from re2nn_seq_b200 import synth
 prec = sys.argv[1] if len(sys.argv) > 1 else 'auto'
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 c = synth.CONFIGS['cfg2']
-args = synth.make_args(farnn=0, use_crf=1, update_nonlinear='tanh', beta=0.1)
+farnn = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+args = synth.make_args(farnn=farnn, use_crf=1, update_nonlinear='tanh', beta=0.1)
 f = synth.make_decompose_factors(0, c['V'], c['S'], c['R'], c['C'], c['D'], dtype=np.float32)
 x, lens, lab = synth.make_batch(1000, c['B'], c['Lmax'], c['V'], c['C'])
 torch.manual_seed(0)
