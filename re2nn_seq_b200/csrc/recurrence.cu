@@ -196,7 +196,8 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
 
   if constexpr (PREC != RE2NN_PREC_FP32) {
     // Inference without gates: one resident launch (a CTA pair per 128-row tile runs all steps; recurrence_resident.cuh)
-    if (g_resident_on && !a.save_for_backward && a.farnn == 0 && resident_supported(OperandFmt<PREC>::kPlanes, S, R)) {
+    if (g_resident_on && !a.save_for_backward && a.farnn == 0 &&
+        resident_supported(OperandFmt<PREC>::kPlanes, S, R, PREC != RE2NN_PREC_BF16)) {
       std::unique_ptr<ResidentLaunch> rl(new ResidentLaunch);
       memset(rl.get(), 0, sizeof(ResidentLaunch));
       const int bn1 = resident_part(R), bn2 = resident_part(S);
@@ -215,8 +216,9 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
         if (int rc = tc_make_launch<PREC>(r2, &rl->g2[par], bn2)) return rc;
       }
       rl->steps = L;
+      rl->alias_tbuf = resident_alias(OperandFmt<PREC>::kPlanes, rl->q_first != 0) ? 1 : 0;
       rl->stage_bytes = resident_stage_bytes(OperandFmt<PREC>::kPlanes, S, R);
-      rl->stages = resident_stages(OperandFmt<PREC>::kPlanes, S, R);
+      rl->stages = resident_stages(OperandFmt<PREC>::kPlanes, S, R, rl->q_first != 0);
       for (int z = 0; z < 2; ++z) { p.Hbar_cur[z] = w.Hbar[0][z]; p.Hbar_next[z] = w.Hbar[1][z]; }
       const int pi = prof_begin(3, st);
       cudaError_t e = a.update_nonlinear == RE2NN_NL_TANH ? launch_resident<PREC, RE2NN_NL_TANH>(*rl, p, B, st)
@@ -449,7 +451,7 @@ size_t re2nn_decompose_recurrence_workspace(const re2nn_recurrence_args* a) {
 static bool takes_resident_path(const re2nn_recurrence_args& a) {
   if (a.precision == RE2NN_PREC_FP32 || !g_resident_on || a.save_for_backward || a.farnn != 0) return false;
   const int planes = a.precision == RE2NN_PREC_BF16 ? 1 : 2;
-  return resident_supported(planes, a.S, a.R);
+  return resident_supported(planes, a.S, a.R, a.precision != RE2NN_PREC_BF16);
 }
 
 int re2nn_decompose_recurrence_launches(const re2nn_recurrence_args* a) {

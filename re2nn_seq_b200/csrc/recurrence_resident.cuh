@@ -28,12 +28,14 @@ struct __align__(64) ResidentLaunch {
   int steps;                 // L
   int stage_bytes, stages;   // pipeline geometry (planes * (A tile 16 KB + widest B tile))
   int q_first;               // G2 segment order: 0 = [Hbar @ W, Q @ S^T] (W overlaps the G1 epilogue), 1 = [Q, W]
+  int alias_tbuf;            // epilogue transpose buffers live in the A regions of the pipeline stages (q_first only)
 };
 
 constexpr int kResEpiWarps = 12;        // three epilogue warps per TMEM lane quarter
 constexpr int kResThreads = 64 + 32 * kResEpiWarps;
 constexpr int kResTbufBytes = kResEpiWarps * 32 * 33 * 4;
 constexpr int kResCtxBytes = kResEpiWarps * kTcCtxWords * 4;
+constexpr int kResTbufPerStage = 7;     // 7 x 4224 B fit the 32 KB A region (two planes) of one stage
 constexpr uint32_t kResCorrOff = 256;   // TMEM column of the second (residual) accumulator of the fp16 split
 
 template <int PREC, int NL>
@@ -72,6 +74,10 @@ __global__ void __launch_bounds__(kResThreads, 1) tc_resident_kernel(const __gri
   const uint32_t tfull_bar = bars + 64, tempty_bar = bars + 72, ready_bar = bars + 80, tmem_slot = bars + 88;
   volatile uint32_t* tmem_slot_p = (volatile uint32_t*)(gen_base + stage_region + 88);
   int* ctx_base = reinterpret_cast<int*>(gen_base + stage_region + 256);
+  // Transpose buffers.  With q_first every A-tile load of a phase is issued after the `ready` barrier, i.e. after
+  // every epilogue warp of this CTA is done with its buffer, and the next epilogue starts after all MMAs of the
+  // phase have read the stages: the buffers can then live in the A regions of the stages (7 per 32 KB region)
+  // and the whole 227 KB go to the operand pipeline.
   float* tbuf_base = reinterpret_cast<float*>(gen_base + stage_region + 256 + kResCtxBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -220,7 +226,9 @@ __global__ void __launch_bounds__(kResThreads, 1) tc_resident_kernel(const __gri
   } else {
     // ---- epilogue warps: warp w may touch TMEM lanes 32*(w%4) .. +31 ------------------------------------------
     const int q = warp & 3, ew = warp - 2, half = ew >> 2;
-    float* tbuf = tbuf_base + ew * (32 * 33);
+    float* tbuf = RL.alias_tbuf ? reinterpret_cast<float*>(gen_base + (size_t)(ew / kResTbufPerStage) * stage_bytes) +
+                                      (ew % kResTbufPerStage) * (32 * 33)
+                                : tbuf_base + ew * (32 * 33);
     int* ctx = ctx_base + ew * kTcCtxWords;
     const uint32_t tmem_rows = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t ready_mine = mapa_shared(ready_bar, (uint32_t)crank), ready_peer = mapa_shared(ready_bar, (uint32_t)(crank ^ 1));
@@ -280,26 +288,30 @@ __global__ void __launch_bounds__(kResThreads, 1) tc_resident_kernel(const __gri
   }
 }
 
-inline int resident_smem_bytes(int stages, int stage_bytes) {
-  return stages * stage_bytes + 256 + kResCtxBytes + kResTbufBytes;
-}
-
 inline int resident_part(int n) { return ((cdiv(n, 2) + 15) / 16) * 16; }      // columns of one CTA of the pair
 inline int resident_stage_bytes(int planes, int S, int R) {
   return planes * (128 * 128 + std::max(resident_part(S), resident_part(R)) * 128);
 }
-inline int resident_stages(int planes, int S, int R) {
-  return std::min(4, (kTcSmemLimit - 256 - kResCtxBytes - kResTbufBytes) / resident_stage_bytes(planes, S, R));
+// transpose buffers inside the stages: needs the [Q, W] order (see the kernel) and two-plane A regions
+inline bool resident_alias(int planes, bool q_first) { return q_first && planes == 2; }
+inline int resident_stages(int planes, int S, int R, bool q_first) {
+  const int fixed = 256 + kResCtxBytes + (resident_alias(planes, q_first) ? 0 : kResTbufBytes);
+  return std::min(4, (kTcSmemLimit - fixed) / resident_stage_bytes(planes, S, R));
+}
+inline int resident_smem_bytes(int planes, int stages, int stage_bytes, bool q_first) {
+  return stages * stage_bytes + 256 + kResCtxBytes + (resident_alias(planes, q_first) ? 0 : kResTbufBytes);
 }
 // Can the resident kernel run this problem?  Each CTA of a pair takes half of R and half of S as ONE MMA tile
-// and needs a two-stage operand pipeline.
-inline bool resident_supported(int planes, int S, int R) {
-  return resident_part(S) <= 256 && resident_part(R) <= 256 && resident_stages(planes, S, R) >= 2;
+// and needs a two-stage operand pipeline (and, when aliased, room for all transpose buffers in the A regions).
+inline bool resident_supported(int planes, int S, int R, bool q_first) {
+  const int st = resident_stages(planes, S, R, q_first);
+  if (resident_alias(planes, q_first) && st * kResTbufPerStage < kResEpiWarps) return false;
+  return resident_part(S) <= 256 && resident_part(R) <= 256 && st >= 2;
 }
 
 template <int PREC, int NL>
 inline cudaError_t launch_resident(const ResidentLaunch& RL, const StepParams& p, int B, cudaStream_t st) {
-  const int smem = resident_smem_bytes(RL.stages, RL.stage_bytes);
+  const int smem = resident_smem_bytes(OperandFmt<PREC>::kPlanes, RL.stages, RL.stage_bytes, RL.q_first != 0);
   static int configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(tc_resident_kernel<PREC, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
