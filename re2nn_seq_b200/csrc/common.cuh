@@ -73,6 +73,15 @@ template <bool FAST>
 __device__ __forceinline__ float sigmoid_t(float x) {
   return FAST ? 0.5f * tanh_fast(0.5f * x) + 0.5f : sigmoidf_(x);
 }
+// Branch-free sigmoid for the split-format tensor-core epilogues: ex2.approx + rcp.approx (a few ulp, ~3e-7
+// relative).  The IEEE division of sigmoidf_ carries a slow-path branch per element, which serialises the
+// unrolled 16-row batches of the tcgen05 epilogue (the gate GEMM ran 3x slower than its operand stream).
+__device__ __forceinline__ float sigmoid_ulp(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// MODE 0: exact (fp32 path), 1: MUFU tanh (bf16), 2: few-ulp branch-free (tf32x3 / fp16x3)
+template <int MODE>
+__device__ __forceinline__ float sigmoid_m(float x) {
+  return MODE == 1 ? 0.5f * tanh_fast(0.5f * x) + 0.5f : (MODE == 2 ? sigmoid_ulp(x) : sigmoidf_(x));
+}
 
 // ---- step <-> position mapping ----------------------------------------------------------------
 // The reference runs the backward direction on reverse(input, lengths) and un-reverses the states

@@ -271,6 +271,9 @@ template <int PREC, int NL = -1, int FARNN = -1, bool TRAIN = false> struct EpiH
 // columns [0,S) = update gate pre-activation, [S,2S) = reset gate pre-activation (farnn==2)
 template <int PREC, bool TRAIN = false> struct EpiGate {
   static constexpr bool kFast = PREC == RE2NN_PREC_BF16;
+  // inference on the split formats: few-ulp branch-free sigmoid; training keeps the exact one (its backward
+  // differentiates the saved gate values, parity against the float64 oracle at 1e-4)
+  static constexpr int kSig = PREC == RE2NN_PREC_BF16 ? 1 : ((PREC == RE2NN_PREC_FP32 || TRAIN) ? 0 : 2);
   StepParams p;
   __device__ __forceinline__ EpiGate for_dir(int z) const { EpiGate e = *this; e.p.bind(z); return e; }
   __device__ __forceinline__ bool tile_alive(int z, int mt) const { return re2nn::tile_alive(p, z, mt); }
@@ -285,7 +288,7 @@ template <int PREC, bool TRAIN = false> struct EpiGate {
     return q;
   }
   __device__ __forceinline__ float compute(const Col&, float acc, const Pre& pre) const {
-    return sigmoid_t<kFast>((acc + pre.a) * p.sig_k);
+    return sigmoid_m<kSig>((acc + pre.a) * p.sig_k);
   }
   __device__ __forceinline__ void apply(const Col& c, const RowCtx& r, int m, int n, float acc, const Pre& pre) const {
     store(c, r, m, n, compute(c, acc, pre), acc, pre);

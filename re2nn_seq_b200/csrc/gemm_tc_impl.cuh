@@ -346,12 +346,20 @@ __device__ __forceinline__ void tc_epilogue_chunks(const Epi epi, int M, int N, 
     const int n = n0 + c0 + lane;
     const bool col_ok = n < N && c0 + lane < bn;
     const Col cc = col_ok ? epi.col(n) : Col{0.f, 0.f};
-    // phase 1: every dependent global load of this 32x32 block in flight at once
+    // phase 1: every dependent global load of this 32x32 block in flight at once.  Full-row blocks load without
+    // any guard (lanes past the last column read a valid column of their row and drop the value): one guarded
+    // region per row costs as many instructions as the arithmetic of the row.
     Pre pre[32];
+    if (nrows == 32) {
+      const int n_ld = col_ok ? n : n0;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      pre[i] = Pre{0.f, 0.f};
-      if (col_ok && i < nrows) pre[i] = epi.prefetch(RowCtx{ctx[i], ctx_o[i], ctx_o[i] >= 0}, mrow0 + i, n);
+      for (int i = 0; i < 32; ++i) pre[i] = epi.prefetch(RowCtx{ctx[i], ctx_o[i], ctx_o[i] >= 0}, mrow0 + i, n_ld);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        pre[i] = Pre{0.f, 0.f};
+        if (col_ok && i < nrows) pre[i] = epi.prefetch(RowCtx{ctx[i], ctx_o[i], ctx_o[i] >= 0}, mrow0 + i, n);
+      }
     }
     if (!acc_ready) {
       if (stamp) tc_stamp(trace, 4);   // first prefetch batch issued

@@ -196,7 +196,7 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
 
   if constexpr (PREC != RE2NN_PREC_FP32) {
     // Inference without gates: one resident launch (a CTA pair per 128-row tile runs all steps; recurrence_resident.cuh)
-    if (g_resident_on && !a.save_for_backward && a.farnn == 0 &&
+    if (g_resident_on && !a.save_for_backward &&
         resident_supported(OperandFmt<PREC>::kPlanes, S, R, PREC != RE2NN_PREC_BF16)) {
       std::unique_ptr<ResidentLaunch> rl(new ResidentLaunch);
       memset(rl.get(), 0, sizeof(ResidentLaunch));
@@ -215,14 +215,19 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
         if (int rc = tc_make_launch<PREC>(g_1[par], &rl->g1[par], bn1)) return rc;
         if (int rc = tc_make_launch<PREC>(r2, &rl->g2[par], bn2)) return rc;
       }
+      if (a.farnn >= 1)
+        if (int rc = tc_make_launch<PREC>(g_gate, &rl->gate, bn2)) return rc;
       rl->steps = L;
       rl->alias_tbuf = resident_alias(OperandFmt<PREC>::kPlanes, rl->q_first != 0) ? 1 : 0;
       rl->stage_bytes = resident_stage_bytes(OperandFmt<PREC>::kPlanes, S, R);
       rl->stages = resident_stages(OperandFmt<PREC>::kPlanes, S, R, rl->q_first != 0);
-      for (int z = 0; z < 2; ++z) { p.Hbar_cur[z] = w.Hbar[0][z]; p.Hbar_next[z] = w.Hbar[1][z]; }
+      for (int z = 0; z < 2; ++z) { p.Hbar_cur[z] = w.Hbar[0][z]; p.Hbar_next[z] = w.Hbar[1][z]; p.Z[z] = w.Z[z]; }
       const int pi = prof_begin(3, st);
-      cudaError_t e = a.update_nonlinear == RE2NN_NL_TANH ? launch_resident<PREC, RE2NN_NL_TANH>(*rl, p, B, st)
-                                                           : launch_resident<PREC, -1>(*rl, p, B, st);
+      const bool th = a.update_nonlinear == RE2NN_NL_TANH;
+      cudaError_t e;
+      if (a.farnn == 0) e = th ? launch_resident<PREC, RE2NN_NL_TANH, 0>(*rl, p, B, st) : launch_resident<PREC, -1, 0>(*rl, p, B, st);
+      else if (a.farnn == 1) e = launch_resident<PREC, -1, 1>(*rl, p, B, st);
+      else e = th ? launch_resident<PREC, RE2NN_NL_TANH, 2>(*rl, p, B, st) : launch_resident<PREC, -1, 2>(*rl, p, B, st);
       prof_end(pi, st);
       RE2NN_CUDA(e);
       return 0;
@@ -449,7 +454,7 @@ size_t re2nn_decompose_recurrence_workspace(const re2nn_recurrence_args* a) {
 
 // does this call take the resident single-launch path?  (mirrors the test in run_recurrence)
 static bool takes_resident_path(const re2nn_recurrence_args& a) {
-  if (a.precision == RE2NN_PREC_FP32 || !g_resident_on || a.save_for_backward || a.farnn != 0) return false;
+  if (a.precision == RE2NN_PREC_FP32 || !g_resident_on || a.save_for_backward) return false;
   const int planes = a.precision == RE2NN_PREC_BF16 ? 1 : 2;
   return resident_supported(planes, a.S, a.R, a.precision != RE2NN_PREC_BF16);
 }

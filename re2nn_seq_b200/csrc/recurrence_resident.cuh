@@ -1,4 +1,4 @@
-// Resident decompose recurrence (inference, farnn = 0): ONE launch runs every step of both directions.
+// Resident decompose recurrence (inference, farnn = 0 / 1 / 2): ONE launch runs every step of both directions.
 //
 // The per-step launches of recurrence.cu are bound by what happens BETWEEN the GEMMs, not by the GEMMs: every
 // step boundary is a grid-wide dependency (drain the epilogue stores, resolve the launch, refill the operand
@@ -7,6 +7,8 @@
 // steps of row-independent updates) and the only synchronisation left is between those two CTAs:
 //
 //   CTA j of the pair computes column part j of both GEMMs of every step
+//     G0:  (farnn >= 1) update gate z = sigma(k (H @ Wss1 + gtab_z)), and for farnn = 2 in a second phase the reset
+//          gate r and the blended operand Hbar = (1 - r) h_init + r H [* o]          (EpiGate; z never leaves the CTA)
 //     G1:  Q[:, part j of R]  = (Hbar @ S1|S2) * v_t                      (EpiQ)
 //     G2:  H'[:, part j of S] = phi((Hbar @ W + Q @ S2^T|S1^T) [* o])      (EpiH: alpha/beta rows + next Hbar operand)
 //   through the same TMA -> swizzled smem -> tcgen05.mma -> TMEM -> fused-epilogue pipeline as tc_gemm_kernel.
@@ -25,21 +27,25 @@ namespace re2nn {
 
 struct __align__(64) ResidentLaunch {
   TcLaunch g1[2], g2[2];     // per ping-pong parity of the Hbar operand; cg = 1, bn = the columns of ONE CTA
+  TcLaunch gate;             // farnn >= 1: H @ [Wss1 | Wss2] (N = S * farnn), tiles of the G2 width
   int steps;                 // L
   int stage_bytes, stages;   // pipeline geometry (planes * (A tile 16 KB + widest B tile))
   int q_first;               // G2 segment order: 0 = [Hbar @ W, Q @ S^T] (W overlaps the G1 epilogue), 1 = [Q, W]
   int alias_tbuf;            // epilogue transpose buffers live in the A regions of the pipeline stages (q_first only)
 };
 
-constexpr int kResEpiWarps = 12;        // three epilogue warps per TMEM lane quarter
+constexpr int kResEpiWarps = 12;        // at most three epilogue warps per TMEM lane quarter (shared-memory sizing)
+// epilogue warps actually launched: 12 without gates; the gate epilogues hold two gathered operands per row and
+// spill at the 128 registers twelve warps leave, so the gated kernels run 8
+__host__ __device__ constexpr int resident_epi_warps(int farnn) { return farnn == 0 ? 12 : 8; }
 constexpr int kResThreads = 64 + 32 * kResEpiWarps;
 constexpr int kResTbufBytes = kResEpiWarps * 32 * 33 * 4;
 constexpr int kResCtxBytes = kResEpiWarps * kTcCtxWords * 4;
 constexpr int kResTbufPerStage = 7;     // 7 x 4224 B fit the 32 KB A region (two planes) of one stage
 constexpr uint32_t kResCorrOff = 256;   // TMEM column of the second (residual) accumulator of the fp16 split
 
-template <int PREC, int NL>
-__global__ void __launch_bounds__(kResThreads, 1) tc_resident_kernel(const __grid_constant__ ResidentLaunch RL,
+template <int PREC, int NL, int FARNN>
+__global__ void __launch_bounds__(64 + 32 * resident_epi_warps(FARNN), 1) tc_resident_kernel(const __grid_constant__ ResidentLaunch RL,
                                                                     const StepParams p_in) {
   constexpr bool TF32 = PREC == RE2NN_PREC_TF32X3;
   constexpr int kPlanes = OperandFmt<PREC>::kPlanes;
@@ -47,6 +53,7 @@ __global__ void __launch_bounds__(kResThreads, 1) tc_resident_kernel(const __gri
   constexpr bool TWOACC = PREC == RE2NN_PREC_FP16X3;
   constexpr int kpb = 128 / OperandFmt<PREC>::kElemBytes;
   constexpr int kATile = 128 * 128;
+  constexpr int EW = resident_epi_warps(FARNN);
 
   const int crank = (int)cluster_ctarank();
   const int worker = (int)(blockIdx.x >> 1), nworkers = (int)(gridDim.x >> 1);
@@ -94,13 +101,18 @@ __global__ void __launch_bounds__(kResThreads, 1) tc_resident_kernel(const __gri
           tma_prefetch_desc(&RL.g2[par].maps[s2.b_map]);
         }
       }
+    if (FARNN >= 1)
+      for (int z = 0; z < 2; ++z) {
+        tma_prefetch_desc(&RL.gate.maps[RL.gate.seg[z][0].a_map]);
+        tma_prefetch_desc(&RL.gate.maps[RL.gate.seg[z][0].b_map]);
+      }
     for (int s = 0; s < 4; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tfull_bar, 1);
-    mbar_init(tempty_bar, kResEpiWarps);
-    mbar_init(ready_bar, 2 * kResEpiWarps);       // the epilogue warps of both CTAs
+    mbar_init(tempty_bar, EW);
+    mbar_init(ready_bar, 2 * EW);       // the epilogue warps of both CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -161,7 +173,13 @@ __global__ void __launch_bounds__(kResThreads, 1) tc_resident_kernel(const __gri
       if (lane == 0) {
         for (int k = 0; k < ns; ++k) {
           const int par = k & 1;
-          // G1: A = Hbar[par], published by the previous step's G2 epilogues (or rec_init_kernel for the first)
+          // every phase waits for the rows published by the previous phase (nothing to wait for at the very start)
+          if (FARNN >= 1) {      // G0: A = H (operand format), z columns [0,S), then r columns [S,2S) of [Wss1 | Wss2]
+            load_segment(RL.gate, RL.gate.seg[z][0], m0, crank * bn2, bn2, !first, -1);
+            first = false;
+            if (FARNN == 2) load_segment(RL.gate, RL.gate.seg[z][0], m0, S + crank * bn2, bn2, true, -1);
+          }
+          // G1: A = Hbar[par], published by the previous phase (or rec_init_kernel for the first)
           const bool tr = tile == worker && (k == 2 || k == 3);     // debug trace: one steady-state step
           const int tb = k == 2 ? 8 : 21;
           load_segment(RL.g1[par], RL.g1[par].seg[z][0], m0, crank * bn1, bn1, !first, tr ? tb : -1);
@@ -217,6 +235,8 @@ __global__ void __launch_bounds__(kResThreads, 1) tc_resident_kernel(const __gri
         const int kb2 = RL.g2[0].seg[z][0].kblocks + RL.g2[0].seg[z][1].kblocks;
         for (int k = 0; k < ns; ++k) {
           const bool tr = tile == worker && k == 2;
+          if (FARNN >= 1) mma_gemm(RL.gate.seg[z][0].kblocks, bn2, -1);
+          if (FARNN == 2) mma_gemm(RL.gate.seg[z][0].kblocks, bn2, -1);
           mma_gemm(kb1, bn1, tr ? 14 : -1);
           mma_gemm(kb2, bn2, tr ? 16 : -1);
         }
@@ -267,12 +287,23 @@ __global__ void __launch_bounds__(kResThreads, 1) tc_resident_kernel(const __gri
         }
         __syncwarp();
         const bool tr = tile == worker && k == 2 && ew == 0 && lane == 0;
-        tc_epilogue_chunks<TWOACC, kResEpiWarps / 4>(e1, M, R, mrow0, crank * bn1, bn1, tmem_rows, kResCorrOff, half, lane, tbuf, ctx,
+        if (FARNN >= 1) {
+          const EpiGate<PREC> eg{ps};
+          tc_epilogue_chunks<TWOACC, EW / 4>(eg, M, S, mrow0, crank * bn2, bn2, tmem_rows, kResCorrOff, half, lane,
+                                                       tbuf, ctx, tfull_bar, acc & 1u, nullptr);
+          release_and_publish();
+          if (FARNN == 2) {
+            tc_epilogue_chunks<TWOACC, EW / 4>(eg, M, 2 * S, mrow0, S + crank * bn2, bn2, tmem_rows, kResCorrOff,
+                                                         half, lane, tbuf, ctx, tfull_bar, acc & 1u, nullptr);
+            release_and_publish();
+          }
+        }
+        tc_epilogue_chunks<TWOACC, EW / 4>(e1, M, R, mrow0, crank * bn1, bn1, tmem_rows, kResCorrOff, half, lane, tbuf, ctx,
                                    tfull_bar, acc & 1u, nullptr);
         if (tr) tc_stamp(trace, 18);
         release_and_publish();
-        const EpiH<PREC, NL, 0> e2{ps};
-        tc_epilogue_chunks<TWOACC, kResEpiWarps / 4>(e2, M, S, mrow0, crank * bn2, bn2, tmem_rows, kResCorrOff, half, lane, tbuf, ctx,
+        const EpiH<PREC, NL, FARNN> e2{ps};
+        tc_epilogue_chunks<TWOACC, EW / 4>(e2, M, S, mrow0, crank * bn2, bn2, tmem_rows, kResCorrOff, half, lane, tbuf, ctx,
                                    tfull_bar, acc & 1u, nullptr);
         if (tr) tc_stamp(trace, 19);
         release_and_publish();
@@ -309,12 +340,12 @@ inline bool resident_supported(int planes, int S, int R, bool q_first) {
   return resident_part(S) <= 256 && resident_part(R) <= 256 && st >= 2;
 }
 
-template <int PREC, int NL>
+template <int PREC, int NL, int FARNN>
 inline cudaError_t launch_resident(const ResidentLaunch& RL, const StepParams& p, int B, cudaStream_t st) {
   const int smem = resident_smem_bytes(OperandFmt<PREC>::kPlanes, RL.stages, RL.stage_bytes, RL.q_first != 0);
   static int configured = 0;
   if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(tc_resident_kernel<PREC, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(tc_resident_kernel<PREC, NL, FARNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
@@ -322,7 +353,7 @@ inline cudaError_t launch_resident(const ResidentLaunch& RL, const StepParams& p
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(std::min<long>(tiles, 74) * 2));   // one CTA pair per SM pair
-  cfg.blockDim = dim3(kResThreads);
+  cfg.blockDim = dim3(64 + 32 * resident_epi_warps(FARNN));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -332,7 +363,7 @@ inline cudaError_t launch_resident(const ResidentLaunch& RL, const StepParams& p
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, tc_resident_kernel<PREC, NL>, RL, p);
+  return cudaLaunchKernelEx(&cfg, tc_resident_kernel<PREC, NL, FARNN>, RL, p);
 }
 
 }  // namespace re2nn
