@@ -356,9 +356,10 @@ def main():
         if prof_n[3] > 0:
             # dominant kernel: the resident recurrence kernel (ALL steps of both directions in one launch).
             # Algorithmic flops per launch: every valid position, both directions, G1 (2*S*R) + G2 (2*(R+S)*S)
+            # [+ gate GEMM 2*S*S*farnn]
             dom_name = 'resident recurrence: all steps, G1 + G2 + fused epilogues (%s)' % prec
             dom_cls = 3
-            dom_flops = 2.0 * n_tok * (2.0 * S * R + 2.0 * (R + S) * S)
+            dom_flops = 2.0 * n_tok * (2.0 * S * R + 2.0 * (R + S) * S + 2.0 * S * S * a.farnn)
             try:
                 traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json'))).get(prec + '_resident')
             except Exception:

@@ -226,7 +226,7 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
       const bool th = a.update_nonlinear == RE2NN_NL_TANH;
       cudaError_t e;
       if (a.farnn == 0) e = th ? launch_resident<PREC, RE2NN_NL_TANH, 0>(*rl, p, B, st) : launch_resident<PREC, -1, 0>(*rl, p, B, st);
-      else if (a.farnn == 1) e = launch_resident<PREC, -1, 1>(*rl, p, B, st);
+      else if (a.farnn == 1) e = th ? launch_resident<PREC, RE2NN_NL_TANH, 1>(*rl, p, B, st) : launch_resident<PREC, -1, 1>(*rl, p, B, st);
       else e = th ? launch_resident<PREC, RE2NN_NL_TANH, 2>(*rl, p, B, st) : launch_resident<PREC, -1, 2>(*rl, p, B, st);
       prof_end(pi, st);
       RE2NN_CUDA(e);

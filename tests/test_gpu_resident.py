@@ -116,3 +116,33 @@ def test_resident_precomputed_factors():
             out[prec] = m.forward_scores(vt, lt).cpu().numpy()
     mask = orc.length_mask(lens, L)
     assert rel_err(out['fp16x3'][mask], out['fp32'][mask]) < 1e-5
+
+
+@pytest.mark.parametrize('prec', ['fp16x3', 'tf32x3', 'bf16'])
+@pytest.mark.parametrize('farnn', [1, 2])
+@pytest.mark.parametrize('B,S,R,L', [(5000, 96, 48, 7), (300, 300, 200, 12)])
+def test_resident_gated_matches_per_step_and_oracle(B, S, R, L, farnn, prec):
+    """farnn = 1 / 2: the gate GEMM runs as one (z) or two (z, r) extra phases of the resident kernel."""
+    from test_gpu_parity import _random_decompose
+    _need_tc()
+    m, args, x, lens, lab = _random_decompose(13, 500, S, R, 20, 50, B, L, farnn=farnn, use_crf=0, update_nonlinear='tanh',
+                                              beta=0.1)
+    m.precision = prec
+    m.use_cuda_graph = False
+    xt, lt = _t(x), _t(lens)
+    try:
+        _set_resident(True)
+        s_res, n_res = _launches(m, xt, lt)
+        _set_resident(False)
+        s_step, n_step = _launches(m, xt, lt)
+    finally:
+        _set_resident(True)
+    assert n_res < n_step
+    mask = orc.length_mask(lens, int(lens.max()))
+    a, b = s_res.cpu().numpy()[mask], s_step.cpu().numpy()[mask]
+    if prec != 'bf16':
+        assert np.array_equal(a, b)
+    truth = _truth(m, args, x, lens)[mask]
+    tol = 3e-2 if prec == 'bf16' else 1e-5
+    assert rel_err(a, truth) < tol
+    assert rel_err(b, truth) < tol
