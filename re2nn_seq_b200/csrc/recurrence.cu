@@ -286,7 +286,17 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
       if (a.farnn >= 1)
         RE2NN_CUDA((launch_gemm<PREC>(0, gg, EpiGate<PREC, true>{p}, tm ? &tm->gate : nullptr, st)));
       RE2NN_CUDA((launch_gemm<PREC>(1, g1, EpiQ<PREC, true>{p}, tm ? &tm->g1[par] : nullptr, st)));
-      RE2NN_CUDA((launch_gemm<PREC>(2, g2, EpiH<PREC, -1, -1, true>{p}, tm ? &tm->g2[par] : nullptr, st)));
+      {   // compile-time specialisations of the common training configurations (generic functor otherwise)
+        const TcStepMaps* m2 = tm ? &tm->g2[par] : nullptr;
+        cudaError_t e;
+        if (a.farnn == 0 && a.update_nonlinear == RE2NN_NL_TANH)
+          e = launch_gemm<PREC>(2, g2, EpiH<PREC, RE2NN_NL_TANH, 0, true>{p}, m2, st);
+        else if (a.farnn == 2 && a.update_nonlinear == RE2NN_NL_TANH)
+          e = launch_gemm<PREC>(2, g2, EpiH<PREC, RE2NN_NL_TANH, 2, true>{p}, m2, st);
+        else
+          e = launch_gemm<PREC>(2, g2, EpiH<PREC, -1, -1, true>{p}, m2, st);
+        RE2NN_CUDA(e);
+      }
       continue;
     }
     if (a.farnn >= 1)
