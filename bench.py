@@ -41,6 +41,7 @@ def parse():
     ap.add_argument('--train-precision', default='auto', help='forward GEMMs of --mode train: auto|fp32|tf32x3|fp16x3')
     ap.add_argument('--cta-group', type=int, default=0, help='debug: force the tcgen05 CTA-group size (0 = cost model)')
     ap.add_argument('--resident', type=int, default=1, help='debug: 0 = one launch per step GEMM instead of the resident recurrence kernel')
+    ap.add_argument('--backward-tc', type=int, default=1, help='debug: 0 = BPTT step GEMMs on fp32 CUDA cores')
     ap.add_argument('--cpu-sample', type=int, default=256, help='sequences in the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
@@ -203,6 +204,9 @@ def main():
     if not a.resident:
         from re2nn_seq_b200 import _lib
         _lib.check(_lib.fn['re2nn_debug_set_resident'](0), 'resident')
+    if not a.backward_tc:
+        from re2nn_seq_b200 import _lib
+        _lib.check(_lib.fn['re2nn_debug_set_backward_tc'](0), 'backward_tc')
     if a.cta_group:
         from re2nn_seq_b200 import _lib
         _lib.check(_lib.fn['re2nn_debug_set_tc_cta_group'](a.cta_group), 'cta_group')

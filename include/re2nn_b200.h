@@ -178,6 +178,9 @@ typedef struct re2nn_backward_args {
   float* dvtab;                 /* table_rows x R */
   void* ws; size_t ws_bytes;
 } re2nn_backward_args;
+/* debug / calibration: 1 (default) = the two GEMMs of every BPTT step run on the tensor cores in 3xTF32 when
+ * tcgen05 is available, 0 = fp32 CUDA cores.  Changes the workspace size: set it before querying. */
+int re2nn_debug_set_backward_tc(int on);
 size_t re2nn_decompose_backward_workspace(const re2nn_backward_args* a);
 int re2nn_decompose_backward(const re2nn_backward_args* a, void* stream);
 

@@ -14,8 +14,10 @@
 // (K = 2*L*B), reduced deterministically (split-K partials + ordered sum); bias / vector gradients are
 // deterministic column sums of the per-step slabs.
 #include <algorithm>
+#include <memory>
 
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 
 namespace re2nn {
 
@@ -30,6 +32,10 @@ struct EpiStore2 {          // C_z = acc (per direction output pointers)
   __device__ __forceinline__ Col col(int) const { return Col{0.f, 0.f}; }
   __device__ __forceinline__ Pre prefetch(const RowCtx&, int m, int n) const {
     return Pre{accumulate ? C[0][(size_t)m * ldc + n] : 0.f, 0.f};
+  }
+  __device__ __forceinline__ float compute(const Col&, float acc, const Pre& pre) const { return acc + pre.a; }
+  __device__ __forceinline__ void store(const Col&, const RowCtx&, int m, int n, float v, float, const Pre&) const {
+    C[0][(size_t)m * ldc + n] = v;
   }
   __device__ __forceinline__ void apply(const Col&, const RowCtx&, int m, int n, float acc, const Pre& pre) const {
     C[0][(size_t)m * ldc + n] = acc + pre.a;
@@ -194,6 +200,10 @@ struct BwdCtx {
   float *DU, *Qs;                                    // slabs 2 x L x B x R
   float *DQ, *DHb;                                   // 2 x B x R, 2 x B x S
   float *dvtab, *dgtab;
+  // tensor-core sweep: 3xTF32 operand-format copies of this step's DA / DU (A operands of the two step GEMMs)
+  void* DAop[2]; void* DUop[2];
+  int ldS, ldR;
+  size_t da_plane, du_plane;
 };
 
 __device__ __forceinline__ size_t slab(const BwdCtx& c, int z, int k, int width) {
@@ -217,6 +227,7 @@ __global__ void bwd_e1_kernel(const BwdCtx c) {
     const int gw = c.S * c.farnn;
     if (!alive) {
       c.DA[sl] = 0.f;
+      if (c.DAop[0]) OperandFmt<RE2NN_PREC_TF32X3>::store(c.DAop[z], (size_t)b * c.ldS + s, c.da_plane, 0.f);
       if (z == 0) c.DOprod[sl] = 0.f;
       if (c.farnn >= 1) c.DZR[slab(c, z, c.k, gw) + (size_t)b * gw + s] = 0.f;
       c.GA[(size_t)z * c.B * c.S + e] = 0.f;
@@ -237,12 +248,10 @@ __global__ void bwd_e1_kernel(const BwdCtx c) {
       c.DZR[slab(c, z, c.k, gw) + (size_t)b * gw + s] = dzpre;
     }
     const float dpre = dhhat * nl_grad_from_out(hhat, c.nl);
-    if (z == 0) {
-      c.DA[sl] = dpre * on;
-      c.DOprod[sl] = dpre * a;
-    } else {
-      c.DA[sl] = dpre;
-    }
+    const float da = z == 0 ? dpre * on : dpre;
+    c.DA[sl] = da;
+    if (z == 0) c.DOprod[sl] = dpre * a;
+    if (c.DAop[0]) OperandFmt<RE2NN_PREC_TF32X3>::store(c.DAop[z], (size_t)b * c.ldS + s, c.da_plane, da);
     c.GA[(size_t)z * c.B * c.S + e] = gA;
   }
 }
@@ -261,6 +270,7 @@ __global__ void bwd_e2_kernel(const BwdCtx c) {
     if (!alive) {
       c.DU[sl] = 0.f;
       c.Qs[sl] = 0.f;
+      if (c.DUop[0]) OperandFmt<RE2NN_PREC_TF32X3>::store(c.DUop[z], (size_t)b * c.ldR + r, c.du_plane, 0.f);
       continue;
     }
     const size_t vrow = c.v_mode == RE2NN_V_TOKEN ? (size_t)c.x[(size_t)b * c.Lpad + tpos] : (size_t)b * c.Lpad + tpos;
@@ -268,6 +278,7 @@ __global__ void bwd_e2_kernel(const BwdCtx c) {
     const float u = c.u_save[sl];
     const float dq = c.DQ[(size_t)z * c.B * c.R + e];
     c.DU[sl] = dq * v;
+    if (c.DUop[0]) OperandFmt<RE2NN_PREC_TF32X3>::store(c.DUop[z], (size_t)b * c.ldR + r, c.du_plane, dq * v);
     c.Qs[sl] = u * v;
     const float dv = dq * u;
     if (dv != 0.f) atomicAdd(c.dvtab + vrow * c.R + r, dv);
@@ -371,8 +382,14 @@ struct EpiTokenBwd {
   }
 };
 
+// The two GEMMs of every BPTT step (dq = DA @ S, dhbar = DU @ S^T + DA @ W^T) run on the tensor cores in 3xTF32
+// (fp32-grade products, 8-bit exponent: safe for gradients of any magnitude) when tcgen05 is there.
+static bool g_bwd_tc = true;
+extern "C" int re2nn_has_tcgen05(void);
+static bool bwd_uses_tc() { return g_bwd_tc && re2nn_has_tcgen05() != 0; }
+
 static size_t bwd_carve(const re2nn_backward_args& a, char* base, BwdCtx* c, float** draw, float** partial,
-                        float** dalpha, float** dbeta) {
+                        float** dalpha, float** dbeta, WeightPrep* wp = nullptr) {
   size_t off = 0;
   auto take = [&](size_t floats) -> float* {
     float* p = base ? (float*)(base + off) : nullptr;
@@ -400,6 +417,18 @@ static size_t bwd_carve(const re2nn_backward_args& a, char* base, BwdCtx* c, flo
   float* dr = a.priority_mat ? take(B * L * (size_t)a.C) : nullptr;
   size_t pmax = std::max({S * R, S * S, (size_t)a.C * S, gw ? S * S : (size_t)0, gw ? R * S : (size_t)0});
   float* part = take((size_t)kTnSplit * pmax);
+  if (bwd_uses_tc()) {
+    constexpr int P = RE2NN_PREC_TF32X3;
+    x.ldS = operand_ld(P, (int)S); x.ldR = operand_ld(P, (int)R);
+    x.da_plane = B * x.ldS; x.du_plane = B * x.ldR;
+    for (int z = 0; z < 2; ++z) {
+      x.DAop[z] = take(operand_bytes(P, B, (int)S) / 4);
+      x.DUop[z] = take(operand_bytes(P, B, (int)R) / 4);
+    }
+    WeightPrep w;
+    off += weight_prep_carve(P, (int)S, (int)R, 0, base ? base + off : nullptr, &w);
+    if (wp) *wp = w;
+  }
   if (c) *c = x;
   if (draw) *draw = dr;
   if (partial) *partial = part;
@@ -413,7 +442,10 @@ static int grid_for(size_t total) { return (int)std::min<size_t>((total + 255) /
 static int run_backward(const re2nn_backward_args& a, cudaStream_t st) {
   BwdCtx c;
   float *draw_ws, *partial, *dalpha, *dbeta;
-  const size_t need = bwd_carve(a, (char*)a.ws, &c, &draw_ws, &partial, &dalpha, &dbeta);
+  WeightPrep wp;
+  memset(&wp, 0, sizeof(wp));
+  const bool tc = bwd_uses_tc();
+  const size_t need = bwd_carve(a, (char*)a.ws, &c, &draw_ws, &partial, &dalpha, &dbeta, &wp);
   RE2NN_CHECK(a.ws && a.ws_bytes >= need, "decompose_backward: workspace too small (%zu < %zu)", a.ws_bytes, need);
   const int B = a.B, L = a.L, S = a.S, R = a.R, C = a.C, gw = a.S * a.farnn;
   const size_t M = (size_t)B * L;
@@ -451,6 +483,30 @@ static int run_backward(const re2nn_backward_args& a, cudaStream_t st) {
   RE2NN_CUDA(cudaMemsetAsync(c.g, 0, (size_t)2 * B * S * 4, st));
   RE2NN_CUDA(cudaMemsetAsync(a.dvtab, 0, (size_t)a.table_rows * R * 4, st));
   if (a.farnn >= 1) RE2NN_CUDA(cudaMemsetAsync(c.dgtab, 0, (size_t)a.table_rows * gw * 4, st));
+  std::unique_ptr<TcLaunch> tq, th;
+  if (tc) {
+    // K-major operand-format copies of S1, S2, W (the same layouts the forward uses) + the tensor maps of the two
+    // step GEMMs; the A operands are the per-step DAop / DUop buffers, rewritten every step
+    constexpr int P = RE2NN_PREC_TF32X3;
+    re2nn_recurrence_args ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.S = S; ra.R = R; ra.farnn = 0; ra.S1 = a.S1; ra.S2 = a.S2; ra.W = a.W;
+    if (int rc = weight_prep_run<P>(ra, wp, st)) return rc;
+    GemmProblem gq, gh;
+    memset(&gq, 0, sizeof(gq));
+    memset(&gh, 0, sizeof(gh));
+    gq.M = B; gq.N = R; gq.nseg = 1; gq.ndir = 2;
+    gh.M = B; gh.N = S; gh.nseg = 2; gh.ndir = 2;
+    for (int z = 0; z < 2; ++z) {
+      gq.seg[z][0] = wp.seg_g1(1 - z, c.DAop[z], c.ldS, c.da_plane);      // DA @ S2 (fwd) | DA @ S1 (bwd)
+      gh.seg[z][0] = wp.seg_g2q(1 - z, c.DUop[z], c.ldR, c.du_plane);     // DU @ S1^T (fwd) | DU @ S2^T (bwd)
+      gh.seg[z][1] = wp.seg_g2w(1 - z, c.DAop[z], c.ldS, c.da_plane);     // DA @ W^T (fwd) | DA @ W (bwd)
+    }
+    tq.reset(new TcLaunch);
+    th.reset(new TcLaunch);
+    if (int rc = tc_make_launch<P>(gq, tq.get())) return rc;
+    if (int rc = tc_make_launch<P>(gh, th.get())) return rc;
+  }
   for (int k = L - 1; k >= 0; --k) {
     c.k = k;
     bwd_e1_kernel<<<grid_for((size_t)2 * B * S), 256, 0, st>>>(c);
@@ -460,7 +516,10 @@ static int run_backward(const re2nn_backward_args& a, cudaStream_t st) {
     g.M = B; g.N = R; g.nseg = 1; g.ndir = 2;
     for (int z = 0; z < 2; ++z)
       g.seg[z][0] = GemmSeg{c.DA + ((size_t)z * L + k) * B * S, z == 0 ? a.S2 : a.S1, S, R, S, 0, 0, 0};
-    RE2NN_CUDA(launch_simt_gemm(g, EpiStore2{{c.DQ, c.DQ + (size_t)B * R}, R, 0}, ALoadPlain{}, st));
+    if (tc)
+      RE2NN_CUDA((launch_tc_gemm<RE2NN_PREC_TF32X3>(g, EpiStore2{{c.DQ, c.DQ + (size_t)B * R}, R, 0}, tq.get(), st)));
+    else
+      RE2NN_CUDA(launch_simt_gemm(g, EpiStore2{{c.DQ, c.DQ + (size_t)B * R}, R, 0}, ALoadPlain{}, st));
     bwd_e2_kernel<<<grid_for((size_t)2 * B * R), 256, 0, st>>>(c);
     RE2NN_LAUNCH_CHECK();
     // dhb = DU[k] @ S1^T + DA[k] @ W^T (fwd) | DU[k] @ S2^T + DA[k] @ W (bwd)
@@ -470,7 +529,10 @@ static int run_backward(const re2nn_backward_args& a, cudaStream_t st) {
       g.seg[z][0] = GemmSeg{c.DU + ((size_t)z * L + k) * B * R, z == 0 ? a.S1 : a.S2, R, R, R, 1, 0, 0};
       g.seg[z][1] = GemmSeg{c.DA + ((size_t)z * L + k) * B * S, a.W, S, S, S, z == 0 ? 1 : 0, 0, 0};
     }
-    RE2NN_CUDA(launch_simt_gemm(g, EpiStore2{{c.DHb, c.DHb + (size_t)B * S}, S, 0}, ALoadPlain{}, st));
+    if (tc)
+      RE2NN_CUDA((launch_tc_gemm<RE2NN_PREC_TF32X3>(g, EpiStore2{{c.DHb, c.DHb + (size_t)B * S}, S, 0}, th.get(), st)));
+    else
+      RE2NN_CUDA(launch_simt_gemm(g, EpiStore2{{c.DHb, c.DHb + (size_t)B * S}, S, 0}, ALoadPlain{}, st));
     bwd_e3_kernel<<<grid_for((size_t)2 * B * S), 256, 0, st>>>(c);
     RE2NN_LAUNCH_CHECK();
     if (a.farnn >= 1) {
@@ -575,6 +637,11 @@ static int run_backward(const re2nn_backward_args& a, cudaStream_t st) {
 using namespace re2nn;
 
 extern "C" {
+
+int re2nn_debug_set_backward_tc(int on) {
+  g_bwd_tc = on != 0;
+  return 0;
+}
 
 size_t re2nn_decompose_backward_workspace(const re2nn_backward_args* a) {
   if (!a) return 0;

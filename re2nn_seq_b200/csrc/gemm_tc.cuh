@@ -68,7 +68,7 @@ inline size_t weight_prep_carve(int prec, int S, int R, int farnn, char* base, W
   return off;
 }
 
-__global__ void concat_gate_kernel(const float* Wss1, const float* Wss2, int S, float* Wg) {
+static __global__ void concat_gate_kernel(const float* Wss1, const float* Wss2, int S, float* Wg) {
   const int total = S * 2 * S;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     int k = i / (2 * S), n = i - k * 2 * S;

@@ -315,9 +315,9 @@ template <int PREC, int BN, int CG = 1> struct TcCfg {
 };
 
 // optional per-CTA phase trace (debug): 8 clock64 stamps per CTA when a buffer is installed
-__device__ unsigned long long* g_tc_trace = nullptr;
-__device__ unsigned long long* g_tc_timeline = nullptr;   // [launch][2] globaltimer ns of CTA (0,0,0): entry, exit
-__device__ unsigned int g_tc_timeline_ctr = 0;
+static __device__ unsigned long long* g_tc_trace = nullptr;
+static __device__ unsigned long long* g_tc_timeline = nullptr;   // [launch][2] globaltimer ns of CTA (0,0,0): entry, exit
+static __device__ unsigned int g_tc_timeline_ctr = 0;
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
