@@ -198,6 +198,117 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_nll_kernel(
   }
 }
 
+// Same log-partition in the scaled exponential domain: with M = max_i part[i] and cmax[j] = max_i trans[i][j]
+//   LSE_i(part[i] + trans[i][j]) = M + cmax[j] + log sum_i exp(part[i] - M) * exp(trans[i][j] - cmax[j])
+// so a step costs T exps and T*T FFMAs instead of 2*T*T exps (the log-domain kernel above spends ~1200 instructions
+// per (t, j); this one ~100).  exp(trans - cmax) is tabulated once per CTA.  A column whose sum underflows (only
+// reachable from states that are e^-87 below the best one, e.g. hard-constrained transitions) falls back to the
+// exact two-pass form for that (t, j), so the result stays within fp32 rounding of the log-domain kernel.
+// dynamic smem: trans T*T | exp table T*T | cmax Tp | per warp: part a, part b, E (3 * Tp)
+template <int NJ>
+__global__ void __launch_bounds__(kCrfWarps * 32) crf_nll_exp_kernel(
+    const float* __restrict__ feats, const float* __restrict__ trans_g, const int64_t* __restrict__ len,
+    const int64_t* __restrict__ tags, int B, int L, int Ltags, int T, float* __restrict__ per_seq,
+    float* __restrict__ part_save) {
+  extern __shared__ float smem[];
+  const int Tp = (T + 31) & ~31;
+  float* tr = smem;
+  float* te = tr + T * T;
+  float* cmax = te + T * T;
+  float* s_part = cmax + Tp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < T * T; i += blockDim.x) tr[i] = trans_g[i];
+  __syncthreads();
+  for (int j = threadIdx.x; j < Tp; j += blockDim.x) {
+    float m = -INFINITY;
+    if (j < T)
+      for (int i = 0; i < T; ++i) m = fmaxf(m, tr[i * T + j]);
+    cmax[j] = m;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * T; i += blockDim.x) te[i] = expf(tr[i] - cmax[i % T]);
+  __syncthreads();
+  const int b = blockIdx.x * kCrfWarps + warp;
+  if (b >= B) return;
+  const int n = (int)len[b];
+  float* pa = s_part + warp * 3 * Tp;
+  float* pb = pa + Tp;
+  float* E = pb + Tp;
+  const float* fb = feats + (size_t)b * L * T;
+  float* ps = part_save ? part_save + (size_t)b * L * T : nullptr;
+
+  for (int j = lane; j < Tp; j += 32) {
+    float v = -INFINITY;
+    if (j < T) {
+      v = __ldg(fb + j) + tr[(T - 2) * T + j];
+      if (ps) ps[j] = v;
+    }
+    pa[j] = v;
+  }
+  __syncwarp();
+  for (int t = 1; t < n; ++t) {
+    const float* ft = fb + (size_t)t * T;
+    float M = -INFINITY;
+    for (int i = lane; i < T; i += 32) M = fmaxf(M, pa[i]);
+    M = warp_max(M);
+    for (int i = lane; i < Tp; i += 32) E[i] = i < T ? expf(pa[i] - M) : 0.f;
+    __syncwarp();
+    float acc[NJ];
+#pragma unroll
+    for (int q = 0; q < NJ; ++q) acc[q] = 0.f;
+    // lanes whose last slot falls past T read (and ignore) the following shared-memory words
+#pragma unroll 5
+    for (int i = 0; i < T; ++i) {
+      const float e = E[i];
+      const float* tei = te + i * T + lane;
+#pragma unroll
+      for (int q = 0; q < NJ; ++q) acc[q] = fmaf(e, tei[32 * q], acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < NJ; ++q) {
+      const int j = lane + 32 * q;
+      if (j < T) {
+        const float f = __ldg(ft + j);
+        float v;
+        if (acc[q] > 1e-30f) {
+          v = ((M + cmax[j]) + f) + logf(acc[q]);
+        } else {   // underflow: exact log-domain evaluation of this column
+          float m = -INFINITY;
+          for (int i = 0; i < T; ++i) m = fmaxf(m, (f + tr[i * T + j]) + pa[i]);
+          float sm = 0.f;
+          for (int i = 0; i < T; ++i) sm += expf(((f + tr[i * T + j]) + pa[i]) - m);
+          v = m + logf(sm);
+        }
+        pb[j] = v;
+        if (ps) ps[(size_t)t * T + j] = v;
+      }
+    }
+    __syncwarp();
+    float* tmp = pa; pa = pb; pb = tmp;
+  }
+  // logZ = LSE_i(trans[i][STOP] + part_i)
+  float m = -INFINITY;
+  for (int i = lane; i < T; i += 32) m = fmaxf(m, tr[i * T + (T - 1)] + pa[i]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int i = lane; i < T; i += 32) s += expf((tr[i * T + (T - 1)] + pa[i]) - m);
+  s = warp_sum(s);
+  const float logZ = m + logf(s);
+  // gold path
+  const int64_t* tg = tags + (size_t)b * Ltags;
+  float g = 0.f;
+  for (int t = lane; t < n; t += 32) {
+    int cur = (int)tg[t];
+    int prev = t == 0 ? T - 2 : (int)tg[t - 1];
+    g += __ldg(fb + (size_t)t * T + cur) + tr[prev * T + cur];
+  }
+  g = warp_sum(g);
+  if (lane == 0) {
+    g += tr[(int)tg[n - 1] * T + (T - 1)];
+    per_seq[b] = logZ - g;
+  }
+}
+
 // CRF backward: marginals by the backward recursion, reusing the saved forward partitions.
 //   dfeats[b,t,j] = gs * (P(y_t=j) - [tag_t=j]);  dtrans[i,j] += gs * (sum_t P(y_{t-1}=i,y_t=j) - gold counts)
 // Every warp owns a private T x T accumulator in shared memory (row pitch padded to an odd number of words:
@@ -279,6 +390,120 @@ __global__ void crf_nll_backward_kernel(
       float* tmp = ba; ba = bb; bb = tmp;
     }
     // zero the pad rows of dfeats
+    for (int i = n * T + lane; i < L * T; i += 32) df[i] = 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
+    const int r = i / T, c = i - r * T;
+    float v = 0.f;
+    for (int w = 0; w < nw; ++w) v += s_dtr[(size_t)w * T * Tq + r * Tq + c];
+    if (v != 0.f) atomicAdd(dtrans + i, v);
+  }
+}
+
+// CRF backward in the scaled exponential domain (see crf_nll_exp_kernel): with w_j = feat_t[j] + beta_t[j],
+// Mw = max_j w_j, W_j = exp(w_j - Mw), rmax[i] = max_j trans[i][j] and the table exp(trans[i][j] - rmax[i]),
+//   beta_{t-1}[i]    = rmax[i] + Mw + log S_i,   S_i = sum_j table[i][j] * W_j
+//   P(y_{t-1}=i,y_t=j) = exp(part_{t-1}[i] - logZ + rmax[i] + Mw) * table[i][j] * W_j
+// i.e. T exps, T logs and 2 T*T multiply-adds per step instead of 3 T*T exps.  A row whose S_i underflows is
+// evaluated exactly in the log domain (same formulas as crf_nll_backward_kernel).
+// dynamic smem: trans T*T | table T*T | rmax Tp | per warp: dtrans accumulator T*Tq, beta a / b, W (3 * Tp)
+__global__ void crf_nll_backward_exp_kernel(
+    const float* __restrict__ feats, const float* __restrict__ trans_g, const int64_t* __restrict__ len,
+    const int64_t* __restrict__ tags, const float* __restrict__ part_save, const float* __restrict__ gscale, int B,
+    int L, int Ltags, int T, float* __restrict__ dfeats, float* __restrict__ dtrans) {
+  extern __shared__ float smem[];
+  const int nw = blockDim.x >> 5;
+  const int Tp = (T + 31) & ~31;
+  const int Tq = T | 1;
+  float* tr = smem;
+  float* te = tr + T * T;
+  float* rmax = te + T * T;
+  float* s_dtr = rmax + Tp;
+  float* s_vec = s_dtr + (size_t)nw * T * Tq;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < T * T; i += blockDim.x) tr[i] = trans_g[i];
+  for (int i = threadIdx.x; i < nw * T * Tq; i += blockDim.x) s_dtr[i] = 0.f;
+  __syncthreads();
+  for (int i = threadIdx.x; i < Tp; i += blockDim.x) {
+    float m = -INFINITY;
+    if (i < T)
+      for (int j = 0; j < T; ++j) m = fmaxf(m, tr[i * T + j]);
+    rmax[i] = m;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * T; i += blockDim.x) te[i] = expf(tr[i] - rmax[i / T]);
+  __syncthreads();
+  const float gs = gscale ? *gscale : 1.f;
+  float* dw = s_dtr + (size_t)warp * T * Tq;
+  const int b = blockIdx.x * nw + warp;
+  if (b < B) {
+    const int n = (int)len[b];
+    float* ba = s_vec + warp * 3 * Tp;   // beta_t
+    float* bb = ba + Tp;                 // beta_{t-1}
+    float* W = bb + Tp;
+    const float* fb = feats + (size_t)b * L * T;
+    const float* ps = part_save + (size_t)b * L * T;
+    float* df = dfeats + (size_t)b * L * T;
+    const int64_t* tg = tags + (size_t)b * Ltags;
+    const float* pl = ps + (size_t)(n - 1) * T;
+    float m = -INFINITY;
+    for (int i = lane; i < T; i += 32) m = fmaxf(m, tr[i * T + (T - 1)] + pl[i]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int i = lane; i < T; i += 32) s += expf((tr[i * T + (T - 1)] + pl[i]) - m);
+    s = warp_sum(s);
+    const float logZ = m + logf(s);
+    for (int i = lane; i < T; i += 32) ba[i] = tr[i * T + (T - 1)];
+    __syncwarp();
+    for (int t = n - 1; t >= 0; --t) {
+      const float* pt = ps + (size_t)t * T;
+      const int gold = (int)tg[t];
+      for (int j = lane; j < T; j += 32) {
+        const float d = gs * (expf(pt[j] + ba[j] - logZ) - (j == gold ? 1.f : 0.f));
+        df[(size_t)t * T + j] = d;
+        if (t == n - 1) dw[j * Tq + (T - 1)] += d;
+      }
+      __syncwarp();
+      if (t == 0) {
+        for (int j = lane; j < T; j += 32) dw[(T - 2) * Tq + j] += df[j];
+        break;
+      }
+      const float* pp = ps + (size_t)(t - 1) * T;
+      const float* ft = fb + (size_t)t * T;
+      const int gprev = (int)tg[t - 1];
+      // W_j = exp(feat_t[j] + beta_t[j] - Mw)
+      float Mw = -INFINITY;
+      for (int j = lane; j < T; j += 32) Mw = fmaxf(Mw, __ldg(ft + j) + ba[j]);
+      Mw = warp_max(Mw);
+      for (int j = lane; j < T; j += 32) W[j] = expf((__ldg(ft + j) + ba[j]) - Mw);
+      __syncwarp();
+      for (int i = lane; i < T; i += 32) {      // lane owns source rows i
+        const float* tei = te + i * T;
+        float* dwi = dw + i * Tq;
+        float S = 0.f;
+        for (int j = 0; j < T; ++j) S = fmaf(tei[j], W[j], S);
+        if (S > 1e-30f) {
+          const float A = gs * expf(((pp[i] - logZ) + rmax[i]) + Mw);
+          for (int j = 0; j < T; ++j) dwi[j] = fmaf(A * tei[j], W[j], dwi[j]);
+          bb[i] = (rmax[i] + Mw) + logf(S);
+        } else {                                 // underflow: exact log-domain evaluation of this row
+          float mx = -INFINITY;
+          for (int j = 0; j < T; ++j) mx = fmaxf(mx, (tr[i * T + j] + __ldg(ft + j)) + ba[j]);
+          float sm = 0.f;
+          const float pi = pp[i] - logZ;
+          for (int j = 0; j < T; ++j) {
+            const float e = (tr[i * T + j] + __ldg(ft + j)) + ba[j];
+            sm += expf(e - mx);
+            dwi[j] += gs * expf(pi + e);
+          }
+          bb[i] = mx + logf(sm);
+        }
+        if (i == gprev) dwi[gold] -= gs;
+      }
+      __syncwarp();
+      float* tmp = ba; ba = bb; bb = tmp;
+    }
     for (int i = n * T + lane; i < L * T; i += 32) df[i] = 0.f;
   }
   __syncthreads();
@@ -471,7 +696,24 @@ int re2nn_crf_nll(const float* feats, const float* transitions, const int64_t* l
   const size_t with_tr = part + (size_t)T * T * 4;
   const int grid = cdiv(B, kCrfWarps);
   cudaStream_t st = (cudaStream_t)stream;
-  if (with_tr <= kSmemLimit) {
+  const size_t exp_smem = ((size_t)2 * T * T + Tp + (size_t)kCrfWarps * 3 * Tp) * 4 + 32 * 4 * 5;   // + overrun slack
+  if (exp_smem <= kSmemLimit && T <= 160) {
+#define RE2NN_NLL(NJ)                                                                                              \
+  do {                                                                                                             \
+    RE2NN_CUDA(cudaFuncSetAttribute(crf_nll_exp_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                    (int)exp_smem));                                                               \
+    crf_nll_exp_kernel<NJ><<<grid, kCrfWarps * 32, exp_smem, st>>>(feats, transitions, lengths, tags, B, L, Ltags, \
+                                                                   T, per_seq, part_save);                         \
+  } while (0)
+    switch (cdiv(T, 32)) {
+      case 1: RE2NN_NLL(1); break;
+      case 2: RE2NN_NLL(2); break;
+      case 3: RE2NN_NLL(3); break;
+      case 4: RE2NN_NLL(4); break;
+      default: RE2NN_NLL(5); break;
+    }
+#undef RE2NN_NLL
+  } else if (with_tr <= kSmemLimit) {
     RE2NN_CUDA(cudaFuncSetAttribute(crf_nll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_tr));
     crf_nll_kernel<true><<<grid, kCrfWarps * 32, with_tr, st>>>(feats, transitions, lengths, tags, B, L, Ltags, T,
                                                                 per_seq, part_save);
@@ -496,6 +738,19 @@ int re2nn_crf_nll_backward(const float* feats, const float* transitions, const i
   const size_t tr_bytes = (size_t)T * T * 4;
   cudaStream_t st = (cudaStream_t)stream;
   RE2NN_CUDA(cudaMemsetAsync(dtrans, 0, tr_bytes, st));
+  {   // scaled-exponential kernel when transitions + table + at least two warps' accumulators fit
+    const size_t pw = ((size_t)T * Tq + 3 * Tp) * 4;
+    const size_t fixed = 2 * tr_bytes + (size_t)Tp * 4;
+    if (fixed + 2 * pw <= kSmemLimit) {
+      const int nwe = (int)std::min<size_t>(kCrfWarps, (kSmemLimit - fixed) / pw);
+      const size_t smem_e = fixed + nwe * pw;
+      RE2NN_CUDA(cudaFuncSetAttribute(crf_nll_backward_exp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+      crf_nll_backward_exp_kernel<<<cdiv(B, nwe), nwe * 32, smem_e, st>>>(feats, transitions, lengths, tags, part_save,
+                                                                          gscale, B, L, Ltags, T, dfeats, dtrans);
+      RE2NN_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   // as many warps (sequences) per CTA as the private accumulators allow, transitions in smem when they still fit
   bool ts = tr_bytes + per_warp <= kSmemLimit;
   size_t avail = kSmemLimit - (ts ? tr_bytes : 0);
