@@ -228,3 +228,46 @@ def test_training_with_tensor_core_forward(farnn, crf, tp):
         if v.requires_grad:
             err = rel_err(v.grad.cpu().numpy(), g64[rename.get(k, k)])
             assert err < 1e-4, '%s: rel err %.3e' % (k, err)
+
+
+def test_crf_hard_constraints_underflow_fallback():
+    """Spiky features + forbidden (-1e4) transitions: the scaled-exponential CRF kernels underflow on some columns /
+    rows and must take their exact log-domain fallback; loss and gradients against a float64 autograd CRF."""
+    import re2nn_seq_b200 as r
+    rs = np.random.RandomState(3)
+    ntag, B, L = 20, 37, 14
+    T = ntag + 2
+    feats = (rs.randn(B, L, T) * 12.0).astype(np.float32)
+    lens = rs.randint(2, L + 1, size=B).astype(np.int64)
+    lens[0] = L
+    tags = rs.randint(0, ntag, size=(B, L)).astype(np.int64)
+    trans = rs.randn(T, T).astype(np.float32)
+    trans[rs.rand(T, T) < 0.4] = -10000.0
+    trans[:, T - 2] = -10000.0
+    trans[T - 1, :] = -10000.0
+    crf = r.CRF(ntag, True).cuda()
+    with torch.no_grad():
+        crf.transitions.copy_(_t(trans))
+    f = _t(feats).requires_grad_(True)
+    mask = _t(orc.length_mask(lens, L))
+    loss = crf.neg_log_likelihood_loss(f, mask, _t(tags))
+    loss.backward()
+    # float64 reference (crf.py:48-99,202-251 in plain autograd)
+    f64 = torch.from_numpy(feats).double().requires_grad_(True)
+    t64 = torch.from_numpy(trans).double().requires_grad_(True)
+    total = 0.0
+    for b in range(B):
+        n = int(lens[b])
+        part = f64[b, 0] + t64[T - 2]
+        gold = f64[b, 0, tags[b, 0]] + t64[T - 2, tags[b, 0]]
+        for t in range(1, n):
+            part = torch.logsumexp(part[:, None] + t64, 0) + f64[b, t]
+            gold = gold + f64[b, t, tags[b, t]] + t64[tags[b, t - 1], tags[b, t]]
+        logz = torch.logsumexp(part + t64[:, T - 1], 0)
+        gold = gold + t64[tags[b, n - 1], T - 1]
+        total = total + (logz - gold)
+    total.backward()
+    assert rel_err(loss.item(), total.item()) < TOL
+    # log Z is a few hundred here: fp32 keeps ~3e-5 absolute on it, which is the relative error of every marginal
+    assert rel_err(f.grad.cpu().numpy(), f64.grad.numpy()) < 3e-4
+    assert rel_err(crf.transitions.grad.cpu().numpy(), t64.grad.numpy()) < 3e-4
