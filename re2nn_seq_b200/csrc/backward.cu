@@ -202,6 +202,7 @@ struct BwdCtx {
   float *dvtab, *dgtab;
   // tensor-core sweep: 3xTF32 operand-format copies of this step's DA / DU (A operands of the two step GEMMs)
   void* DAop[2]; void* DUop[2];
+  void* DZop[2]; void* DRop[2];                      // farnn >= 1: dz / dr of this step (A operands of the gate GEMM)
   int ldS, ldR;
   size_t da_plane, du_plane;
 };
@@ -229,7 +230,10 @@ __global__ void bwd_e1_kernel(const BwdCtx c) {
       c.DA[sl] = 0.f;
       if (c.DAop[0]) OperandFmt<RE2NN_PREC_TF32X3>::store(c.DAop[z], (size_t)b * c.ldS + s, c.da_plane, 0.f);
       if (z == 0) c.DOprod[sl] = 0.f;
-      if (c.farnn >= 1) c.DZR[slab(c, z, c.k, gw) + (size_t)b * gw + s] = 0.f;
+      if (c.farnn >= 1) {
+        c.DZR[slab(c, z, c.k, gw) + (size_t)b * gw + s] = 0.f;
+        if (c.DZop[0]) OperandFmt<RE2NN_PREC_TF32X3>::store(c.DZop[z], (size_t)b * c.ldS + s, c.da_plane, 0.f);
+      }
       c.GA[(size_t)z * c.B * c.S + e] = 0.f;
       continue;
     }
@@ -246,6 +250,7 @@ __global__ void bwd_e1_kernel(const BwdCtx c) {
       gA = G * (1.f - zt);
       const float dzpre = G * (hhat - hk) * zt * (1.f - zt) * c.kappa;
       c.DZR[slab(c, z, c.k, gw) + (size_t)b * gw + s] = dzpre;
+      if (c.DZop[0]) OperandFmt<RE2NN_PREC_TF32X3>::store(c.DZop[z], (size_t)b * c.ldS + s, c.da_plane, dzpre);
     }
     const float dpre = dhhat * nl_grad_from_out(hhat, c.nl);
     const float da = z == 0 ? dpre * on : dpre;
@@ -302,6 +307,7 @@ __global__ void bwd_e3_kernel(const BwdCtx c) {
       if (c.farnn == 2) {
         c.Pinit[sl] = 0.f;
         c.DZR[slab(c, z, c.k, gw) + (size_t)b * gw + c.S + s] = 0.f;
+        if (c.DRop[0]) OperandFmt<RE2NN_PREC_TF32X3>::store(c.DRop[z], (size_t)b * c.ldS + s, c.da_plane, 0.f);
       }
       continue;
     }
@@ -323,6 +329,7 @@ __global__ void bwd_e3_kernel(const BwdCtx c) {
       c.Pinit[sl] = dht * (1.f - rt);
       const float drpre = dht * (hk - hinit) * rt * (1.f - rt) * c.kappa;
       c.DZR[slab(c, z, c.k, gw) + (size_t)b * gw + c.S + s] = drpre;
+      if (c.DRop[0]) OperandFmt<RE2NN_PREC_TF32X3>::store(c.DRop[z], (size_t)b * c.ldS + s, c.da_plane, drpre);
     }
     c.g[(size_t)z * c.B * c.S + e] = c.GA[(size_t)z * c.B * c.S + e] + gB;
   }
@@ -425,8 +432,16 @@ static size_t bwd_carve(const re2nn_backward_args& a, char* base, BwdCtx* c, flo
       x.DAop[z] = take(operand_bytes(P, B, (int)S) / 4);
       x.DUop[z] = take(operand_bytes(P, B, (int)R) / 4);
     }
+    for (int z = 0; z < 2 && a.farnn >= 1; ++z) {
+      x.DZop[z] = take(operand_bytes(P, B, (int)S) / 4);
+      if (a.farnn == 2) x.DRop[z] = take(operand_bytes(P, B, (int)S) / 4);
+    }
     WeightPrep w;
     off += weight_prep_carve(P, (int)S, (int)R, 0, base ? base + off : nullptr, &w);
+    if (a.farnn >= 1) {      // K-major copies of Wss1 / Wss2 themselves (the forward holds their transposes)
+      w.buf[6] = take(operand_bytes(P, S, (int)S) / 4);
+      if (a.farnn == 2) w.buf[7] = take(operand_bytes(P, S, (int)S) / 4);
+    }
     if (wp) *wp = w;
   }
   if (c) *c = x;
@@ -483,7 +498,7 @@ static int run_backward(const re2nn_backward_args& a, cudaStream_t st) {
   RE2NN_CUDA(cudaMemsetAsync(c.g, 0, (size_t)2 * B * S * 4, st));
   RE2NN_CUDA(cudaMemsetAsync(a.dvtab, 0, (size_t)a.table_rows * R * 4, st));
   if (a.farnn >= 1) RE2NN_CUDA(cudaMemsetAsync(c.dgtab, 0, (size_t)a.table_rows * gw * 4, st));
-  std::unique_ptr<TcLaunch> tq, th;
+  std::unique_ptr<TcLaunch> tq, th, tg;
   if (tc) {
     // K-major operand-format copies of S1, S2, W (the same layouts the forward uses) + the tensor maps of the two
     // step GEMMs; the A operands are the per-step DAop / DUop buffers, rewritten every step
@@ -506,6 +521,22 @@ static int run_backward(const re2nn_backward_args& a, cudaStream_t st) {
     th.reset(new TcLaunch);
     if (int rc = tc_make_launch<P>(gq, tq.get())) return rc;
     if (int rc = tc_make_launch<P>(gh, th.get())) return rc;
+    if (a.farnn >= 1) {
+      const size_t pl = (size_t)S * wp.ldS;
+      const int blocks = (int)(((size_t)S * wp.ldS + 255) / 256);
+      convert_weight_kernel<P><<<blocks, 256, 0, st>>>(a.Wss1, S, S, S, 0, wp.buf[6], wp.ldS, pl, 0);
+      if (a.farnn == 2) convert_weight_kernel<P><<<blocks, 256, 0, st>>>(a.Wss2, S, S, S, 0, wp.buf[7], wp.ldS, pl, 0);
+      RE2NN_LAUNCH_CHECK();
+      GemmProblem gg;
+      memset(&gg, 0, sizeof(gg));
+      gg.M = B; gg.N = S; gg.nseg = a.farnn; gg.ndir = 2;
+      for (int z = 0; z < 2; ++z) {
+        gg.seg[z][0] = GemmSeg{c.DZop[z], wp.buf[6], c.ldS, wp.ldS, S, 1, c.da_plane, pl};
+        if (a.farnn == 2) gg.seg[z][1] = GemmSeg{c.DRop[z], wp.buf[7], c.ldS, wp.ldS, S, 1, c.da_plane, pl};
+      }
+      tg.reset(new TcLaunch);
+      if (int rc = tc_make_launch<P>(gg, tg.get())) return rc;
+    }
   }
   for (int k = L - 1; k >= 0; --k) {
     c.k = k;
@@ -544,7 +575,10 @@ static int run_backward(const re2nn_backward_args& a, cudaStream_t st) {
         g.seg[z][0] = GemmSeg{dzr, a.Wss1, gw, S, S, 1, 0, 0};
         if (a.farnn == 2) g.seg[z][1] = GemmSeg{dzr + S, a.Wss2, gw, S, S, 1, 0, 0};
       }
-      RE2NN_CUDA(launch_simt_gemm(g, EpiStore2{{c.g, c.g + (size_t)B * S}, S, 1}, ALoadPlain{}, st));
+      if (tc)
+        RE2NN_CUDA((launch_tc_gemm<RE2NN_PREC_TF32X3>(g, EpiStore2{{c.g, c.g + (size_t)B * S}, S, 1}, tg.get(), st)));
+      else
+        RE2NN_CUDA(launch_simt_gemm(g, EpiStore2{{c.g, c.g + (size_t)B * S}, S, 1}, ALoadPlain{}, st));
       bwd_gate_scatter_kernel<<<grid_for((size_t)2 * B * gw), 256, 0, st>>>(c);
       RE2NN_LAUNCH_CHECK();
     }

@@ -9,7 +9,8 @@ import re2nn_seq_b200 as r
 from re2nn_seq_b200 import synth
 
 c = synth.CONFIGS['cfg3']
-args = synth.make_args(farnn=0, use_crf=1, update_nonlinear='tanh', beta=0.1)
+farnn = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+args = synth.make_args(farnn=farnn, use_crf=1, update_nonlinear='tanh', beta=0.1, sigmoid_exponent=5, bias_init=5.0)
 f = synth.make_decompose_factors(0, c['V'], c['S'], c['R'], c['C'], c['D'], dtype=np.float32)
 x, lens, lab = synth.make_batch(1000, c['B'], c['Lmax'], c['V'], c['C'])
 torch.manual_seed(0)
@@ -17,7 +18,7 @@ m = r.FARNN_S_D_W_I_S(args=args, o_idx=0, **f)
 with torch.no_grad():
     m.crf.transitions.copy_(torch.from_numpy(synth.crf_transitions(0, m.C)))
 m = m.cuda().train()
-m.train_precision = 'auto'
+m.train_precision = "auto"
 xt, lt, yt = (torch.from_numpy(a).cuda() for a in (x, lens, lab))
 def step():
     for q in m.parameters():
