@@ -51,3 +51,27 @@ def test_utils_match_oracle():
                                   orc.flatten_rows(a, lens))
     np.testing.assert_array_equal(utils.get_length_mask(torch.from_numpy(lens)).numpy(), orc.length_mask(lens))
     np.testing.assert_array_equal(utils.exclusive_offsets(torch.from_numpy(lens)).numpy(), [0, 7, 8, 11, 16])
+
+
+def test_embed_aggregator_surface():
+    """EmbedAggregator / FARNN_S_bert expose the reference's parameter names (bert_embeddings.py:46-80,
+    model_decompose_single_with_bert.py:16-47) and its initialisation embed_r_generalized = pinv(E) @ V."""
+    import re2nn_seq_b200 as r
+    from re2nn_seq_b200 import synth
+    args = synth.make_args(farnn=0, use_crf=0, train_V_embed=1, train_beta=0, train_word_embed=0)
+    f = synth.make_decompose_factors(0, 120, 24, 16, 6, 20, dtype=np.float64)
+    agg = r.EmbedAggregator(args, f['V'], f['pretrained_word_embed'])
+    assert sorted(agg.state_dict()) == ['V_embed', 'beta_vec', 'embed.embedding.weight', 'embed_r_generalized']
+    E = torch.from_numpy(f['pretrained_word_embed']).float()
+    np.testing.assert_array_equal(agg.embed_r_generalized.detach().numpy(),
+                                  torch.matmul(E.pinverse(), torch.from_numpy(f['V']).float()).numpy())
+    assert agg.V_embed.requires_grad and not agg.beta_vec.requires_grad and not agg.embed.embedding.weight.requires_grad
+    keep = ('S1', 'S2', 'C_output_mat', 'wildcard_mat', 'wildcard_output_vector', 'final_vector', 'start_vector')
+    m = r.FARNN_S_bert(V=f['V'], static_embed=f['pretrained_word_embed'], priority_mat=None, args=args, o_idx=0,
+                       is_cuda=False, **{k: f[k] for k in keep})
+    keys = set(m.state_dict())
+    assert {'embed.V_embed', 'embed.embed_r_generalized', 'embed.beta_vec', 'slot_filler.S1', 'slot_filler.S2',
+            'slot_filler.C_output_mat'} <= keys
+    args.use_bert = 1
+    with pytest.raises(ValueError, match='encoder'):
+        r.EmbedAggregator(args, f['V'], f['pretrained_word_embed'])
