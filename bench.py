@@ -25,6 +25,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'token positions/sec (decompose i-FST inference + Viterbi)'
 UNIT = 'tokens/s'
+METRIC_TRAIN = 'token positions/sec (decompose i-FST training step: fwd + CRF loss + bwd + grad all-reduce)'
 
 
 def parse():
@@ -376,7 +377,7 @@ def main():
         g2_ms = prof_ms[dom_cls] / max(prof_n[dom_cls], 1)
         achieved = dom_flops / (g2_ms * 1e-3) / 1e12 if g2_ms > 0 else 0.0
         line = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
+            'metric': METRIC if a.mode == 'infer' else METRIC_TRAIN, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': {'fp32': 'f32', 'bf16': 'bf16', 'tf32x3': 'tf32x3', 'fp16x3': 'fp16x3'}[prec], 'data': 'synthetic',
             'config': {'workload': '%s decompose i-FST %s (V=%d,C=%d,S=%d,R=%d,D=%d,len<=%d,B=%d per GPU)'
