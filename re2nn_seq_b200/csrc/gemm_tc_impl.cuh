@@ -1,10 +1,12 @@
 // tcgen05 step GEMM (sm_100a): TMA -> 128B-swizzled shared memory -> tcgen05.mma (accumulator in TMEM)
-// -> tcgen05.ld -> fused epilogue functor.  One 128 x BN output tile per CTA, warp-specialised:
+// -> tcgen05.ld -> fused epilogue functor.  Persistent, one 128 x bn output tile at a time per CTA, warp-specialised:
 //   warp 0      TMA producer (one elected lane), STAGES-deep mbarrier ring
 //   warp 1      TMEM allocator + MMA issuer (one elected lane)
-//   warps 2..5  epilogue: each warp owns the 32 TMEM lanes (rows) its warp-id quarter may access
-// Both operands are K-major (A: M x K, B: N x K, K contiguous), bf16 (kind::f16) or tf32 (kind::tf32);
-// TF32X3 runs three (A_hi,B_hi) / (A_lo,B_hi) / (A_hi,B_lo) segment passes into the same accumulator.
+//   warps 2..9  epilogue: two warps per TMEM lane quarter (a warp may only access the 32 lanes of warp-id % 4),
+//               alternating 32-column chunks of the accumulator
+// Both operands are K-major (A: M x K, B: N x K, K contiguous): bf16 or fp16 (kind::f16) or tf32 (kind::tf32).
+// The split formats keep a residual plane next to each operand plane: TF32X3 issues hi*hi, lo*hi, hi*lo into one
+// accumulator, FP16X3 sends the two residual products to a second accumulator that the epilogue folds in.
 // CG = 2 runs the same kernel on CTA pairs (thread-block clusters of two, cta_group::2): one 256 x bn tile per
 // pair, each CTA stages its own 128 A rows and HALF of the B rows, the leader CTA issues the MMAs for both and
 // every CTA keeps the accumulator of its own 128 rows in its own TMEM.  The L2 -> SM operand stream is what
