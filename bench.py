@@ -43,6 +43,7 @@ def parse():
     ap.add_argument('--cta-group', type=int, default=0, help='debug: force the tcgen05 CTA-group size (0 = cost model)')
     ap.add_argument('--resident', type=int, default=1, help='debug: 0 = one launch per step GEMM instead of the resident recurrence kernel')
     ap.add_argument('--backward-tc', type=int, default=1, help='debug: 0 = BPTT step GEMMs on fp32 CUDA cores')
+    ap.add_argument('--infer-chunks', type=int, default=4, help='streams the graphed inference body forks into (1 = single stream)')
     ap.add_argument('--cpu-sample', type=int, default=256, help='sequences in the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
@@ -219,6 +220,7 @@ def main():
     m = r.FARNN_S_D_W_I_S(args=args, o_idx=0, **f)
     with torch.no_grad():
         m.crf.transitions.copy_(torch.from_numpy(synth.crf_transitions(0, m.C)))
+    m.infer_chunks = a.infer_chunks
     m.precision = a.precision      # 'auto': parity-grade tensor-core mode (split fp16 / 3xTF32), fp32 without tcgen05
     with torch.no_grad():
         prec = m._resolved_precision()

@@ -132,7 +132,7 @@ class _DecomposeBase(nn.Module):
         return names
 
     # ---- decode (model_decompose.py:339-371) ------------------------------------------------------
-    def decode(self, all_scores, flattened_all_scores, mask, lengths, _shape=None, _offsets=None):
+    def decode(self, all_scores, flattened_all_scores, mask, lengths, _shape=None, _offsets=None, _flat_out=None):
         """all_scores B x L x C -> flat predictions N (int64).  `flattened_all_scores` and `mask`
         are accepted for signature compatibility; the kernels address valid positions directly."""
         with torch.no_grad():
@@ -145,10 +145,10 @@ class _DecomposeBase(nn.Module):
             if self.use_crf:
                 flat, _ = ops.crf_viterbi(sc, self.crf.transitions.detach(), lengths, offsets, N,
                                           clamp_col=self.C - 3 if ce1 else -1, threshold=self.args.threshold,
-                                          o_idx=self.o_idx, want_flat=True, want_padded=False)
+                                          o_idx=self.o_idx, want_flat=True, want_padded=False, flat_out=_flat_out)
             else:
                 flat, _ = ops.argmax_decode(sc, lengths, offsets, N, clamp_col=self.C - 1 if ce1 else -1,
-                                            threshold=self.args.threshold, o_idx=self.o_idx)
+                                            threshold=self.args.threshold, o_idx=self.o_idx, flat_out=_flat_out)
         return flat
 
     # ---- loss + decode tail shared by forward_local / forward (model_decompose_single.py:271-304) ---
@@ -167,7 +167,8 @@ class _DecomposeBase(nn.Module):
     # parameter version) with static buffers and replayed: one graph launch per batch.
     def _graph_key(self, B, Lpad, L, tag):
         vers = tuple((q.data_ptr(), q._version) for q in self.parameters())
-        return (tag, B, Lpad, L, self._resolved_precision(), bool(getattr(self, 'sort_by_length', True)), vers)
+        return (tag, B, Lpad, L, self._resolved_precision(), bool(getattr(self, 'sort_by_length', True)),
+                int(getattr(self, 'infer_chunks', 4)), vers)
 
     def _infer_body(self, inp, label, lengths, L):
         """Sync-free inference body: every shape is a function of (B, Lpad, L) only."""
@@ -181,9 +182,44 @@ class _DecomposeBase(nn.Module):
             inp = inp.index_select(0, order)
         else:
             offsets = offs0
-        scores = self._scores_from(inp, lengths, (L, nmax))
-        pred = self.decode(scores, None, None, lengths, _shape=(L, nmax), _offsets=offsets)
+        chunks = self._infer_chunks(B) if order is not None else None
+        if chunks is None:
+            scores = self._scores_from(inp, lengths, (L, nmax))
+            pred = self.decode(scores, None, None, lengths, _shape=(L, nmax), _offsets=offsets)
+            return pred, true
+        # Sequences are sorted longest-first, so the recurrence of a later chunk finishes earlier (its tiles stop at
+        # their own last step) and every row tile is independent: fork one stream per chunk.  Label scoring and
+        # Viterbi of the short chunks then run on the SMs their recurrence has already released while the longest
+        # chunk is still iterating; only the post-processing of the LAST chunk to finish stays on the critical path.
+        self._warm_tables()                                  # shared tables on the main stream, before the fork
+        pred = torch.empty((nmax,), dtype=torch.int64, device=lengths.device)
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        if not hasattr(self, '_chunk_streams') or len(self._chunk_streams) < len(chunks):
+            self._chunk_streams = [torch.cuda.Stream() for _ in chunks]
+        for st, (b0, b1) in zip(self._chunk_streams, chunks):
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                lc = lengths[b0:b1]
+                sc = self._scores_from(inp[b0:b1], lc, (L, nmax))
+                self.decode(sc, None, None, lc, _shape=(L, nmax), _offsets=offsets[b0:b1], _flat_out=pred)
+                done = torch.cuda.Event()
+                done.record(st)
+            main.wait_event(done)
         return pred, true
+
+    def _infer_chunks(self, B):
+        """[(b0, b1), ...] row ranges (multiples of the 128-row tile) for the multi-stream inference body, or None."""
+        n = int(getattr(self, 'infer_chunks', 4))
+        if n <= 1 or B < 256 * n:
+            return None
+        per = ((B + n - 1) // n + 127) // 128 * 128
+        return [(b0, min(B, b0 + per)) for b0 in range(0, B, per)]
+
+    def _warm_tables(self):
+        """Token / gate tables and the output-vector sum into the per-module cache (no-op for dense factors)."""
+        return None
 
     def _infer_graphed(self, inp, label, lengths, shape, tag):
         L, N = shape
@@ -333,6 +369,11 @@ class FARNN_S_D_W_I_S(_DecomposeBase):
 
     def _scores_from(self, inp, lengths, shape):
         return self.forward_scores(inp, lengths, shape)
+
+    def _warm_tables(self):
+        names, tensors = self._fn_params()
+        p = {n: t.detach().contiguous() for n, t in zip(names, tensors)}
+        autograd_fns._prepare(self._recurrence_consts(), p, None, self._cache)
 
     def forward_local(self, input, label, lengths, train=True, re_tags=None):
         dev = self._device()

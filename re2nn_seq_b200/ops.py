@@ -164,9 +164,12 @@ def label_scores(alpha, beta, lengths, C_mat, priority_mat=None, priority_bias=N
     return scores
 
 
-def argmax_decode(scores, lengths, offsets, n_flat, clamp_col, threshold, o_idx, want_flat=True, want_padded=False):
+def argmax_decode(scores, lengths, offsets, n_flat, clamp_col, threshold, o_idx, want_flat=True, want_padded=False,
+                  flat_out=None):
+    """flat_out: optional shared int64 buffer the flat predictions are scattered into (through `offsets`)."""
     B, L, Cn = scores.shape
-    flat = torch.empty((n_flat,), dtype=torch.int64, device=scores.device) if want_flat else None
+    flat = (flat_out if flat_out is not None else torch.empty((n_flat,), dtype=torch.int64, device=scores.device)) \
+        if want_flat else None
     padded = torch.empty((B, L), dtype=torch.int64, device=scores.device) if want_padded else None
     check(fn['re2nn_argmax_decode'](_f32(scores), _i64(lengths), _i64(offsets) if offsets is not None else None,
                                     B, L, Cn, clamp_col, float(threshold), int(o_idx),
@@ -177,10 +180,11 @@ def argmax_decode(scores, lengths, offsets, n_flat, clamp_col, threshold, o_idx,
 
 
 def crf_viterbi(feats, transitions, lengths, offsets=None, n_flat=0, clamp_col=-1, threshold=0.0, o_idx=0,
-                want_flat=False, want_padded=True):
+                want_flat=False, want_padded=True, flat_out=None):
     B, L, T = feats.shape
     dev = feats.device
-    flat = torch.empty((n_flat,), dtype=torch.int64, device=dev) if want_flat else None
+    flat = (flat_out if flat_out is not None else torch.empty((n_flat,), dtype=torch.int64, device=dev)) \
+        if want_flat else None
     padded = torch.empty((B, L), dtype=torch.int64, device=dev) if want_padded else None
     bp = torch.empty((B * L * T,), dtype=torch.int16, device=dev)
     check(fn['re2nn_crf_viterbi'](_f32(feats), _f32(transitions), _i64(lengths),
