@@ -146,3 +146,28 @@ def test_resident_gated_matches_per_step_and_oracle(B, S, R, L, farnn, prec):
     tol = 3e-2 if prec == 'bf16' else 1e-5
     assert rel_err(a, truth) < tol
     assert rel_err(b, truth) < tol
+
+
+@pytest.mark.parametrize('farnn,crf', [(0, 1), (2, 0)])
+def test_chunked_multi_stream_inference_matches_single_stream(farnn, crf):
+    """The graphed inference body forks one stream per chunk of the length-sorted batch (scoring + decode of the
+    short chunks overlap the recurrence of the longest): same predictions as the single-stream and eager paths."""
+    from test_gpu_parity import _random_decompose
+    _need_tc()
+    m, args, x, lens, lab = _random_decompose(17, 400, 96, 48, 14, 50, 1500, 11, farnn=farnn, use_crf=crf,
+                                              update_nonlinear='tanh', beta=0.1)
+    m.precision = 'fp16x3'
+    xt, lt, yt = _t(x), _t(lens), _t(lab)
+    out = {}
+    with torch.no_grad():
+        for chunks in (1, 4, 3):
+            m.infer_chunks = chunks
+            for _ in range(2):                       # capture, then replay
+                _, pred, true = m.forward_local(xt, yt, lt, train=False)
+            out[chunks] = (pred.clone(), true.clone())
+        m.use_cuda_graph = False
+        _, pred_e, true_e = m.forward_local(xt, yt, lt, train=False)
+    for chunks in (1, 4, 3):
+        assert torch.equal(out[chunks][0], pred_e), chunks
+        assert torch.equal(out[chunks][1], true_e), chunks
+    assert pred_e.shape[0] == int(lens.sum())
