@@ -158,7 +158,9 @@ class _DecomposeBase(nn.Module):
         the caller's order: flat predictions are scattered through the original offsets."""
         if not getattr(self, 'sort_by_length', True) or re_tags is not None or lengths.shape[0] <= 128:
             return None, None
-        _, order = torch.sort(lengths, descending=True, stable=True)
+        # 16-bit keys: the radix sort needs 2 passes instead of 8.  The order is only a scheduling heuristic (any
+        # permutation gives the same outputs), so lengths beyond int16 merely sort less usefully.
+        _, order = torch.sort(lengths.to(torch.int16), descending=True, stable=True)
         return order, exclusive_offsets(lengths).index_select(0, order)
 
     # ---- CUDA-graph replay of the inference path --------------------------------------------------------
