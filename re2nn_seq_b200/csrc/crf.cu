@@ -13,6 +13,7 @@
 namespace re2nn {
 
 constexpr int kCrfWarps = 8;
+constexpr int kCrfOverrun = 32 * 5;   // floats a register-blocked row sweep may read past the T x T table (ignored values)
 
 __device__ __forceinline__ float clamped_feat(const float* f, int j, int clamp_col, float thr) {
   float v = __ldg(f + j);
@@ -28,7 +29,7 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_viterbi_kernel(
   extern __shared__ float smem[];
   const int Tp = (T + 31) & ~31;
   float* s_trans = smem;
-  float* s_part = smem + (TS ? T * T : 0);
+  float* s_part = smem + (TS ? T * T + kCrfOverrun : 0);   // pad: the row-overrun reads below never touch live words
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (TS) {
     for (int i = threadIdx.x; i < T * T; i += blockDim.x) s_trans[i] = trans_g[i];
@@ -59,8 +60,8 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_viterbi_kernel(
         best[q] = -INFINITY;
         bi[q] = 0;
       }
-      // lanes whose last slot falls past T read (and ignore) the following shared-memory words: the loop stays
-      // warp-uniform and the transitions are followed by the partition buffers, so the reads are in bounds
+      // lanes whose last slot falls past T read (and ignore) the padding words that follow the table (kCrfOverrun):
+      // the loop stays warp-uniform and never touches another warp's live partition buffers
 #pragma unroll 5
       for (int i = 0; i < T; ++i) {
         const float p = pa[i];
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_nll_exp_kernel(
   const int Tp = (T + 31) & ~31;
   float* tr = smem;
   float* te = tr + T * T;
-  float* cmax = te + T * T;
+  float* cmax = te + T * T + kCrfOverrun;     // pad: the row-overrun reads of the sweep never touch live words
   float* s_part = cmax + Tp;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < T * T; i += blockDim.x) tr[i] = trans_g[i];
@@ -657,7 +658,7 @@ int re2nn_crf_viterbi(const float* feats, const float* transitions, const int64_
   RE2NN_CHECK(!flat_pred || offsets, "crf_viterbi: flat output needs offsets");
   const int Tp = (T + 31) & ~31;
   const size_t part = (size_t)kCrfWarps * 2 * Tp * 4;
-  const size_t with_tr = part + (size_t)T * T * 4;
+  const size_t with_tr = part + ((size_t)T * T + kCrfOverrun) * 4;
   const int grid = cdiv(B, kCrfWarps);
   cudaStream_t st = (cudaStream_t)stream;
 #define RE2NN_VIT(NJ)                                                                                              \
@@ -696,7 +697,7 @@ int re2nn_crf_nll(const float* feats, const float* transitions, const int64_t* l
   const size_t with_tr = part + (size_t)T * T * 4;
   const int grid = cdiv(B, kCrfWarps);
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t exp_smem = ((size_t)2 * T * T + Tp + (size_t)kCrfWarps * 3 * Tp) * 4 + 32 * 4 * 5;   // + overrun slack
+  const size_t exp_smem = ((size_t)2 * T * T + kCrfOverrun + Tp + (size_t)kCrfWarps * 3 * Tp) * 4;
   if (exp_smem <= kSmemLimit && T <= 160) {
 #define RE2NN_NLL(NJ)                                                                                              \
   do {                                                                                                             \
