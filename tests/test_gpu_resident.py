@@ -171,3 +171,34 @@ def test_chunked_multi_stream_inference_matches_single_stream(farnn, crf):
         assert torch.equal(out[chunks][0], pred_e), chunks
         assert torch.equal(out[chunks][1], true_e), chunks
     assert pred_e.shape[0] == int(lens.sum())
+
+
+def test_chunked_multi_stream_inference_precomputed_factors():
+    """FARNN_S_SF (dense B x L x R input) through the chunked, graphed inference body."""
+    import re2nn_seq_b200 as r
+    from re2nn_seq_b200 import synth
+    _need_tc()
+    S, R, C, B, L = 96, 48, 11, 1300, 9
+    args = synth.make_args(farnn=0, use_crf=1, update_nonlinear='tanh', beta=0.1)
+    f = synth.make_decompose_factors(6, 300, S, R, C, 50, dtype=np.float32)
+    keep = ('S1', 'S2', 'C_output_mat', 'wildcard_mat', 'wildcard_output_vector', 'final_vector', 'start_vector')
+    torch.manual_seed(2)
+    m = r.FARNN_S_SF(args=args, o_idx=0, is_cuda=True, priority_mat=None, **{k: f[k] for k in keep}).cuda()
+    with torch.no_grad():
+        m.crf.transitions.copy_(torch.from_numpy(synth.crf_transitions(6, m.C)))
+    m.precision = 'fp16x3'
+    rs = np.random.RandomState(7)
+    v = _t((rs.randn(B, L, R) * 0.3).astype(np.float32))
+    lens = rs.randint(2, L + 1, size=B).astype(np.int64)
+    lens[0] = L
+    lt, yt = _t(lens), _t(rs.randint(0, C, size=(B, L)).astype(np.int64))
+    out = {}
+    with torch.no_grad():
+        for chunks in (1, 4):
+            m.infer_chunks = chunks
+            for _ in range(2):
+                _, pred, true = m(v, yt, lt, train=False)
+            out[chunks] = pred.clone()
+        m.use_cuda_graph = False
+        _, pred_e, _ = m(v, yt, lt, train=False)
+    assert torch.equal(out[1], pred_e) and torch.equal(out[4], pred_e)
