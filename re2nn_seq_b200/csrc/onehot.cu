@@ -18,6 +18,15 @@ __device__ __forceinline__ float tw(const float* __restrict__ T, const float* __
   return W ? __ldg(T + i) + __ldg(W + i) : __ldg(T + i);
 }
 
+__device__ __forceinline__ float4 tw4(const float* __restrict__ T, const float* __restrict__ W, size_t i) {
+  float4 t = __ldg(reinterpret_cast<const float4*>(T + i));
+  if (W) {
+    const float4 w = __ldg(reinterpret_cast<const float4*>(W + i));
+    t.x += w.x; t.y += w.y; t.z += w.z; t.w += w.w;
+  }
+  return t;
+}
+
 // sum[v][s][j] = language[v][s][j] + W[s][j]   (model_onehot.py:366, hoisted: once per parameter version)
 __global__ void onehot_sum_kernel(const float* __restrict__ lang, const float* __restrict__ W, size_t n_slice,
                                   size_t total, float* __restrict__ out) {
@@ -28,6 +37,19 @@ __global__ void onehot_sum_kernel(const float* __restrict__ lang, const float* _
 template <bool MAXP>
 __device__ __forceinline__ float comb(float acc, float h, float t) {
   return MAXP ? fmaxf(acc, h * t) : fmaf(h, t, acc);
+}
+
+template <bool MAXP>
+__device__ __forceinline__ float4 comb4(float4 acc, float h, float4 t) {
+  acc.x = comb<MAXP>(acc.x, h, t.x); acc.y = comb<MAXP>(acc.y, h, t.y);
+  acc.z = comb<MAXP>(acc.z, h, t.z); acc.w = comb<MAXP>(acc.w, h, t.w);
+  return acc;
+}
+template <bool MAXP>
+__device__ __forceinline__ float dot4(float acc, float4 h, float4 t) {
+  acc = comb<MAXP>(acc, h.x, t.x); acc = comb<MAXP>(acc, h.y, t.y);
+  acc = comb<MAXP>(acc, h.z, t.z); acc = comb<MAXP>(acc, h.w, t.w);
+  return acc;
 }
 
 template <bool MAXP>
@@ -43,6 +65,8 @@ __global__ void __launch_bounds__(kOhThreads) onehot_recurrence_kernel(const re2
   const float* __restrict__ o = a.o;
   float* out = z == 0 ? a.alpha : a.beta;
   const float init = MAXP ? -INFINITY : 0.f;
+  // 16-byte path: rows start 16-byte aligned when S % 4 == 0 (cudaMalloc bases are 256-byte aligned)
+  const bool vec4 = (S & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.language) | reinterpret_cast<uintptr_t>(W)) & 15) == 0;
 
   for (int s = tid; s < S; s += kOhThreads) {
     float v = z == 0 ? a.h0[s] : a.hT[s];
@@ -61,7 +85,40 @@ __global__ void __launch_bounds__(kOhThreads) onehot_recurrence_kernel(const re2
     if (!alive) break;   // block-uniform
     const int64_t tok = a.x[(size_t)b * a.Lpad + tpos];
     const float* __restrict__ T = a.language + (size_t)tok * S * S;
-    if (z == 0) {
+    if (z == 0 && vec4) {
+      // 16-byte loads, four rows in flight per lane: a CTA is one (sequence, direction), so at small batch the
+      // bytes in flight per SM decide the speed (8 KB with scalar loads = ~9 GB/s per SM).  Every column keeps the
+      // accumulation order of the scalar path (rows s = warp, warp + 16, ...; then warps in order): same bits.
+      for (int jb = 0; jb < S; jb += 128) {
+        const int j = jb + 4 * lane;
+        if (j < S) {
+          float4 acc = make_float4(init, init, init, init);
+          int s = warp;
+          for (; s + 3 * kOhWarps < S; s += 4 * kOhWarps) {
+            const float4 t0 = tw4(T, W, (size_t)s * S + j);
+            const float4 t1 = tw4(T, W, (size_t)(s + kOhWarps) * S + j);
+            const float4 t2 = tw4(T, W, (size_t)(s + 2 * kOhWarps) * S + j);
+            const float4 t3 = tw4(T, W, (size_t)(s + 3 * kOhWarps) * S + j);
+            acc = comb4<MAXP>(acc, h[s], t0);
+            acc = comb4<MAXP>(acc, h[s + kOhWarps], t1);
+            acc = comb4<MAXP>(acc, h[s + 2 * kOhWarps], t2);
+            acc = comb4<MAXP>(acc, h[s + 3 * kOhWarps], t3);
+          }
+          for (; s < S; s += kOhWarps) acc = comb4<MAXP>(acc, h[s], tw4(T, W, (size_t)s * S + j));
+          *reinterpret_cast<float4*>(part + warp * S + j) = acc;
+        }
+      }
+      __syncthreads();
+      for (int j = tid; j < S; j += kOhThreads) {
+        float acc = init;
+#pragma unroll
+        for (int w = 0; w < kOhWarps; ++w) acc = MAXP ? fmaxf(acc, part[w * S + j]) : acc + part[w * S + j];
+        float v = apply_nl(acc * o[j], a.update_nonlinear);
+        h[j] = v;
+        if (orow >= 0) out[((size_t)b * a.L + orow) * S + j] = v;
+      }
+      __syncthreads();
+    } else if (z == 0) {
       // out[j] = (+|max)_s h[s] * (T[s][j] + W[s][j]); warps stride over rows s, lanes over columns j
       for (int jb = 0; jb < S; jb += 32) {
         const int j = jb + lane;
@@ -91,6 +148,45 @@ __global__ void __launch_bounds__(kOhThreads) onehot_recurrence_kernel(const re2
         float v = apply_nl(acc * o[j], a.update_nonlinear);
         h[j] = v;
         if (orow >= 0) out[((size_t)b * a.L + orow) * S + j] = v;
+      }
+      __syncthreads();
+    } else if (vec4) {
+      // out[s] = (+|max)_j h[j] * (T[s][j] + W[s][j]); a warp takes two rows at a time, lanes take 4 columns per load
+      float* hn = part;   // S
+      for (int s = warp; s < S; s += 2 * kOhWarps) {
+        const int s1 = s + kOhWarps;
+        const bool two = s1 < S;
+        const float* __restrict__ Tr0 = T + (size_t)s * S;
+        const float* __restrict__ Tr1 = T + (size_t)(two ? s1 : s) * S;
+        const float* __restrict__ Wr0 = W ? W + (size_t)s * S : nullptr;
+        const float* __restrict__ Wr1 = W ? W + (size_t)(two ? s1 : s) * S : nullptr;
+        float acc0 = init, acc1 = init;
+        for (int j = 4 * lane; j < S; j += 256) {
+          const bool more = j + 128 < S;
+          const float4 a0 = tw4(Tr0, Wr0, j), b0 = tw4(Tr1, Wr1, j);
+          const float4 a1 = more ? tw4(Tr0, Wr0, j + 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 b1 = more ? tw4(Tr1, Wr1, j + 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 hv = *reinterpret_cast<const float4*>(h + j);
+          acc0 = dot4<MAXP>(acc0, hv, a0);
+          acc1 = dot4<MAXP>(acc1, hv, b0);
+          if (more) {
+            const float4 hw = *reinterpret_cast<const float4*>(h + j + 128);
+            acc0 = dot4<MAXP>(acc0, hw, a1);
+            acc1 = dot4<MAXP>(acc1, hw, b1);
+          }
+        }
+        acc0 = MAXP ? warp_max(acc0) : warp_sum(acc0);
+        acc1 = MAXP ? warp_max(acc1) : warp_sum(acc1);
+        if (lane == 0) {
+          hn[s] = acc0;
+          if (two) hn[s1] = acc1;
+        }
+      }
+      __syncthreads();
+      for (int s = tid; s < S; s += kOhThreads) {
+        float v = apply_nl(hn[s], a.update_nonlinear);
+        if (orow >= 0) out[((size_t)b * a.L + orow) * S + s] = v;
+        h[s] = v * o[s];
       }
       __syncthreads();
     } else {
