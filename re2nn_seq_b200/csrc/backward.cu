@@ -166,24 +166,46 @@ static cudaError_t run_tn(const TnProblem& prob, float* partial, float* out, int
   return cudaGetLastError();
 }
 
-// deterministic column sums: out[c] (+)= sum_r X[r, c]; one CTA per 32 columns, 32 x 32 threads
+// deterministic column sums: out[c] (+)= sum_r X[r, c].  grid (column blocks of 32, row splits): every CTA sums its
+// contiguous row range for 32 columns (32 x 32 threads, fixed order); with more than one split the partials go to
+// `part[split][c]` and colsum_finish_kernel adds them in split order, so the result does not depend on scheduling.
 __global__ void __launch_bounds__(1024) colsum_rows_kernel(const float* __restrict__ X, size_t rows, int cols, int ld,
-                                                           float* __restrict__ out, int accumulate) {
+                                                           float* __restrict__ out, int accumulate,
+                                                           float* __restrict__ part) {
   __shared__ float sh[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
+  const size_t per = (rows + gridDim.y - 1) / gridDim.y;
+  const size_t r0 = (size_t)blockIdx.y * per, r1 = r0 + per < rows ? r0 + per : rows;
   float acc = 0.f;
   if (c < cols)
-    for (size_t r = threadIdx.y; r < rows; r += 32) acc += X[r * ld + c];
+    for (size_t r = r0 + threadIdx.y; r < r1; r += 32) acc += X[r * ld + c];
   sh[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.y == 0 && c < cols) {
-    float t = accumulate ? out[c] : 0.f;
+    float t = (part == nullptr && accumulate) ? out[c] : 0.f;
     for (int i = 0; i < 32; ++i) t += sh[i][threadIdx.x];
-    out[c] = t;
+    if (part) part[(size_t)blockIdx.y * cols + c] = t;
+    else out[c] = t;
   }
 }
-static cudaError_t colsum_rows(const float* X, size_t rows, int cols, int ld, float* out, int accumulate, cudaStream_t st) {
-  colsum_rows_kernel<<<cdiv(cols, 32), dim3(32, 32), 0, st>>>(X, rows, cols, ld, out, accumulate);
+__global__ void colsum_finish_kernel(const float* __restrict__ part, int nsplit, int cols, float* __restrict__ out,
+                                     int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float t = accumulate ? out[c] : 0.f;
+  for (int i = 0; i < nsplit; ++i) t += part[(size_t)i * cols + c];
+  out[c] = t;
+}
+// ws: optional scratch of at least 64 * cols floats; tall inputs are then split over up to 64 CTAs per column block
+static cudaError_t colsum_rows(const float* X, size_t rows, int cols, int ld, float* out, int accumulate, cudaStream_t st,
+                               float* ws = nullptr) {
+  const int nsplit = ws ? (int)std::min<size_t>(64, (rows + 2047) / 2048) : 1;
+  if (nsplit <= 1) {
+    colsum_rows_kernel<<<dim3(cdiv(cols, 32), 1), dim3(32, 32), 0, st>>>(X, rows, cols, ld, out, accumulate, nullptr);
+    return cudaGetLastError();
+  }
+  colsum_rows_kernel<<<dim3(cdiv(cols, 32), nsplit), dim3(32, 32), 0, st>>>(X, rows, cols, ld, out, accumulate, ws);
+  colsum_finish_kernel<<<cdiv(cols, 256), 256, 0, st>>>(ws, nsplit, cols, out, accumulate);
   return cudaGetLastError();
 }
 
@@ -643,8 +665,8 @@ static int run_backward(const re2nn_backward_args& a, cudaStream_t st) {
       t.pair[0] = TnPair{a.vtab, c.dgtab + S, R, gw, (size_t)a.table_rows};
       RE2NN_CUDA(run_tn(t, partial, a.dWrs2, 0, YLoadPlain{}, st));
     }
-    if (a.dbs1) RE2NN_CUDA(colsum_rows(c.dgtab, a.table_rows, S, gw, a.dbs1, 0, st));
-    if (a.farnn == 2 && a.dbs2) RE2NN_CUDA(colsum_rows(c.dgtab + S, a.table_rows, S, gw, a.dbs2, 0, st));
+    if (a.dbs1) RE2NN_CUDA(colsum_rows(c.dgtab, a.table_rows, S, gw, a.dbs1, 0, st, partial));
+    if (a.farnn == 2 && a.dbs2) RE2NN_CUDA(colsum_rows(c.dgtab + S, a.table_rows, S, gw, a.dbs2, 0, st, partial));
     memset(&g, 0, sizeof(g));
     g.M = a.table_rows; g.N = R; g.nseg = a.farnn; g.ndir = 1;
     g.seg[0][0] = GemmSeg{c.dgtab, a.Wrs1, gw, S, S, 1, 0, 0};
@@ -652,14 +674,14 @@ static int run_backward(const re2nn_backward_args& a, cudaStream_t st) {
     RE2NN_CUDA(launch_simt_gemm(g, EpiStore2{{a.dvtab, a.dvtab}, R, 1}, ALoadPlain{}, st));
   }
   // 5. vector gradients
-  if (a.d_o) RE2NN_CUDA(colsum_rows(c.DOprod, (size_t)2 * rows1, S, S, a.d_o, 0, st));
+  if (a.d_o) RE2NN_CUDA(colsum_rows(c.DOprod, (size_t)2 * rows1, S, S, a.d_o, 0, st, partial));
   if (a.dh0) {
     RE2NN_CUDA(colsum_rows(c.g, B, S, S, a.dh0, 0, st));
-    if (a.farnn == 2) RE2NN_CUDA(colsum_rows(c.Pinit, rows1, S, S, a.dh0, 1, st));
+    if (a.farnn == 2) RE2NN_CUDA(colsum_rows(c.Pinit, rows1, S, S, a.dh0, 1, st, partial));
   }
   if (a.dhT) {
     RE2NN_CUDA(colsum_rows(c.g + (size_t)B * S, B, S, S, a.dhT, 0, st));
-    if (a.farnn == 2) RE2NN_CUDA(colsum_rows(c.Pinit + rows1 * S, rows1, S, S, a.dhT, 1, st));
+    if (a.farnn == 2) RE2NN_CUDA(colsum_rows(c.Pinit + rows1 * S, rows1, S, S, a.dhT, 1, st, partial));
     bwd_direct_hT_kernel<<<cdiv(S, 128), 128, 0, st>>>(dbeta, a.lengths, B, L, S, a.dhT);
     RE2NN_LAUNCH_CHECK();
   }
