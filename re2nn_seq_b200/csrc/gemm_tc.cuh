@@ -1,7 +1,5 @@
 // Weight preparation for the step GEMMs + the tcgen05 (5th-gen tensor core) mainloop.
 #pragma once
-#include <algorithm>
-
 #include "gemm_common.cuh"
 
 namespace re2nn {
@@ -92,22 +90,6 @@ __global__ void convert_weight_kernel(const float* src, int N, int K, int ld_src
   }
 }
 
-// All weight copies of one recurrence call in ONE launch (blockIdx.y = job): the conversions sit at the head of every
-// call, in front of the recurrence kernel, so eight 2-us launches were ~14 us of pure latency per call.
-struct ConvertJob { const float* src; void* dst; int N, K, ld_src, transpose, ldk, n_off; size_t plane; };
-struct ConvertBatch { ConvertJob job[8]; int njobs; };
-template <int PREC>
-__global__ void convert_weights_kernel(const ConvertBatch b) {
-  const ConvertJob j = b.job[blockIdx.y];
-  const size_t total = (size_t)j.N * j.ldk;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int n = (int)(i / j.ldk), k = (int)(i % j.ldk);
-    float v = 0.f;
-    if (k < j.K) v = j.transpose ? j.src[(size_t)k * j.ld_src + n] : j.src[(size_t)n * j.ld_src + k];
-    OperandFmt<PREC>::store(j.dst, (size_t)(n + j.n_off) * j.ldk + k, j.plane, v);
-  }
-}
-
 template <int PREC>
 inline int weight_prep_run(const re2nn_recurrence_args& a, WeightPrep& w, cudaStream_t st) {
   const int S = a.S, R = a.R;
@@ -124,30 +106,28 @@ inline int weight_prep_run(const re2nn_recurrence_args& a, WeightPrep& w, cudaSt
     }
     return 0;
   }
-  ConvertBatch cb;
-  memset(&cb, 0, sizeof(cb));
-  size_t most = 0;
-  auto conv = [&](const float* src, int N, int K, int ld_src, int tr, void* dst, int ldk, size_t plane, int n_off) {
-    cb.job[cb.njobs++] = ConvertJob{src, dst, N, K, ld_src, tr, ldk, n_off, plane};
-    most = std::max(most, (size_t)N * ldk);
+  auto conv = [&](const float* src, int N, int K, int ld_src, int tr, void* dst, int ldk, size_t plane,
+                  int n_off) -> cudaError_t {
+    size_t total = (size_t)N * ldk;
+    int blocks = (int)((total + 255) / 256);
+    convert_weight_kernel<PREC><<<blocks, 256, 0, st>>>(src, N, K, ld_src, tr, dst, ldk, plane, n_off);
+    return cudaGetLastError();
   };
   const size_t pl_g1 = w.pl_g1, pl_g2q = w.pl_g2q, pl_ss = w.pl_ss, pl_gate = w.pl_gate;
-  conv(a.S1, R, S, R, 1, w.buf[0], w.ldS, pl_g1, 0);   // [R][S] = S1^T
-  conv(a.S2, R, S, R, 1, w.buf[1], w.ldS, pl_g1, 0);
-  conv(a.S2, S, R, R, 0, w.buf[2], w.ldR, pl_g2q, 0);  // [S][R] = S2
-  conv(a.S1, S, R, R, 0, w.buf[3], w.ldR, pl_g2q, 0);
-  conv(a.W, S, S, S, 1, w.buf[4], w.ldS, pl_ss, 0);    // fwd: B[k=s][n=j] = W[s][j] -> [n][k] = W^T
-  conv(a.W, S, S, S, 0, w.buf[5], w.ldS, pl_ss, 0);    // bwd: B[k][n] = W[n][k]   -> [n][k] = W
-  if (a.farnn >= 1) {
-    conv(a.Wss1, S, S, S, 1, w.buf[6], w.ldS, pl_gate, 0);
-    if (a.farnn == 2) conv(a.Wss2, S, S, S, 1, w.buf[6], w.ldS, pl_gate, S);
-  }
-  convert_weights_kernel<PREC><<<dim3((unsigned)std::min<size_t>((most + 255) / 256, 1024), cb.njobs), 256, 0, st>>>(cb);
-  RE2NN_LAUNCH_CHECK();
+  RE2NN_CUDA(conv(a.S1, R, S, R, 1, w.buf[0], w.ldS, pl_g1, 0));   // [R][S] = S1^T
+  RE2NN_CUDA(conv(a.S2, R, S, R, 1, w.buf[1], w.ldS, pl_g1, 0));
+  RE2NN_CUDA(conv(a.S2, S, R, R, 0, w.buf[2], w.ldR, pl_g2q, 0));  // [S][R] = S2
+  RE2NN_CUDA(conv(a.S1, S, R, R, 0, w.buf[3], w.ldR, pl_g2q, 0));
+  RE2NN_CUDA(conv(a.W, S, S, S, 1, w.buf[4], w.ldS, pl_ss, 0));    // fwd: B[k=s][n=j] = W[s][j] -> [n][k] = W^T
+  RE2NN_CUDA(conv(a.W, S, S, S, 0, w.buf[5], w.ldS, pl_ss, 0));    // bwd: B[k][n] = W[n][k]   -> [n][k] = W
   w.g1[0] = w.buf[0]; w.g1[1] = w.buf[1];
   w.g2q[0] = w.buf[2]; w.g2q[1] = w.buf[3];
   w.g2w[0] = w.buf[4]; w.g2w[1] = w.buf[5];
-  if (a.farnn >= 1) w.gate = w.buf[6];
+  if (a.farnn >= 1) {
+    RE2NN_CUDA(conv(a.Wss1, S, S, S, 1, w.buf[6], w.ldS, pl_gate, 0));
+    if (a.farnn == 2) RE2NN_CUDA(conv(a.Wss2, S, S, S, 1, w.buf[6], w.ldS, pl_gate, S));
+    w.gate = w.buf[6];
+  }
   return 0;
 }
 

@@ -473,7 +473,7 @@ int re2nn_decompose_recurrence_launches(const re2nn_recurrence_args* a) {
   if (!a) return -1;
   int n = 2;                                                     // tile_last + rec_init
   if (a->precision == RE2NN_PREC_FP32) n += a->farnn == 2 ? 1 : 0;   // [Wss1 | Wss2] concat
-  else n += 1;                                                   // operand-format copies of the weights (one launch)
+  else n += 6 + a->farnn;                                        // operand-format copies of the weights
   n += takes_resident_path(*a) ? 1 : a->L * (2 + (a->farnn >= 1 ? 1 : 0));
   return n;
 }
