@@ -149,6 +149,9 @@ int re2nn_decompose_recurrence(const re2nn_recurrence_args* a, void* stream);
 /* Number of kernels re2nn_decompose_recurrence launches for this argument block (inference without gates on the
  * tensor-core paths runs ALL steps in one resident kernel; otherwise 2-3 step GEMMs per step). */
 int re2nn_decompose_recurrence_launches(const re2nn_recurrence_args* a);
+/* 1 when the call would take the resident single-launch path (only precision, S, R, farnn and save_for_backward of
+ * the block are read): callers use it to decide whether splitting a batch over streams pays off. */
+int re2nn_decompose_recurrence_resident(const re2nn_recurrence_args* a);
 
 /* Same recurrence under the max-product semiring (train_mode == 'max': model_decompose_single.py:159-166,
  * utils.py:192-195).  Takes the same argument block (precision ignored: fp32; save_for_backward must be 0);

@@ -95,6 +95,7 @@ SYMBOLS = {
     're2nn_output_vector_sum': (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),
     're2nn_decompose_recurrence_workspace': (sz, [C.POINTER(RecurrenceArgs)]),
     're2nn_decompose_recurrence_launches': (C.c_int, [C.POINTER(RecurrenceArgs)]),
+    're2nn_decompose_recurrence_resident': (C.c_int, [C.POINTER(RecurrenceArgs)]),
     're2nn_decompose_recurrence': (C.c_int, [C.POINTER(RecurrenceArgs), vp]),
     're2nn_decompose_backward_workspace': (sz, [C.POINTER(BackwardArgs)]),
     're2nn_decompose_backward': (C.c_int, [C.POINTER(BackwardArgs), vp]),

@@ -469,6 +469,11 @@ static bool takes_resident_path(const re2nn_recurrence_args& a) {
   return resident_supported(planes, a.S, a.R, a.precision != RE2NN_PREC_BF16);
 }
 
+int re2nn_decompose_recurrence_resident(const re2nn_recurrence_args* a) {
+  if (!a) return 0;
+  return takes_resident_path(*a) ? 1 : 0;
+}
+
 int re2nn_decompose_recurrence_launches(const re2nn_recurrence_args* a) {
   if (!a) return -1;
   int n = 2;                                                     // tile_last + rec_init

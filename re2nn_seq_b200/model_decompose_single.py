@@ -216,6 +216,11 @@ class _DecomposeBase(nn.Module):
         n = int(getattr(self, 'infer_chunks', 4))
         if n <= 1 or B < 256 * n:
             return None
+        # only the resident recurrence kernel leaves SMs idle as its short tiles finish; with one launch per step GEMM
+        # (large S / R) the chunks would just compete for the machine (measured: cfg5 shapes 10.0 -> 12.2 ms)
+        S, R = self.S1.shape
+        if not ops.recurrence_is_resident(S, R, self.args.farnn, self._resolved_precision()):
+            return None
         per = ((B + n - 1) // n + 127) // 128 * 128
         return [(b0, min(B, b0 + per)) for b0 in range(0, B, per)]
 

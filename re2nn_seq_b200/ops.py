@@ -243,6 +243,13 @@ def profile_enable(on):
     check(fn['re2nn_profile_enable'](int(on)), 'profile_enable')
 
 
+def recurrence_is_resident(S, R, farnn, precision):
+    """Would an inference call of this shape run all steps in the resident kernel?"""
+    a = RecurrenceArgs()
+    a.S, a.R, a.farnn, a.precision, a.save_for_backward = S, R, farnn, PREC[precision], 0
+    return bool(fn['re2nn_decompose_recurrence_resident'](C.byref(a)))
+
+
 def profile_read():
     """-> ([ms_gate, ms_gemm1, ms_gemm2, ms_resident], [n_gate, n_gemm1, n_gemm2, n_resident]) since the last read."""
     ms = (C.c_double * 4)()
