@@ -214,6 +214,8 @@ class _DecomposeBase(nn.Module):
     def _infer_chunks(self, B):
         """[(b0, b1), ...] row ranges (multiples of the 128-row tile) for the multi-stream inference body, or None."""
         n = int(getattr(self, 'infer_chunks', 4))
+        if self.args.farnn >= 1:
+            n = min(n, 2)        # gated steps are bound by L2 traffic of the state / gate arrays: measured best with 1-2 chunks
         if n <= 1 or B < 256 * n:
             return None
         # only the resident recurrence kernel leaves SMs idle as its short tiles finish; with one launch per step GEMM
