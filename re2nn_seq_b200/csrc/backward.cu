@@ -474,7 +474,7 @@ static size_t bwd_carve(const re2nn_backward_args& a, char* base, BwdCtx* c, flo
   return off;
 }
 
-static int grid_for(size_t total) { return (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 16); }
+static int grid_for(size_t total) { return (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 16); }
 
 static int run_backward(const re2nn_backward_args& a, cudaStream_t st) {
   BwdCtx c;

@@ -28,6 +28,34 @@ int set_error(const char* fmt, ...);
 #define RE2NN_LAUNCH_CHECK() RE2NN_CUDA(cudaGetLastError())
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---- per-device launch facts (a process may drive several GPUs; nothing here is a process-wide constant) ----
+constexpr int kMaxDevices = 64;
+inline int device_slot() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
+  return d % kMaxDevices;
+}
+inline int sm_count() {
+  static int cache[kMaxDevices];      // 0 = not queried yet; a racing second query writes the same value
+  const int d = device_slot();
+  if (cache[d] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || n <= 0) n = 148;
+    cache[d] = n;
+  }
+  return cache[d];
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: `done` is the caller's
+// per-kernel array of the largest size already configured on each device.
+template <class Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes, int (&done)[kMaxDevices]) {
+  const int d = device_slot();
+  if (done[d] >= bytes) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done[d] = bytes;
+  return e;
+}
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- nonlinearities ---------------------------------------------------------------------------

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const GemmProblem prob, 
 template <class Epi, class ALoad>
 inline cudaError_t launch_simt_gemm(const GemmProblem& prob, const Epi& epi, const ALoad& aload, cudaStream_t st) {
   const long ctas128 = (long)cdiv(prob.M, 128) * cdiv(prob.N, 64) * prob.ndir;
-  if (ctas128 >= 148) {
+  if (ctas128 >= sm_count()) {
     dim3 grid(cdiv(prob.M, 128), cdiv(prob.N, 64), prob.ndir);
     simt_gemm_kernel<128, Epi, ALoad><<<grid, 256, 0, st>>>(prob, epi, aload);
   } else {

@@ -88,7 +88,7 @@ inline void tc_pick_shape(int M, int N, int ndir, int planes, int mmas, int* bn_
   for (int cg = 1; cg <= 2; ++cg) {
     if (g_tc_force_cg && cg != g_tc_force_cg) continue;
     const long mt = (long)cdiv(M, 128 * cg) * ndir;
-    const long slots = 148 / cg;
+    const long slots = sm_count() / cg;
     for (int nt = 1; nt <= cdiv(N, 16); ++nt) {
       int bn = ((cdiv(N, nt) + 15) / 16) * 16;
       if (bn > 256) continue;
@@ -683,14 +683,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
 template <int PREC, int BN, int CG, class Epi>
 inline cudaError_t launch_tc_bn(const TcLaunch& L, const Epi& epi, cudaStream_t st) {
   using Cfg = TcCfg<PREC, BN, CG>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<PREC, BN, CG, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static int configured[kMaxDevices];
+  if (cudaError_t e = ensure_dynamic_smem(tc_gemm_kernel<PREC, BN, CG, Epi>, Cfg::kSmem, configured)) return e;
   const long tiles = (long)cdiv(L.M, 128 * CG) * cdiv(L.N, L.bn) * L.ndir;
-  const int grid = (int)std::min<long>(tiles, 148 / CG) * CG;   // one persistent CTA (pair) per SM (pair)
+  const int grid = (int)std::min<long>(tiles, sm_count() / CG) * CG;   // one persistent CTA (pair) per SM (pair)
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);

@@ -316,7 +316,7 @@ using namespace re2nn;
 extern "C" int re2nn_onehot_sum_tensor(const float* language, const float* W, int V1, int S, float* out, void* stream) {
   RE2NN_CHECK(language && W && out && V1 > 0 && S > 0, "onehot_sum_tensor: bad arguments");
   const size_t total = (size_t)V1 * S * S;
-  onehot_sum_kernel<<<148 * 16, 256, 0, (cudaStream_t)stream>>>(language, W, (size_t)S * S, total, out);
+  onehot_sum_kernel<<<sm_count() * 16, 256, 0, (cudaStream_t)stream>>>(language, W, (size_t)S * S, total, out);
   RE2NN_LAUNCH_CHECK();
   return 0;
 }

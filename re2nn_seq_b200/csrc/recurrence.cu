@@ -159,7 +159,7 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
   {
     size_t total = (size_t)2 * B * S;
     int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
     rec_init_kernel<PREC><<<blocks, 256, 0, st>>>(B, L, S, a.farnn, a.lengths, a.h0, a.hT, a.o, w, ldh, h_plane, a.beta,
                                                   a.save_for_backward ? a.hst_save : nullptr,
                                                   a.save_for_backward ? a.hbar_save : nullptr);

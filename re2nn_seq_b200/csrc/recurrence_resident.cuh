@@ -343,16 +343,12 @@ inline bool resident_supported(int planes, int S, int R, bool q_first) {
 template <int PREC, int NL, int FARNN>
 inline cudaError_t launch_resident(const ResidentLaunch& RL, const StepParams& p, int B, cudaStream_t st) {
   const int smem = resident_smem_bytes(OperandFmt<PREC>::kPlanes, RL.stages, RL.stage_bytes, RL.q_first != 0);
-  static int configured = 0;
-  if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(tc_resident_kernel<PREC, NL, FARNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  static int configured[kMaxDevices];
+  if (cudaError_t e = ensure_dynamic_smem(tc_resident_kernel<PREC, NL, FARNN>, smem, configured)) return e;
   const long tiles = 2L * cdiv(B, 128);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)(std::min<long>(tiles, 74) * 2));   // one CTA pair per SM pair
+  cfg.gridDim = dim3((unsigned)(std::min<long>(tiles, sm_count() / 2) * 2));   // one CTA pair per SM pair
   cfg.blockDim = dim3(64 + 32 * resident_epi_warps(FARNN));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
