@@ -75,6 +75,14 @@ int re2nn_debug_set_tc_cta_group(int cta_group);
  * (a CTA pair per 128-row tile iterates over all steps); 0 = one launch per step GEMM. */
 int re2nn_debug_set_resident(int on);
 int re2nn_profile_read(double* ms_out_host, int64_t* count_out_host);
+/* Per-launch [start, end] of kernel class `cls` in ms relative to the earliest start of the class, for up to
+ * `cap` launches recorded since the last clearing read.  The event pairs also work inside stream capture (they
+ * become external event nodes; every graph replay re-records them), so the timed configuration itself -- CUDA
+ * graph, forked chunk streams -- can be measured: pass clear = 0 to keep the pairs registered across replays.
+ * re2nn_profile_count: launches currently registered for the class.  re2nn_profile_enabled: current switch. */
+int re2nn_profile_intervals(int cls, double* start_ms_host, double* end_ms_host, int cap, int clear);
+int re2nn_profile_count(int cls);
+int re2nn_profile_enabled(void);
 
 /* ---- stand-alone GEMM through the step-GEMM mainloops (unit-test / calibration entry) -------------------
  * C[M x N] = A[M x K] @ B[N x K]^T, A/B/C fp32 row-major.  precision selects the mainloop:
@@ -272,11 +280,15 @@ int re2nn_flatten_i64(const int64_t* padded, const int64_t* lengths, const int64
  * (model_decompose.py:349-359).  feats B x L x T (T = tagset+2), transitions T x T.
  * padded_path reproduces the reference's B x L output bit for bit (pads 0, last column = final
  * pointer); flat_pred additionally applies the clamp_col -> o_idx remap.  Either may be NULL.
- * bp_ws: B*L*T uint16 scratch. */
+ * part_ws: B*L*T fp32 scratch (the partition history; back-pointers on the best path are recomputed from it).
+ * Sequences of length 0 produce no tags (their padded row is zero); lengths are clamped to L. */
 int re2nn_crf_viterbi(const float* feats, const float* transitions, const int64_t* lengths,
                       const int64_t* offsets, int B, int L, int T, int clamp_col, float threshold,
-                      int64_t o_idx, int64_t* padded_path, int64_t* flat_pred, uint16_t* bp_ws,
+                      int64_t o_idx, int64_t* padded_path, int64_t* flat_pred, float* part_ws,
                       void* stream);
+
+/* debug / calibration: sequences one warp of the Viterbi sweep decodes together (0 = pick by batch size; 1, 2, 4). */
+int re2nn_debug_set_viterbi_seqs(int ns);
 
 /* ---- CRF negative log-likelihood ---------------------------------------------------------------------
  * replaces CRF.neg_log_likelihood_loss = _calculate_PZ - _score_sentence (baselines/crf.py:48-99,

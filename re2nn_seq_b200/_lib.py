@@ -87,7 +87,11 @@ SYMBOLS = {
     're2nn_debug_set_tc_cta_group': (C.c_int, [C.c_int]),
     're2nn_debug_set_resident': (C.c_int, [C.c_int]),
     're2nn_debug_set_backward_tc': (C.c_int, [C.c_int]),
+    're2nn_debug_set_viterbi_seqs': (C.c_int, [C.c_int]),
     're2nn_profile_read': (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    're2nn_profile_intervals': (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int]),
+    're2nn_profile_count': (C.c_int, [C.c_int]),
+    're2nn_profile_enabled': (C.c_int, []),
     're2nn_gemm_nt_workspace': (sz, [C.c_int, C.c_int, C.c_int, C.c_int]),
     're2nn_gemm_nt': (C.c_int, [C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, sz, vp]),
     're2nn_token_table': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),

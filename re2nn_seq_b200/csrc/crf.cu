@@ -20,114 +20,272 @@ __device__ __forceinline__ float clamped_feat(const float* f, int j, int clamp_c
   return (j == clamp_col) ? fminf(v, thr) : v;
 }
 
-// dynamic smem: [TS ? T*T : 0] transitions, then kCrfWarps * 2 * Tp partitions
-template <bool TS, int NJ>
+// ---- Viterbi (crf.py:102-195) ----------------------------------------------------------------------------------
+// The sweep is issue-bound (T^2 candidate scores per position), so it keeps only what the result needs:
+//   forward:   part_t[j] = max_i ((feat_t[j] + trans[i][j]) + part_{t-1}[i])      -- the reference's rounding order,
+//              maxima only (max is exact in any order): per four source tags one LDS.128 of the TRANSPOSED
+//              transition table, four packed adds (add.f32x2) and two three-input maxima per target tag;
+//              every part_t is written to a history buffer instead of back-pointers;
+//   backtrace: only the pointers ON the best path are ever read (crf.py:189-192), so each one is recomputed from
+//              the stored partition: argmax_i ((feat_t[ptr] + trans[i][ptr]) + part_{t-1}[i]) with the same
+//              expression bit for bit and the first maximal index (torch.max) -- T operations per position
+//              instead of a T^2 compare/select sweep.
+__device__ __forceinline__ unsigned long long pack_f32x2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float max3_of(float m, unsigned long long v) {
+  float a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(m) : "f"(m), "f"(a), "f"(b));
+  return m;
+}
+// row pitch of the transposed table: a multiple of 4 words whose quarter is odd, so the 16-byte reads of eight
+// consecutive target tags fall into distinct bank groups
+__host__ __device__ inline int viterbi_pitch(int T) {
+  int q = (T + 3) / 4;
+  if ((q & 1) == 0) ++q;
+  return 4 * q;
+}
+
+// dynamic smem: trT[T][Tq] (trT[j][i] = trans[i][j], source tags i >= T hold -inf), then kCrfWarps * NS * 2 * Tq
+// partitions.  One warp sweeps NS neighbouring sequences together: every transition value read from shared memory
+// (the binding resource once the compare/select sweep is gone: each candidate needs its own 4-byte trans[i][j])
+// serves NS candidates.  The inference path hands over length-sorted batches, so the NS sequences end within a
+// step or two of each other; a finished sequence keeps computing (unobserved) values and stops storing.
+template <int NJ, int NS>
 __global__ void __launch_bounds__(kCrfWarps * 32) crf_viterbi_kernel(
     const float* __restrict__ feats, const float* __restrict__ trans_g, const int64_t* __restrict__ len,
     const int64_t* __restrict__ offsets, int B, int L, int T, int clamp_col, float thr, int64_t o_idx,
-    int64_t* __restrict__ padded, int64_t* __restrict__ flat, uint16_t* __restrict__ bp) {
-  extern __shared__ float smem[];
-  const int Tp = (T + 31) & ~31;
-  float* s_trans = smem;
-  float* s_part = smem + (TS ? T * T + kCrfOverrun : 0);   // pad: the row-overrun reads below never touch live words
+    int64_t* __restrict__ padded, int64_t* __restrict__ flat, float* hist) {
+  extern __shared__ __align__(16) float smem[];
+  const int Tq = viterbi_pitch(T);
+  float* trT = smem;
+  float* s_part = smem + (size_t)T * Tq;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (TS) {
-    for (int i = threadIdx.x; i < T * T; i += blockDim.x) s_trans[i] = trans_g[i];
-    __syncthreads();
+  for (int e = threadIdx.x; e < T * Tq; e += blockDim.x) {
+    const int j = e / Tq, i = e - j * Tq;
+    trT[e] = i < T ? trans_g[i * T + j] : -INFINITY;
   }
-  const float* tr = TS ? s_trans : trans_g;
-  const int b = blockIdx.x * kCrfWarps + warp;
-  if (b >= B) return;
-  const int n = (int)len[b];
-  float* pa = s_part + warp * 2 * Tp;
-  float* pb = pa + Tp;
-  const float* fb = feats + (size_t)b * L * T;
-  uint16_t* bpb = bp + (size_t)b * L * T;
+  for (int e = threadIdx.x; e < kCrfWarps * NS * 2 * Tq; e += blockDim.x) s_part[e] = 0.f;   // pad source slots stay 0
+  __syncthreads();
+  const int b0 = (blockIdx.x * kCrfWarps + warp) * NS;
+  if (b0 >= B) return;
+  constexpr int NQ = NJ > 0 ? NJ : 1;
+  int n[NS];
+  int nmax = 0;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    n[s] = b0 + s < B ? min((int)len[b0 + s], L) : 0;
+    nmax = max(nmax, n[s]);
+  }
+  float* pa = s_part + warp * NS * 2 * Tq;      // [s][Tq] current, then [s][Tq] next
+  float* pb = pa + NS * Tq;
+  const size_t seq = (size_t)L * T;
+  const float* fb = feats + (size_t)b0 * seq;
+  float* hb = hist + (size_t)b0 * seq;
 
-  for (int j = lane; j < T; j += 32) pa[j] = clamped_feat(fb, j, clamp_col, thr) + tr[(T - 2) * T + j];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    if (n[s] > 0)
+      for (int j = lane; j < T; j += 32) {
+        const float v = clamped_feat(fb + s * seq, j, clamp_col, thr) + trT[j * Tq + (T - 2)];
+        pa[s * Tq + j] = v;
+        hb[s * seq + j] = v;
+      }
+  }
   __syncwarp();
   if (NJ > 0) {
-    // register-blocked: lane owns target tags j = lane + 32*q (q < NJ); one pass over the source tags i shares the
-    // partition load and keeps NJ independent max/argmax chains in flight
-    for (int t = 1; t < n; ++t) {
-      const float* ft = fb + (size_t)t * T;
-      float f[NJ > 0 ? NJ : 1], best[NJ > 0 ? NJ : 1];
-      int bi[NJ > 0 ? NJ : 1];
+    // lane owns target tags j = lane + 32 q; slots past T re-read the last row and drop the result
+    const float* rowp[NQ];
+    float fnext[NS][NQ];
 #pragma unroll
-      for (int q = 0; q < NJ; ++q) {
-        const int j = lane + 32 * q;
-        f[q] = j < T ? clamped_feat(ft, j, clamp_col, thr) : 0.f;
-        best[q] = -INFINITY;
-        bi[q] = 0;
-      }
-      // lanes whose last slot falls past T read (and ignore) the padding words that follow the table (kCrfOverrun):
-      // the loop stays warp-uniform and never touches another warp's live partition buffers
-#pragma unroll 5
-      for (int i = 0; i < T; ++i) {
-        const float p = pa[i];
-        const float* tri = tr + i * T + lane;
+    for (int q = 0; q < NQ; ++q) {
+      const int j = min(lane + 32 * q, T - 1);
+      rowp[q] = trT + j * Tq;
 #pragma unroll
-        for (int q = 0; q < NJ; ++q) {
-          const float v = (f[q] + tri[32 * q]) + p;
-          if (v > best[q]) { best[q] = v; bi[q] = i; }
+      for (int s = 0; s < NS; ++s) fnext[s][q] = n[s] > 1 ? clamped_feat(fb + s * seq + T, j, clamp_col, thr) : 0.f;
+    }
+    for (int t = 1; t < nmax; ++t) {
+      unsigned long long ff[NS][NQ];
+      float best[NS][NQ];
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          ff[s][q] = pack_f32x2(fnext[s][q], fnext[s][q]);
+          best[s][q] = -INFINITY;
+        }
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+        if (t + 1 < n[s]) {      // next position's features in flight during this sweep
+#pragma unroll
+          for (int q = 0; q < NQ; ++q)
+            fnext[s][q] = clamped_feat(fb + s * seq + (size_t)(t + 1) * T, min(lane + 32 * q, T - 1), clamp_col, thr);
+        }
+#pragma unroll 1
+      for (int i0 = 0; i0 < Tq; i0 += 4) {
+        unsigned long long p01[NS], p23[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const float4 p4 = *reinterpret_cast<const float4*>(pa + s * Tq + i0);
+          p01[s] = pack_f32x2(p4.x, p4.y);
+          p23[s] = pack_f32x2(p4.z, p4.w);
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const float4 t4 = *reinterpret_cast<const float4*>(rowp[q] + i0);
+          const unsigned long long t01 = pack_f32x2(t4.x, t4.y), t23 = pack_f32x2(t4.z, t4.w);
+#pragma unroll
+          for (int s = 0; s < NS; ++s) {
+            const unsigned long long v01 = add_f32x2(add_f32x2(ff[s][q], t01), p01[s]);
+            const unsigned long long v23 = add_f32x2(add_f32x2(ff[s][q], t23), p23[s]);
+            best[s][q] = max3_of(max3_of(best[s][q], v01), v23);
+          }
         }
       }
 #pragma unroll
-      for (int q = 0; q < NJ; ++q) {
-        const int j = lane + 32 * q;
-        if (j < T) {
-          pb[j] = best[q];
-          bpb[(size_t)t * T + j] = (uint16_t)bi[q];
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int j = lane + 32 * q;
+          if (j < T) {
+            pb[s * Tq + j] = best[s][q];
+            if (t < n[s]) hb[s * seq + (size_t)t * T + j] = best[s][q];
+          }
         }
-      }
       __syncwarp();
       float* tmp = pa; pa = pb; pb = tmp;
     }
   } else {
-    for (int t = 1; t < n; ++t) {
-      const float* ft = fb + (size_t)t * T;
-      for (int j = lane; j < T; j += 32) {
-        const float f = clamped_feat(ft, j, clamp_col, thr);
-        float best = -INFINITY;
-        int bi = 0;
-        for (int i = 0; i < T; ++i) {
-          float v = (f + tr[i * T + j]) + pa[i];
-          if (v > best) { best = v; bi = i; }
+    for (int t = 1; t < nmax; ++t) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        if (t >= n[s]) continue;
+        const float* ft = fb + s * seq + (size_t)t * T;
+        for (int j = lane; j < T; j += 32) {
+          const float f = clamped_feat(ft, j, clamp_col, thr);
+          const float* row = trT + j * Tq;
+          float best = -INFINITY;
+          for (int i = 0; i < T; ++i) best = fmaxf(best, (f + row[i]) + pa[s * Tq + i]);
+          pb[s * Tq + j] = best;
+          hb[s * seq + (size_t)t * T + j] = best;
         }
-        pb[j] = best;
-        bpb[(size_t)t * T + j] = (uint16_t)bi;
       }
       __syncwarp();
       float* tmp = pa; pa = pb; pb = tmp;
     }
   }
-  // transition into STOP: pointer = argmax_i (part_i + trans[i][STOP])
-  float best = -INFINITY;
-  int bi = 0x7fffffff;
-  for (int i = lane; i < T; i += 32) {
-    float v = pa[i] + tr[i * T + (T - 1)];
-    if (v > best) { best = v; bi = i; }
-  }
-  if (bi == 0x7fffffff) bi = lane;   // all -inf in this lane: keep order so lane 0 / index 0 wins ties
-  warp_argmax_first(best, bi);
-  if (best == -INFINITY) bi = 0;
   __syncwarp();
-  if (lane == 0) {
-    int ptr = bi;
+  // first maximal source tag over i of (f + trans[i][j]) + part[i]  (with_f)  or  part[i] + trans[i][j]  (STOP step,
+  // crf.py:166-175), all lanes cooperating (torch.max tie-break)
+  auto best_source = [&](const float* part, float f, int j, bool with_f) -> int {
+    const float* row = trT + j * Tq;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = lane; i < T; i += 32) {
+      const float v = with_f ? (f + row[i]) + part[i] : part[i] + row[i];
+      if (v > best) { best = v; bi = i; }
+    }
+    if (bi == 0x7fffffff) bi = lane;   // nothing above -inf in this lane: keep order so index 0 wins a full tie
+    warp_argmax_first(best, bi);
+    if (best == -INFINITY) bi = 0;
+    return bi;
+  };
+#pragma unroll 1
+  for (int s = 0; s < NS; ++s) {
+    const int b = b0 + s;
+    if (b >= B) break;
+    const int ns = n[s];
+    if (ns <= 0) {   // empty sequence: no tags; the padded row is all zeros like the reference's masked back-pointers
+      if (padded)
+        for (int t = lane; t < L; t += 32) padded[(size_t)b * L + t] = 0;
+      continue;
+    }
+    const float* fs = fb + s * seq;
+    const float* hs = hb + s * seq;      // written by this warp (ordered by __syncwarp)
+    int ptr = best_source(hs + (size_t)(ns - 1) * T, 0.f, T - 1, false);
     const int64_t off = offsets ? offsets[b] : 0;
     auto emit = [&](int t, int tag) {
-      if (padded) padded[(size_t)b * L + t] = tag;
-      if (flat) flat[off + t] = (tag == clamp_col) ? o_idx : (int64_t)tag;
+      if (lane == 0) {
+        if (padded) padded[(size_t)b * L + t] = tag;
+        if (flat) flat[off + t] = (tag == clamp_col) ? o_idx : (int64_t)tag;
+      }
     };
-    if (padded) {   // reference leaves pads at 0 and the final pointer in the last column
-      for (int t = n; t < L - 1; ++t) padded[(size_t)b * L + t] = 0;
-      if (n < L) padded[(size_t)b * L + (L - 1)] = ptr;
+    if (padded && lane == 0) {   // reference leaves pads at 0 and the final pointer in the last column
+      for (int t = ns; t < L - 1; ++t) padded[(size_t)b * L + t] = 0;
+      if (ns < L) padded[(size_t)b * L + (L - 1)] = ptr;
     }
-    emit(n - 1, ptr);
-    for (int t = n - 1; t >= 1; --t) {
-      ptr = bpb[(size_t)t * T + ptr];
+    emit(ns - 1, ptr);
+    for (int t = ns - 1; t >= 1; --t) {
+      ptr = best_source(hs + (size_t)(t - 1) * T, clamped_feat(fs + (size_t)t * T, ptr, clamp_col, thr), ptr, true);
       emit(t - 1, ptr);
     }
+  }
+}
+
+// transitions too large for shared memory: same algorithm straight from global memory
+__global__ void __launch_bounds__(kCrfWarps * 32) crf_viterbi_global_kernel(
+    const float* __restrict__ feats, const float* __restrict__ tr, const int64_t* __restrict__ len,
+    const int64_t* __restrict__ offsets, int B, int L, int T, int clamp_col, float thr, int64_t o_idx,
+    int64_t* __restrict__ padded, int64_t* __restrict__ flat, float* hist) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kCrfWarps + warp;
+  if (b >= B) return;
+  const int n = min((int)len[b], L);
+  if (n <= 0) {
+    if (padded)
+      for (int t = lane; t < L; t += 32) padded[(size_t)b * L + t] = 0;
+    return;
+  }
+  const float* fb = feats + (size_t)b * L * T;
+  float* hb = hist + (size_t)b * L * T;
+  for (int j = lane; j < T; j += 32) hb[j] = clamped_feat(fb, j, clamp_col, thr) + tr[(T - 2) * T + j];
+  __syncwarp();
+  for (int t = 1; t < n; ++t) {
+    const float* pa = hb + (size_t)(t - 1) * T;
+    for (int j = lane; j < T; j += 32) {
+      const float f = clamped_feat(fb + (size_t)t * T, j, clamp_col, thr);
+      float best = -INFINITY;
+      for (int i = 0; i < T; ++i) best = fmaxf(best, (f + tr[i * T + j]) + pa[i]);
+      hb[(size_t)t * T + j] = best;
+    }
+    __syncwarp();
+  }
+  auto first_max = [&](const float* part, float f, int j, bool with_f) -> int {
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = lane; i < T; i += 32) {
+      const float v = with_f ? (f + tr[i * T + j]) + part[i] : part[i] + tr[i * T + j];
+      if (v > best) { best = v; bi = i; }
+    }
+    if (bi == 0x7fffffff) bi = lane;
+    warp_argmax_first(best, bi);
+    if (best == -INFINITY) bi = 0;
+    return bi;
+  };
+  int ptr = first_max(hb + (size_t)(n - 1) * T, 0.f, T - 1, false);
+  const int64_t off = offsets ? offsets[b] : 0;
+  auto emit = [&](int t, int tag) {
+    if (lane == 0) {
+      if (padded) padded[(size_t)b * L + t] = tag;
+      if (flat) flat[off + t] = (tag == clamp_col) ? o_idx : (int64_t)tag;
+    }
+  };
+  if (padded && lane == 0) {
+    for (int t = n; t < L - 1; ++t) padded[(size_t)b * L + t] = 0;
+    if (n < L) padded[(size_t)b * L + (L - 1)] = ptr;
+  }
+  emit(n - 1, ptr);
+  for (int t = n - 1; t >= 1; --t) {
+    ptr = first_max(hb + (size_t)(t - 1) * T, clamped_feat(fb + (size_t)t * T, ptr, clamp_col, thr), ptr, true);
+    emit(t - 1, ptr);
   }
 }
 
@@ -650,41 +808,59 @@ int re2nn_flatten_i64(const int64_t* padded, const int64_t* lengths, const int64
   return 0;
 }
 
+static int g_viterbi_ns = 0;      // debug: sequences per warp (0 = default)
+
 int re2nn_crf_viterbi(const float* feats, const float* transitions, const int64_t* lengths, const int64_t* offsets,
                       int B, int L, int T, int clamp_col, float threshold, int64_t o_idx, int64_t* padded_path,
-                      int64_t* flat_pred, uint16_t* bp_ws, void* stream) {
-  RE2NN_CHECK(feats && transitions && lengths && bp_ws, "crf_viterbi: null tensor");
+                      int64_t* flat_pred, float* part_ws, void* stream) {
+  RE2NN_CHECK(feats && transitions && lengths && part_ws, "crf_viterbi: null tensor");
   RE2NN_CHECK(B > 0 && L > 0 && T >= 3 && T <= 65535, "crf_viterbi: bad dims B=%d L=%d T=%d", B, L, T);
   RE2NN_CHECK(!flat_pred || offsets, "crf_viterbi: flat output needs offsets");
-  const int Tp = (T + 31) & ~31;
-  const size_t part = (size_t)kCrfWarps * 2 * Tp * 4;
-  const size_t with_tr = part + ((size_t)T * T + kCrfOverrun) * 4;
-  const int grid = cdiv(B, kCrfWarps);
+  const int Tq = viterbi_pitch(T);
   cudaStream_t st = (cudaStream_t)stream;
-#define RE2NN_VIT(NJ)                                                                                              \
+  // sequences per warp: two halve the shared-memory reads of the transition table per candidate (measured at T = 131,
+  // B = 16384: 3.7 -> 2.9 ms; four run out of registers: 4.3 ms), as long as the batch still fills the machine with
+  // warps (cfg2, B = 4096: one sequence per warp is fastest, 0.18 vs 0.20 ms)
+  int ns = g_viterbi_ns ? g_viterbi_ns : (B >= sm_count() * kCrfWarps * 8 ? 2 : 1);
+  if (cdiv(T, 32) > 5) ns = 1;
+#define RE2NN_VIT(NJ, NS)                                                                                          \
   do {                                                                                                             \
-    RE2NN_CUDA(cudaFuncSetAttribute(crf_viterbi_kernel<true, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                    (int)with_tr));                                                                \
-    crf_viterbi_kernel<true, NJ><<<grid, kCrfWarps * 32, with_tr, st>>>(feats, transitions, lengths, offsets, B, L, \
-                                                                        T, clamp_col, threshold, o_idx,            \
-                                                                        padded_path, flat_pred, bp_ws);            \
+    static int configured[kMaxDevices];                                                                            \
+    const size_t smem = ((size_t)T * Tq + (size_t)kCrfWarps * NS * 2 * Tq) * 4;                                    \
+    RE2NN_CUDA(ensure_dynamic_smem(crf_viterbi_kernel<NJ, NS>, (int)smem, configured));                            \
+    crf_viterbi_kernel<NJ, NS><<<cdiv(B, kCrfWarps * NS), kCrfWarps * 32, smem, st>>>(                             \
+        feats, transitions, lengths, offsets, B, L, T, clamp_col, threshold, o_idx, padded_path, flat_pred, part_ws); \
   } while (0)
-  if (with_tr <= kSmemLimit) {
+#define RE2NN_VIT_NS(NJ)                                     \
+  do {                                                       \
+    if (ns == 4) RE2NN_VIT(NJ, 4);                           \
+    else if (ns == 2) RE2NN_VIT(NJ, 2);                      \
+    else RE2NN_VIT(NJ, 1);                                   \
+  } while (0)
+  const size_t smem_max = ((size_t)T * Tq + (size_t)kCrfWarps * ns * 2 * Tq) * 4;
+  if (smem_max <= kSmemLimit) {
     switch (cdiv(T, 32)) {
-      case 1: RE2NN_VIT(1); break;
-      case 2: RE2NN_VIT(2); break;
-      case 3: RE2NN_VIT(3); break;
-      case 4: RE2NN_VIT(4); break;
-      case 5: RE2NN_VIT(5); break;
-      default: RE2NN_VIT(0); break;
+      case 1: RE2NN_VIT_NS(1); break;
+      case 2: RE2NN_VIT_NS(2); break;
+      case 3: RE2NN_VIT_NS(3); break;
+      case 4: RE2NN_VIT_NS(4); break;
+      case 5: RE2NN_VIT_NS(5); break;
+      default: RE2NN_VIT(0, 1); break;
     }
   } else {
-    crf_viterbi_kernel<false, 0><<<grid, kCrfWarps * 32, part, st>>>(feats, transitions, lengths, offsets, B, L, T,
-                                                                     clamp_col, threshold, o_idx, padded_path,
-                                                                     flat_pred, bp_ws);
+    crf_viterbi_global_kernel<<<cdiv(B, kCrfWarps), kCrfWarps * 32, 0, st>>>(feats, transitions, lengths, offsets, B, L, T,
+                                                                             clamp_col, threshold, o_idx, padded_path,
+                                                                             flat_pred, part_ws);
   }
 #undef RE2NN_VIT
+#undef RE2NN_VIT_NS
   RE2NN_LAUNCH_CHECK();
+  return 0;
+}
+
+int re2nn_debug_set_viterbi_seqs(int ns) {
+  RE2NN_CHECK(ns == 0 || ns == 1 || ns == 2 || ns == 4, "debug_set_viterbi_seqs: expected 0, 1, 2 or 4");
+  g_viterbi_ns = ns;
   return 0;
 }
 

@@ -109,10 +109,21 @@ struct ProfPair { cudaEvent_t a, b; };
 static bool g_resident_on = true;    // inference, farnn = 0: run the whole recurrence in one resident launch
 static bool g_prof_on = false;
 static std::vector<ProfPair> g_prof_pool;        // all event pairs ever created
-static std::vector<int> g_prof_used[4];          // indices into the pool, per kernel class (3 = resident recurrence)          // indices into the pool, per kernel class
+static std::vector<int> g_prof_used[4];          // indices into the pool, per kernel class (3 = resident recurrence)
+static std::vector<char> g_prof_captured;        // per pool entry: recorded inside stream capture (external event nodes)
 static size_t g_prof_next = 0;
 static std::mutex g_prof_mu;
 
+// Works inside stream capture too: the pair is recorded as EXTERNAL event nodes, so every replay of the captured
+// graph re-records the same two events and re2nn_profile_intervals() reads the launch as it ran inside the graph.
+static bool prof_capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive;
+}
+static cudaError_t prof_record(cudaEvent_t ev, cudaStream_t st) {
+  if (prof_capturing(st)) return cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal);
+  return cudaEventRecord(ev, st);
+}
 static int prof_begin(int cls, cudaStream_t st) {
   if (!g_prof_on) return -1;
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -120,14 +131,28 @@ static int prof_begin(int cls, cudaStream_t st) {
     ProfPair p;
     if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return -1;
     g_prof_pool.push_back(p);
+    g_prof_captured.push_back(0);
   }
   int idx = (int)g_prof_next++;
+  g_prof_captured[idx] = prof_capturing(st) ? 1 : 0;
   g_prof_used[cls].push_back(idx);
-  cudaEventRecord(g_prof_pool[idx].a, st);
+  prof_record(g_prof_pool[idx].a, st);
   return idx;
 }
 static void prof_end(int idx, cudaStream_t st) {
-  if (idx >= 0) cudaEventRecord(g_prof_pool[idx].b, st);
+  if (idx >= 0) prof_record(g_prof_pool[idx].b, st);
+}
+
+// Launches whose events are current: once a graph has been captured only its (re-recorded) pairs are; the eager
+// and warm-up launches registered before the capture are stale.
+static std::vector<int> prof_live(int cls) {
+  std::vector<int> live;
+  bool any_captured = false;
+  for (int c = 0; c < 4; ++c)
+    for (int idx : g_prof_used[c]) any_captured = any_captured || g_prof_captured[idx];
+  for (int idx : g_prof_used[cls])
+    if (!any_captured || g_prof_captured[idx]) live.push_back(idx);
+  return live;
 }
 
 template <int PREC, class Epi>
@@ -455,6 +480,40 @@ int re2nn_profile_read(double* ms_out_host, int64_t* count_out_host) {
   g_prof_next = 0;
   return 0;
 }
+// Per-launch intervals of one kernel class since the last clearing read, in ms relative to the earliest start of
+// that class (launches on forked streams overlap: the caller takes the union).  clear = 0 keeps the event pairs
+// registered, which is what a captured graph needs: its replays re-record the same events.
+int re2nn_profile_intervals(int cls, double* start_ms, double* end_ms, int cap, int clear) {
+  RE2NN_CHECK(cls >= 0 && cls < 4 && start_ms && end_ms && cap >= 0, "profile_intervals: bad arguments");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  const std::vector<int> used = prof_live(cls);
+  const int n = (int)std::min<size_t>(used.size(), (size_t)cap);
+  for (int i = 0; i < n; ++i) RE2NN_CUDA(cudaEventSynchronize(g_prof_pool[used[i]].b));
+  int first = 0;
+  for (int i = 1; i < n; ++i) {      // earliest start: the one no other start precedes
+    float d = 0.f;
+    RE2NN_CUDA(cudaEventElapsedTime(&d, g_prof_pool[used[first]].a, g_prof_pool[used[i]].a));
+    if (d < 0.f) first = i;
+  }
+  for (int i = 0; i < n; ++i) {
+    float s0 = 0.f, s1 = 0.f;
+    RE2NN_CUDA(cudaEventElapsedTime(&s0, g_prof_pool[used[first]].a, g_prof_pool[used[i]].a));
+    RE2NN_CUDA(cudaEventElapsedTime(&s1, g_prof_pool[used[first]].a, g_prof_pool[used[i]].b));
+    start_ms[i] = s0;
+    end_ms[i] = s1;
+  }
+  if (clear) {
+    for (int c = 0; c < 4; ++c) g_prof_used[c].clear();
+    g_prof_next = 0;
+  }
+  return 0;
+}
+int re2nn_profile_count(int cls) {
+  if (cls < 0 || cls >= 4) return 0;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  return (int)prof_live(cls).size();
+}
+int re2nn_profile_enabled(void) { return g_prof_on ? 1 : 0; }
 const char* re2nn_last_error(void) { return re2nn::g_err; }
 
 size_t re2nn_decompose_recurrence_workspace(const re2nn_recurrence_args* a) {

@@ -170,7 +170,7 @@ class _DecomposeBase(nn.Module):
     def _graph_key(self, B, Lpad, L, tag):
         vers = tuple((q.data_ptr(), q._version) for q in self.parameters())
         return (tag, B, Lpad, L, self._resolved_precision(), bool(getattr(self, 'sort_by_length', True)),
-                int(getattr(self, 'infer_chunks', 4)), vers)
+                int(getattr(self, 'infer_chunks', 4)), ops.profile_enabled(), vers)
 
     def _infer_body(self, inp, label, lengths, L):
         """Sync-free inference body: every shape is a function of (B, Lpad, L) only."""
@@ -230,16 +230,68 @@ class _DecomposeBase(nn.Module):
         """Token / gate tables and the output-vector sum into the per-module cache (no-op for dense factors)."""
         return None
 
+    # Capture policy.  An evaluation sweep (val.py:7-43 runs train / dev / test after every epoch) sees a new
+    # (B, L) almost every batch and new parameter versions every epoch; capturing each of them would cost a warm-up
+    # forward + a capture forward + instantiation per batch and pin one private memory pool per capture.  So:
+    #   * a key is captured only when it is seen for the SECOND time (first sighting runs eagerly);
+    #   * entries are evicted least-recently-used, entries captured under other parameter versions first;
+    #   * the pools are capped by `graph_pool_bytes` (default 1/8 of the device memory).
+    _GRAPH_MAX_ENTRIES = 8
+
+    def invalidate_caches(self):
+        """Drop the token / gate / output-sum tables and every captured graph.  The caches are keyed on
+        (data_ptr, _version) of the parameters, which in-place writes through ``p.data`` (EMA, weight swaps, legacy
+        optimisers) do NOT bump -- call this after such writes.  Called automatically by train() / eval(),
+        load_state_dict() and .to() / .cuda()."""
+        if getattr(self, '_cache', None) is not None:
+            self._cache.clear()
+        self._graphs = {}
+        self._graph_seen = {}
+
+    def train(self, mode=True):
+        self.invalidate_caches()
+        return super().train(mode)
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate_caches()
+        return super()._apply(fn, *a, **k)
+
+    def _load_from_state_dict(self, *a, **k):
+        self.invalidate_caches()
+        return super()._load_from_state_dict(*a, **k)
+
+    def _graph_evict(self, need_bytes, vers):
+        cap = getattr(self, 'graph_pool_bytes', None)
+        if cap is None:
+            cap = torch.cuda.get_device_properties(self.S1.device).total_memory // 8
+        g = self._graphs
+        for k in [k for k, e in g.items() if e['vers'] != vers]:      # stale parameter versions can never hit again
+            del g[k]
+        def used():
+            return sum(e['bytes'] for e in g.values())
+        while g and (len(g) >= self._GRAPH_MAX_ENTRIES or used() + need_bytes > cap):
+            del g[min(g, key=lambda k: g[k]['tick'])]
+        return used() + need_bytes <= cap
+
     def _infer_graphed(self, inp, label, lengths, shape, tag):
         L, N = shape
         B, Lpad = lengths.shape[0], inp.shape[1]
         if not hasattr(self, '_graphs'):
-            self._graphs = {}
+            self._graphs, self._graph_seen = {}, {}
+        self._graph_tick = getattr(self, '_graph_tick', 0) + 1
         key = self._graph_key(B, Lpad, L, tag)
+        vers = key[-1]
         ent = self._graphs.get(key)
         if ent is None:
-            if len(self._graphs) >= 8:                      # parameter updates / new shapes: drop stale captures
-                self._graphs.clear()
+            seen = self._graph_seen.get(key, 0)
+            if len(self._graph_seen) > 256:
+                self._graph_seen.clear()
+            self._graph_seen[key] = seen + 1
+            S_full, C_full = self._S_full, self.C
+            est = B * L * (2 * S_full + 2 * C_full + 8) * 4 + B * Lpad * 16      # alpha, beta, scores, partition history
+            if seen == 0 or not self._graph_evict(est, vers):
+                pred, true = self._infer_body(inp, label.contiguous(), lengths, L)   # first sighting: eager
+                return None, pred[:N], true[:N]
             sx, sy, sl = inp.clone(), label.contiguous().clone(), lengths.clone()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -250,8 +302,9 @@ class _DecomposeBase(nn.Module):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 pred, true = self._infer_body(sx, sy, sl, L)
-            ent = dict(g=g, x=sx, y=sy, l=sl, pred=pred, true=true, launches=ops.launches() - l0)
+            ent = dict(g=g, x=sx, y=sy, l=sl, pred=pred, true=true, launches=ops.launches() - l0, bytes=est, vers=vers)
             self._graphs[key] = ent
+        ent['tick'] = self._graph_tick
         ent['x'].copy_(inp, non_blocking=True)
         ent['y'].copy_(label, non_blocking=True)
         ent['l'].copy_(lengths, non_blocking=True)

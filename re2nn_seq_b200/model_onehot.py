@@ -53,6 +53,24 @@ class FARNN_S_O_I_S(nn.Module):
             raise NotImplementedError("re2nn_b200: only the cross-entropy local losses are built (CE, CE1)")
         self.full_pad = False
 
+    def invalidate_caches(self):
+        """Drop the cached language + wildcard sum.  It is keyed on (data_ptr, _version), which in-place writes
+        through ``p.data`` do not bump -- call this after such writes.  Called automatically by train() / eval(),
+        load_state_dict() and .to() / .cuda()."""
+        self._sum_cache = {}
+
+    def train(self, mode=True):
+        self.invalidate_caches()
+        return super().train(mode)
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate_caches()
+        return super()._apply(fn, *a, **k)
+
+    def _load_from_state_dict(self, *a, **k):
+        self.invalidate_caches()
+        return super()._load_from_state_dict(*a, **k)
+
     def _device(self):
         ops.require_cuda()
         if not self.language_tensor.is_cuda:

@@ -74,6 +74,11 @@ def gate_table(vtab, Wrs1, bs1, Wrs2, bs2, farnn):
     return out
 
 
+def affine(x, W, b):
+    """x (M x K) @ W (K x N) + b (N): fp32 CUDA-core GEMM with the bias in the epilogue (priority.py:20-30)."""
+    return gate_table(x, W, b.reshape(1, -1).contiguous(), None, None, 1)
+
+
 def output_vector_sum(C_mat, wildcard_vec=None):
     Cn, S = C_mat.shape
     o = torch.empty((S,), dtype=torch.float32, device=C_mat.device)
@@ -186,7 +191,7 @@ def crf_viterbi(feats, transitions, lengths, offsets=None, n_flat=0, clamp_col=-
     flat = (flat_out if flat_out is not None else torch.empty((n_flat,), dtype=torch.int64, device=dev)) \
         if want_flat else None
     padded = torch.empty((B, L), dtype=torch.int64, device=dev) if want_padded else None
-    bp = torch.empty((B * L * T,), dtype=torch.int16, device=dev)
+    bp = torch.empty((B * L * T,), dtype=torch.float32, device=dev)     # partition history (no back-pointers)
     check(fn['re2nn_crf_viterbi'](_f32(feats), _f32(transitions), _i64(lengths),
                                   _i64(offsets) if offsets is not None else None, B, L, T, clamp_col,
                                   float(threshold), int(o_idx), _i64(padded) if padded is not None else None,
@@ -256,6 +261,20 @@ def profile_read():
     cnt = (C.c_int64 * 4)()
     check(fn['re2nn_profile_read'](ms, cnt), 'profile_read')
     return list(ms), list(cnt)
+
+
+def profile_enabled():
+    return bool(fn['re2nn_profile_enabled']())
+
+
+def profile_intervals(cls, clear=False):
+    """[(start_ms, end_ms), ...] of the launches of kernel class `cls` (3 = resident recurrence) as they last ran --
+    inside a replayed CUDA graph too.  Times are relative to the earliest start of the class."""
+    n = fn['re2nn_profile_count'](cls)
+    s = (C.c_double * max(n, 1))()
+    e = (C.c_double * max(n, 1))()
+    check(fn['re2nn_profile_intervals'](cls, s, e, n, int(clear)), 'profile_intervals')
+    return [(s[i], e[i]) for i in range(n)]
 
 
 def has_tcgen05():

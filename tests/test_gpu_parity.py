@@ -294,3 +294,37 @@ def test_crf_viterbi_large_batch(B, ntag):
     _, path = crf._viterbi_decode(_t(feats), _t(mask))
     want = orc.crf_viterbi(feats, mask, trans)
     np.testing.assert_array_equal(path.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize('B,ntag,L', [(700, 129, 12), (300, 198, 7), (90, 258, 6)])
+def test_crf_viterbi_wide_tagsets(B, ntag, L):
+    """T = 131 (cfg5: five target tags per lane), T = 200 (generic shared-memory sweep) and T = 260 (transition table
+    beyond shared memory: global-memory kernel), real-valued features with many exact ties, one empty sequence:
+    paths bit-exact against the restatement of crf.py:102-195."""
+    import re2nn_seq_b200 as r
+    rs = np.random.RandomState(ntag)
+    T = ntag + 2
+    feats = (rs.randint(-8, 9, size=(B, L, T)) * 0.25).astype(np.float32)
+    feats[::3] += rs.randn(*feats[::3].shape).astype(np.float32)
+    lens = rs.randint(1, L + 1, size=B).astype(np.int64)
+    lens[0] = L
+    trans = (rs.randint(-4, 5, size=(T, T)) * 0.5).astype(np.float32)
+    trans[:, T - 2] = -10000.0
+    trans[T - 1, :] = -10000.0
+    crf = r.CRF(ntag, True).cuda()
+    with torch.no_grad():
+        crf.transitions.copy_(_t(trans))
+    mask = orc.length_mask(lens, L)
+    _, path = crf._viterbi_decode(_t(feats), _t(mask))
+    want = orc.crf_viterbi(feats, mask, trans)
+    np.testing.assert_array_equal(path.cpu().numpy(), want)
+    # an empty sequence decodes to nothing and leaves its neighbours alone (the reference cannot express length 0:
+    # it would index position -1; the kernels return a zero row)
+    lens0 = lens.copy()
+    lens0[1] = 0
+    from re2nn_seq_b200 import ops
+    _, p0 = ops.crf_viterbi(_t(feats), crf.transitions.detach(), _t(lens0), want_padded=True)
+    p0 = p0.cpu().numpy()
+    assert (p0[1] == 0).all()
+    keep = np.arange(B) != 1
+    np.testing.assert_array_equal(p0[keep], want[keep])
