@@ -38,7 +38,11 @@ def global_token_count(lengths, group=None):
 
 
 class GradBucket:
-    """Flat fp32 bucket over the trainable parameters of a module; one all-reduce(SUM) per step."""
+    """Flat fp32 bucket over the trainable parameters of a module; one all-reduce(SUM) per step.
+
+    Every parameter's ``.grad`` IS a view of its slice of the bucket (set once, kept across steps), so the backward
+    pass accumulates straight into the bucket and the collective runs on it in place: no pack / unpack copies.
+    ``zero_grad()`` is one memset of the bucket (use it instead of setting ``p.grad = None``)."""
 
     def __init__(self, module, group=None):
         self.params = [p for p in module.parameters() if p.requires_grad]
@@ -47,33 +51,29 @@ class GradBucket:
         self.total = sum(self.sizes)
         dev = self.params[0].device if self.params else torch.device('cpu')
         self.flat = torch.zeros((self.total,), dtype=torch.float32, device=dev)
-
-    def pack(self):
+        self.views = []
         off = 0
         for p, n in zip(self.params, self.sizes):
-            if p.grad is None:
-                self.flat[off:off + n].zero_()
-            else:
-                self.flat[off:off + n].copy_(p.grad.reshape(-1))
+            self.views.append(self.flat[off:off + n].view_as(p))
             off += n
-        return self.flat
+        self._bind()
 
-    def unpack(self):
-        off = 0
-        for p, n in zip(self.params, self.sizes):
-            g = self.flat[off:off + n].view_as(p)
-            if p.grad is None:
-                p.grad = g.clone()
-            else:
-                p.grad.copy_(g)
-            off += n
+    def _bind(self):
+        for p, v in zip(self.params, self.views):
+            if p.grad is not v:
+                if p.grad is not None:          # a gradient produced before the bucket existed (or after grad = None)
+                    v.copy_(p.grad)
+                p.grad = v
+
+    def zero_grad(self):
+        self.flat.zero_()
+        self._bind()
 
     def all_reduce(self):
-        """pack -> all_reduce(SUM) -> unpack.  Returns the number of bytes reduced."""
-        self.pack()
+        """all_reduce(SUM) of the bucket in place.  Returns the number of bytes reduced."""
+        self._bind()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-        self.unpack()
         return self.total * 4
 
 

@@ -94,6 +94,23 @@ class FARNN_S_O_I_S(nn.Module):
         pr = (self.priority_layer.priority_mat, self.priority_layer.priority_bias)
         return autograd_fns.onehot_scores(self._consts(full_pad), tensors, pr, x, lengths, L), lengths
 
+    def time_recurrence(self, input, lengths):
+        """Measurement hook (bench.py roofline): milliseconds of ONE onehot_recurrence_kernel launch over this batch,
+        CUDA events on the launching stream."""
+        dev = self._device()
+        x, lengths = input.to(dev).contiguous(), lengths.to(dev).contiguous()
+        c = self._consts(self.full_pad)
+        with torch.no_grad():
+            o = ops.output_vector_sum(self.output_mat, None if c['ce1'] else self.output_wildcard_vector)
+            summed = ops.onehot_sum_tensor(self.language_tensor, self.wildcard_mat)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.onehot_recurrence(x, lengths, x.shape[1], summed, None, o, self.h0, self.hT, c['update_nonlinear'],
+                                  c['max_semiring'], c['full_pad'], presummed=True)
+            e1.record()
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
     def forward_score(self, input, label, lengths, train=True):
         """B x L x C scores for all L = input.size(1) positions (model_onehot.py:351-428); pad positions
         are computed like the reference does (its callers may read them)."""

@@ -35,6 +35,15 @@ def _worker(rank, world, port, out):
         assert nbytes == (12 + 2) * 4
         assert torch.equal(model.a.grad, torch.full((3, 4), 3.0))               # 1 + 2
         assert torch.equal(model.c.grad, torch.zeros(2))
+        # second step: gradients are views of the bucket -> backward accumulates into it, no pack / unpack copies
+        bucket.zero_grad()
+        assert model.a.grad.data_ptr() == bucket.flat.data_ptr()
+        ((model.a.sum() + 2.0 * model.c.sum()) * float(rank + 1)).backward()
+        bucket.all_reduce()
+        assert model.a.grad.data_ptr() == bucket.flat.data_ptr()
+        assert torch.equal(model.a.grad, torch.full((3, 4), 3.0))
+        assert torch.equal(model.c.grad, torch.full((2,), 6.0))
+        assert torch.equal(bucket.flat, torch.cat([torch.full((12,), 3.0), torch.full((2,), 6.0)]))
         # sharding covers the batch exactly once, in order
         lens = torch.arange(1, 8)
         lo, hi = rd.shard_bounds(7, world, rank)
