@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RE2NN_ABI_VERSION 1
+#define RE2NN_ABI_VERSION 2
 
 /* update_nonlinear / additional_nonlinear (model_decompose_single.py:184-191, model_decompose.py:228-237) */
 enum { RE2NN_NL_NONE = 0, RE2NN_NL_RELU = 1, RE2NN_NL_TANH = 2, RE2NN_NL_RELUTANH = 3, RE2NN_NL_SIGMOID = 4 };
@@ -167,6 +167,15 @@ int re2nn_decompose_recurrence_resident(const re2nn_recurrence_args* a);
 size_t re2nn_decompose_max_workspace(int S, int R);
 int re2nn_decompose_max_recurrence(const re2nn_recurrence_args* a, void* stream);
 
+/* ---- dense-transition semiring step (FST variants, max-product training) ----------------------------------
+ * out[b,s] = (+|max)_j h[b,j] * T[b,j,s]  (transposed = 0)  or  (+|max)_j h[b,j] * T[b,s,j]  (transposed = 1);
+ * replaces utils.py:192-199 `_matmul` (bmm) / `_maxmul` at the call sites that materialise one dense S x S
+ * transition per sequence (farnn/model_onehot.py:96-103,274-290, model_decompose_independent.py:177-181,
+ * model_decompose_single.py:159-166).  argmax_out (max semiring, optional, B x S int32): the FIRST source state
+ * attaining the maximum, which is where torch.max(dim) routes the gradient. */
+int re2nn_batched_vecmat(const float* h, const float* T, int B, int S, int transposed, int max_semiring,
+                         float* out, int32_t* argmax_out, void* stream);
+
 /* ---- decompose i-FST backward (BPTT through both directions + label scores) ---------------------------
  * replaces torch.autograd over forward_local (train_decompose.py:192).  Input: d loss / d all_scores.
  * Outputs: gradients of every parameter the reference trains (NULL pointer = not wanted).
@@ -188,6 +197,10 @@ typedef struct re2nn_backward_args {
   float *dS1, *dS2, *dW, *dC, *d_o, *dh0, *dhT, *dWss1, *dWss2, *dWrs1, *dWrs2, *dbs1, *dbs2;
   float* dvtab;                 /* table_rows x R */
   void* ws; size_t ws_bytes;
+  /* FST variants (model_decompose.py:373-456: the score is not (alpha*beta) @ C^T): when both are non-NULL the
+   * gradients of the loss w.r.t. alpha / beta (B x L x S, exact zeros at rows past the length) are taken from here
+   * and dscores / C_mat / priority_mat / dC are ignored -- the label-score stage is differentiated by the caller. */
+  const float* dalpha_in; const float* dbeta_in;
 } re2nn_backward_args;
 /* debug / calibration: 1 (default) = the two GEMMs of every BPTT step run on the tensor cores in 3xTF32 when
  * tcgen05 is available, 0 = fp32 CUDA cores.  Changes the workspace size: set it before querying. */

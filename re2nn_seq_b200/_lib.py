@@ -48,7 +48,7 @@ class BackwardArgs(C.Structure):
         ('zsave', vp), ('rsave', vp),
         ('dS1', vp), ('dS2', vp), ('dW', vp), ('dC', vp), ('d_o', vp), ('dh0', vp), ('dhT', vp), ('dWss1', vp),
         ('dWss2', vp), ('dWrs1', vp), ('dWrs2', vp), ('dbs1', vp), ('dbs2', vp), ('dvtab', vp),
-        ('ws', vp), ('ws_bytes', sz),
+        ('ws', vp), ('ws_bytes', sz), ('dalpha_in', vp), ('dbeta_in', vp),
     ]
 
 
@@ -107,6 +107,7 @@ SYMBOLS = {
     're2nn_token_table_backward': (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, sz, vp]),
     're2nn_decompose_max_workspace': (sz, [C.c_int, C.c_int]),
     're2nn_decompose_max_recurrence': (C.c_int, [C.POINTER(RecurrenceArgs), vp]),
+    're2nn_batched_vecmat': (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     're2nn_onehot_recurrence': (C.c_int, [C.POINTER(OnehotArgs), vp]),
     're2nn_onehot_backward': (C.c_int, [C.POINTER(OnehotBackwardArgs), vp]),
     're2nn_onehot_sum_tensor': (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp]),

@@ -496,7 +496,12 @@ static int run_backward(const re2nn_backward_args& a, cudaStream_t st) {
   // 0. undo the priority layer: draw = dscores @ P^T
   const float* draw = a.dscores;
   GemmProblem g;
-  if (a.priority_mat) {
+  const bool direct = a.dalpha_in != nullptr && a.dbeta_in != nullptr;   // caller differentiated its own score stage
+  if (direct) {
+    c.dalpha = a.dalpha_in; c.dbeta = a.dbeta_in;
+    dbeta = const_cast<float*>(a.dbeta_in);
+  }
+  if (!direct && a.priority_mat) {
     memset(&g, 0, sizeof(g));
     g.M = (int)M; g.N = C; g.nseg = 1; g.ndir = 1;
     g.seg[0][0] = GemmSeg{a.dscores, a.priority_mat, C, C, C, 1, 0, 0};
@@ -504,12 +509,14 @@ static int run_backward(const re2nn_backward_args& a, cudaStream_t st) {
     draw = draw_ws;
   }
   // 1. dAB = draw @ C  ->  dAlpha, dBeta
-  memset(&g, 0, sizeof(g));
-  g.M = (int)M; g.N = S; g.nseg = 1; g.ndir = 1;
-  g.seg[0][0] = GemmSeg{draw, a.C_mat, C, S, C, 0, 0, 0};
-  RE2NN_CUDA(launch_simt_gemm(g, EpiDAB{a.alpha, a.beta, a.lengths, dalpha, dbeta, L, S, a.full_pad}, ALoadPlain{}, st));
+  if (!direct) {
+    memset(&g, 0, sizeof(g));
+    g.M = (int)M; g.N = S; g.nseg = 1; g.ndir = 1;
+    g.seg[0][0] = GemmSeg{draw, a.C_mat, C, S, C, 0, 0, 0};
+    RE2NN_CUDA(launch_simt_gemm(g, EpiDAB{a.alpha, a.beta, a.lengths, dalpha, dbeta, L, S, a.full_pad}, ALoadPlain{}, st));
+  }
   // 2. dC = draw^T @ (alpha * beta)
-  if (a.dC) {
+  if (!direct && a.dC) {
     TnProblem t;
     memset(&t, 0, sizeof(t));
     t.P = C; t.Q = S; t.npairs = 1;
@@ -706,10 +713,11 @@ size_t re2nn_decompose_backward_workspace(const re2nn_backward_args* a) {
 
 int re2nn_decompose_backward(const re2nn_backward_args* a, void* stream) {
   RE2NN_CHECK(a != nullptr, "decompose_backward: null args");
-  RE2NN_CHECK(a->B > 0 && a->L > 0 && a->S > 0 && a->R > 0 && a->C > 0, "decompose_backward: bad dims");
+  RE2NN_CHECK(a->B > 0 && a->L > 0 && a->S > 0 && a->R > 0 && (a->C > 0 || (a->dalpha_in && a->dbeta_in)), "decompose_backward: bad dims");
   RE2NN_CHECK(a->farnn >= 0 && a->farnn <= 2, "decompose_backward: farnn must be 0, 1 or 2");
-  RE2NN_CHECK(a->dscores && a->lengths && a->vtab && a->S1 && a->S2 && a->W && a->o && a->h0 && a->hT && a->C_mat &&
-                  a->alpha && a->beta && a->hbar_save && a->hst_save && a->u_save && a->a_save && a->dvtab,
+  const bool direct = a->dalpha_in && a->dbeta_in;
+  RE2NN_CHECK((direct || (a->dscores && a->C_mat)) && a->lengths && a->vtab && a->S1 && a->S2 && a->W && a->o && a->h0 &&
+                  a->hT && a->alpha && a->beta && a->hbar_save && a->hst_save && a->u_save && a->a_save && a->dvtab,
               "decompose_backward: null tensor");
   RE2NN_CHECK(a->v_mode == RE2NN_V_DENSE || a->x, "decompose_backward: token mode needs x");
   RE2NN_CHECK(a->farnn == 0 || (a->zsave && a->Wss1 && a->Wrs1), "decompose_backward: farnn>=1 needs gate tensors");

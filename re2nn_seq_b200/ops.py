@@ -90,7 +90,7 @@ def output_vector_sum(C_mat, wildcard_vec=None):
 
 def decompose_recurrence(x, lengths, L, vtab, gtab, S1, S2, W, o, h0, hT, Wss1, Wss2, farnn,
                          update_nonlinear, sigmoid_exponent, precision='fp32', v_mode=V_TOKEN,
-                         full_pad=False, save_for_backward=False, Lpad=None, max_semiring=False):
+                         full_pad=False, save_for_backward=False, Lpad=None, max_semiring=False, zero_fill=False):
     """Returns (alpha, beta, saves): alpha/beta B x L x S (pad rows undefined); saves = per-step slabs or None."""
     B = lengths.shape[0]
     S, R = S1.shape
@@ -102,8 +102,9 @@ def decompose_recurrence(x, lengths, L, vtab, gtab, S1, S2, W, o, h0, hT, Wss1, 
     a.v_mode, a.full_pad, a.save_for_backward = v_mode, int(full_pad), int(save_for_backward)
     a.sigmoid_exponent = float(sigmoid_exponent)
     # pad rows are never read downstream (label_scores masks them), so no zero-fill is needed
-    alpha = torch.empty((B, L, S), dtype=torch.float32, device=dev)
-    beta = torch.empty((B, L, S), dtype=torch.float32, device=dev)
+    alloc = torch.zeros if zero_fill else torch.empty
+    alpha = alloc((B, L, S), dtype=torch.float32, device=dev)
+    beta = alloc((B, L, S), dtype=torch.float32, device=dev)
     saves = None
     if save_for_backward:
         z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
@@ -294,13 +295,28 @@ def gemm_nt(A, B, precision='fp32'):
     return out
 
 
-def decompose_backward(consts, p, x, dense_v, lengths, L, vtab, o, alpha, beta, saves, dscores, pr_mat, want):
+def batched_vecmat(h, T, transposed=False, max_semiring=False):
+    """out[b,s] = (+|max)_j h[b,j] * T[b,j,s] (or T[b,s,j] when transposed); -> (out, argmax int32 or None)."""
+    B, S = h.shape
+    out = torch.empty((B, S), dtype=torch.float32, device=h.device)
+    idx = torch.empty((B, S), dtype=torch.int32, device=h.device) if max_semiring else None
+    check(fn['re2nn_batched_vecmat'](_f32(h), _f32(T), B, S, int(transposed), int(max_semiring), _f32(out),
+                                     _p(idx) if idx is not None else None, _stream()), 'batched_vecmat')
+    _count(1)
+    return out, idx
+
+
+def decompose_backward(consts, p, x, dense_v, lengths, L, vtab, o, alpha, beta, saves, dscores, pr_mat, want,
+                       dalpha_in=None, dbeta_in=None):
     """BPTT through both directions.  `want` = set of gradient names to produce.  Returns dict name -> tensor
-    (plus 'vtab' = d loss / d token-table rows, 'o' = d loss / d output_vector_sum)."""
+    (plus 'vtab' = d loss / d token-table rows, 'o' = d loss / d output_vector_sum).
+    dalpha_in / dbeta_in: gradients w.r.t. alpha / beta supplied by a caller that differentiates its own score stage
+    (FST variants); dscores, C_output_mat and the priority matrix are then unused."""
     B = lengths.shape[0]
     S, R = p['S1'].shape
-    Cn = p['C_output_mat'].shape[0]
-    dev = dscores.device
+    direct = dalpha_in is not None
+    Cn = 0 if direct else p['C_output_mat'].shape[0]
+    dev = alpha.device
     farnn = consts['farnn']
     a = BackwardArgs()
     a.B, a.L, a.S, a.R, a.C = B, L, S, R, Cn
@@ -311,10 +327,14 @@ def decompose_backward(consts, p, x, dense_v, lengths, L, vtab, o, alpha, beta, 
     a.table_rows = vtab.shape[0]
     a.sigmoid_exponent = float(consts['sigmoid_exponent'])
     a.x = _i64(x) if x is not None else None
-    a.lengths, a.dscores = _i64(lengths), _f32(dscores)
-    a.priority_mat = _f32(pr_mat) if pr_mat is not None else None
+    a.lengths = _i64(lengths)
+    a.dscores = _f32(dscores) if not direct else None
+    a.priority_mat = _f32(pr_mat) if (pr_mat is not None and not direct) else None
+    if direct:
+        a.dalpha_in, a.dbeta_in = _f32(dalpha_in), _f32(dbeta_in)
     a.vtab, a.S1, a.S2, a.W, a.o = _f32(vtab), _f32(p['S1']), _f32(p['S2']), _f32(p['wildcard_mat']), _f32(o)
-    a.h0, a.hT, a.C_mat = _f32(p['h0']), _f32(p['hT']), _f32(p['C_output_mat'])
+    a.h0, a.hT = _f32(p['h0']), _f32(p['hT'])
+    a.C_mat = _f32(p['C_output_mat']) if not direct else None
     for n in ('Wss1', 'Wss2', 'Wrs1', 'Wrs2'):
         setattr(a, n, _f32(p[n]) if n in p else None)
     a.alpha, a.beta = _f32(alpha), _f32(beta)
@@ -330,7 +350,8 @@ def decompose_backward(consts, p, x, dense_v, lengths, L, vtab, o, alpha, beta, 
 
     grad('S1', p['S1'], 'dS1'); grad('S2', p['S2'], 'dS2'); grad('wildcard_mat', p['wildcard_mat'], 'dW')
     grad('h0', p['h0'], 'dh0'); grad('hT', p['hT'], 'dhT')
-    out['C_output_mat'] = torch.empty_like(p['C_output_mat']); a.dC = _f32(out['C_output_mat'])
+    if not direct:
+        out['C_output_mat'] = torch.empty_like(p['C_output_mat']); a.dC = _f32(out['C_output_mat'])
     out['o'] = torch.empty((S,), dtype=torch.float32, device=dev); a.d_o = _f32(out['o'])
     if farnn >= 1:
         grad('Wss1', p['Wss1'], 'dWss1'); grad('Wrs1', p['Wrs1'], 'dWrs1'); grad('bs1', p['bs1'], 'dbs1')

@@ -1,0 +1,3 @@
+from src_seq import chain
+
+chain(__path__, 'baselines')

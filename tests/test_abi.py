@@ -24,7 +24,7 @@ def test_header_symbols_exported():
 
 def test_version_and_error_channel():
     from re2nn_seq_b200 import _lib
-    assert _lib.fn['re2nn_abi_version']() == 1
+    assert _lib.fn["re2nn_abi_version"]() == 2
     # argument validation happens before any CUDA call, so this is safe without a GPU
     rc = _lib.fn['re2nn_decompose_recurrence'](None, None)
     assert rc != 0

@@ -75,3 +75,33 @@ def test_embed_aggregator_surface():
     args.use_bert = 1
     with pytest.raises(ValueError, match='encoder'):
         r.EmbedAggregator(args, f['V'], f['pretrained_word_embed'])
+
+
+@pytest.mark.parametrize('name', golden_files('fst_'))
+def test_fst_constructors_match_reference(name):
+    """Host side only: same torch seed -> the FST drop-ins draw the reference's random numbers in the reference's
+    order (state_dict keys, shapes and values identical; the fixture's gates / CRF transitions were edited after
+    construction and are compared by key and shape only)."""
+    import json
+    import os
+    import numpy as np
+    from helpers import GOLDEN
+    from test_gpu_fst import build_fst_module
+    z = np.load(os.path.join(GOLDEN, name + '.npz'), allow_pickle=False)
+    meta = json.loads(str(z['meta']))
+    meta['name'] = name
+    if meta['kind'] == 'fst_oi':
+        meta['independent'] = 2 if 'ind2' in name else 1
+    m = build_fst_module(z, meta, load_state=False)
+    sd = m.state_dict()
+    want = {k[2:]: z[k] for k in z.files if k.startswith('p.')}
+    assert sorted(sd.keys()) == sorted(want.keys())
+    edited = ('Wss1', 'Wrs1', 'bs1', 'Wss2', 'Wrs2', 'bs2', 'crf.transitions')
+    for k, v in sd.items():
+        assert tuple(v.shape) == want[k].shape, k
+        if k not in edited:
+            np.testing.assert_array_equal(v.cpu().numpy(), want[k], err_msg=k)
+    flags = {k: v.requires_grad for k, v in m.named_parameters()}
+    grads = {k[2:] for k in z.files if k.startswith('g.')}
+    if grads:
+        assert grads <= {k for k, rg in flags.items() if rg}
