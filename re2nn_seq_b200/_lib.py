@@ -17,6 +17,17 @@ if not os.path.exists(LIB_PATH):
 
 lib = C.CDLL(LIB_PATH)
 
+# TORCH_LIBRARY(re2nn, ...) registration of the hot-path ops (csrc/torch_ops.cpp): torch.ops.re2nn.*
+TORCH_LIB_PATH = os.path.join(_HERE, 'libre2nn_torch.so')
+if not os.path.exists(TORCH_LIB_PATH):
+    raise ImportError(
+        "re2nn_seq_b200: %s not found. Build it with `python re2nn_seq_b200/build.py` (or __graft_entry__.build()); "
+        "there is no fallback path." % TORCH_LIB_PATH)
+import torch as _torch  # noqa: E402
+
+_torch.ops.load_library(TORCH_LIB_PATH)
+tops = _torch.ops.re2nn
+
 vp, i32, i64, f32, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 
 NL = {'none': 0, 'relu': 1, 'tanh': 2, 'relutanh': 3, 'sigmoid': 4}

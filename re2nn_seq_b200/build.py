@@ -56,5 +56,39 @@ def build(force=False, verbose=False):
     return LIB
 
 
+TORCH_LIB = os.path.join(HERE, 'libre2nn_torch.so')
+
+
+def build_torch_ops(force=False, verbose=False):
+    """TORCH_LIBRARY(re2nn, ...) registration (csrc/torch_ops.cpp) -> libre2nn_torch.so next to libre2nn_b200.so."""
+    import hashlib
+    import torch
+    from torch.utils import cpp_extension as ce
+    src = os.path.join(CSRC, 'torch_ops.cpp')
+    hdr = os.path.join(HERE, '..', 'include', 're2nn_b200.h')
+    digest = hashlib.sha256(open(src, 'rb').read() + open(hdr, 'rb').read() + torch.__version__.encode()).hexdigest()
+    stamp = TORCH_LIB + '.hash'
+    if not force and os.path.exists(TORCH_LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+        return TORCH_LIB
+    tlib = os.path.join(os.path.dirname(torch.__file__), 'lib')
+    cuda_home = os.environ.get('CUDA_HOME', '/usr/local/cuda')
+    cmd = [os.environ.get('CXX', 'g++'), '-O2', '-std=c++17', '-fPIC', '-shared', src, '-o', TORCH_LIB,
+           '-D_GLIBCXX_USE_CXX11_ABI=%d' % int(torch._C._GLIBCXX_USE_CXX11_ABI)]
+    for inc in ce.include_paths() + [os.path.join(cuda_home, 'include')]:
+        cmd += ['-isystem', inc]
+    cmd += ['-L' + tlib, '-L' + HERE, '-L' + os.path.join(cuda_home, 'lib64'), '-lc10', '-lc10_cuda', '-ltorch_cpu', '-ltorch_cuda',
+            '-ltorch', '-lre2nn_b200', '-lcudart', '-Wl,-rpath,$ORIGIN', '-Wl,-rpath,' + tlib, '-Wl,--no-as-needed']
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError('torch_ops build failed')
+    if verbose:
+        sys.stderr.write(r.stdout)
+    with open(stamp, 'w') as f:
+        f.write(digest)
+    return TORCH_LIB
+
+
 if __name__ == '__main__':
     print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    print(build_torch_ops(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -101,6 +101,10 @@ class _DecomposeBase(nn.Module):
             return 'fp32'
         return 'fp16x3' if self.args.update_nonlinear in ('tanh', 'relutanh') else 'tf32x3'
 
+    def _max_needs_grad(self, tensors):
+        """train_mode == 'max' with a gradient wanted: the differentiable dense-transition form (model_fst.py)."""
+        return self.args.train_mode == 'max' and torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+
     # ---- launch-time constants -----------------------------------------------------------------
     @property
     def _S_full(self):
@@ -425,6 +429,9 @@ class FARNN_S_D_W_I_S(_DecomposeBase):
         lengths = lengths.to(dev).contiguous()
         shape = shape or self._host_shape(lengths)
         names, tensors = self._fn_params()
+        if self._max_needs_grad(tensors):
+            from .model_fst import ifst_decompose_max_scores
+            return ifst_decompose_max_scores(self, x, None, lengths, shape[0])
         pr = (self.priority_layer.priority_mat, self.priority_layer.priority_bias)
         return autograd_fns.decompose_scores(self._recurrence_consts(), names, tensors, pr, x, None, lengths, shape[0],
                                              cache=self._cache)
@@ -503,6 +510,9 @@ class FARNN_S_SF(_DecomposeBase):
         shape = shape or self._host_shape(lengths)
         names = self._params_for_fn()
         tensors = [getattr(self, n) for n in names]
+        if self._max_needs_grad(tensors + [v]):
+            from .model_fst import ifst_decompose_max_scores
+            return ifst_decompose_max_scores(self, None, v, lengths, shape[0])
         pr = (self.priority_layer.priority_mat, self.priority_layer.priority_bias)
         return autograd_fns.decompose_scores(self._recurrence_consts(), names, tensors, pr, None, v, lengths, shape[0])
 

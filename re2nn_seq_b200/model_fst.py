@@ -173,6 +173,100 @@ class _FstRecurrence(torch.autograd.Function):
         return (None, None, None, None) + tuple(out)
 
 
+# ---- max-product TRAINING of the i-FST classes ---------------------------------------------------
+# train_mode = 'max' materialises one dense transition per sequence and step in the reference too
+# (model_decompose_single.py:159-166, model_onehot.py:374-403 with utils.py:192-195); the gradient follows the argmax
+# saved by re2nn_batched_vecmat.  Inference keeps the dedicated kernels (re2nn_decompose_max_recurrence, the MAXP
+# onehot kernel); these differentiable forms run only when a gradient is needed.
+def ifst_decompose_max_scores(m, x, dense_v, lengths, L):
+    """all_scores B x L x C of FARNN_S_D_W_I_S / FARNN_S_SF under the max-product semiring, differentiable."""
+    a = m.args
+    S = m._S_full
+    B = lengths.shape[0]
+    k = float(a.sigmoid_exponent)
+    nl = _nl_name(a.update_nonlinear, _UPDATE_NL)
+    if dense_v is None:
+        vt = _Aggregate.apply(m.V_embed, m.embedding.weight, m.embed_r_generalized, m.beta_vec,
+                              _nl_name(a.additional_nonlinear, _ADD_NL))
+        x = x[:, :L]
+        xr = _reverse_tokens(x, lengths)
+        v_at = lambda i, rev: vt[(xr if rev else x)[:, i]]
+    else:
+        v = dense_v[:, :L]
+        pos = torch.arange(L, device=v.device).unsqueeze(0)
+        n = lengths.unsqueeze(1)
+        ridx = torch.where(pos < n, n - 1 - pos, pos)
+        vr = v.gather(1, ridx.unsqueeze(2).expand(B, L, v.shape[2]))
+        v_at = lambda i, rev: (vr if rev else v)[:, i]
+    o = m.C_output_mat.sum(0)
+    if a.local_loss_func != 'CE1':
+        o = o + m.wildcard_output_vector
+    h0 = m.h0.view(1, S).expand(B, S)
+    hT = m.hT.view(1, S).expand(B, S)
+
+    def step(h, V_vec, h_init, is_forward):
+        h_bar = h
+        if a.farnn >= 1:
+            zt = torch.sigmoid(k * (matmul_nt(h, m.Wss1.t().contiguous()) + matmul_nt(V_vec, m.Wrs1.t().contiguous()) + m.bs1))
+        if a.farnn == 2:
+            rt = torch.sigmoid(k * (matmul_nt(h, m.Wss2.t().contiguous()) + matmul_nt(V_vec, m.Wrs2.t().contiguous()) + m.bs2))
+            h_bar = (1 - rt) * h_init + rt * h
+        if not is_forward:
+            h_bar = h_bar * o
+        X = (m.S1.unsqueeze(0) * V_vec.unsqueeze(1)).reshape(B * S, m.S1.shape[1])
+        Tr = matmul_nt(X, m.S2).view(B, S, S) + m.wildcard_mat
+        hn = vecmat(h_bar, Tr, transposed=not is_forward, maxp=True)
+        if is_forward:
+            hn = hn * o
+        hn = _apply_nl(hn, nl)
+        if a.farnn >= 1:
+            hn = (1 - zt) * h + zt * hn
+        return hn
+
+    hf, hb, fw, bw = h0, hT, [], []
+    for i in range(L):
+        hf = step(hf, v_at(i, False), h0, True)
+        fw.append(hf)
+        hb = step(hb, v_at(i, True), hT, False)
+        bw.append(hb)
+    alpha = torch.stack(fw, dim=1)                                          # h0_forward_score[:, i + 1]
+    beta = _beta_rows(m.hT, torch.stack(bw, dim=1), lengths)                # reversed_backward_score_x[:, i + 1]
+    scores = matmul_nt((alpha * beta).reshape(B * L, S), m.C_output_mat).view(B, L, m.C)
+    if a.use_priority:
+        scores = (matmul_nt(scores.reshape(B * L, m.C), m.priority_layer.priority_mat.t().contiguous()) +
+                  m.priority_layer.priority_bias).view(B, L, m.C)
+    return scores
+
+
+def ifst_onehot_max_scores(m, x, lengths):
+    """all_scores B x L x C of FARNN_S_O_I_S under the max-product semiring, differentiable (model_onehot.py:366-426)."""
+    a = m.args
+    B, L = x.shape
+    S = m.S
+    nl = a.update_nonlinear if a.update_nonlinear in _UPDATE_NL else 'none'
+    T = m.language_tensor + m.wildcard_mat
+    o = m.output_mat.sum(0)
+    if a.local_loss_func != 'CE1':
+        o = o + m.output_wildcard_vector
+    xr = _reverse_tokens(x, lengths)
+    hf = m.h0.view(1, S).expand(B, S)
+    hb = m.hT.view(1, S).expand(B, S)
+    fw, bw = [], []
+    for i in range(L):
+        hf = _apply_nl(vecmat(hf, T[x[:, i]], False, True) * o, nl)
+        fw.append(hf)
+        hb = _apply_nl(vecmat(hb * o, T[xr[:, i]], True, True), nl)
+        bw.append(hb)
+    alpha = torch.stack(fw, dim=1)
+    beta = _beta_rows(m.hT, torch.stack(bw, dim=1), lengths)
+    Cn = m.output_mat.shape[0]
+    scores = matmul_nt((alpha * beta).reshape(B * L, S), m.output_mat).view(B, L, Cn)
+    if a.use_priority:
+        scores = (matmul_nt(scores.reshape(B * L, Cn), m.priority_layer.priority_mat.t().contiguous()) +
+                  m.priority_layer.priority_bias).view(B, L, Cn)
+    return scores
+
+
 # ---- FARNN_S_D_W ------------------------------------------------------------------------------------------------------------
 class FARNN_S_D_W(_DecomposeBase):
     def __init__(self, V=None, C=None, S1=None, S2=None, C_wildcard=None, S1_wildcard=None, S2_wildcard=None,

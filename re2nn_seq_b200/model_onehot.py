@@ -91,6 +91,10 @@ class FARNN_S_O_I_S(nn.Module):
         lengths = lengths.to(dev).contiguous()
         tensors = [self.h0, self.hT, self.language_tensor, self.wildcard_mat, self.output_mat,
                    self.output_wildcard_vector]
+        if self.args.train_mode == 'max' and torch.is_grad_enabled() and any(t.requires_grad for t in tensors) \
+                and L == x.shape[1] and not full_pad:
+            from .model_fst import ifst_onehot_max_scores      # max-product training: argmax-routed gradient
+            return ifst_onehot_max_scores(self, x, lengths), lengths
         pr = (self.priority_layer.priority_mat, self.priority_layer.priority_bias)
         return autograd_fns.onehot_scores(self._consts(full_pad), tensors, pr, x, lengths, L), lengths
 

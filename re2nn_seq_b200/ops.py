@@ -1,7 +1,10 @@
 """Thin Python wrappers over the C-ABI: torch owns device memory and streams, the kernels do the work.
 
-Every function takes contiguous CUDA tensors (fp32 / int64), allocates outputs with torch and
-calls one entry point of libre2nn_b200.so on the current stream.  No computation happens in torch.
+The hot-path ops -- recurrences, label scores, decode, CRF -- are called as registered PyTorch custom ops
+(`torch.ops.re2nn.*`, TORCH_LIBRARY in csrc/torch_ops.cpp, a thin C++ layer over the same C-ABI); the remaining entry
+points (tables, training saves / backward, debug switches) go through ctypes.  Every function takes contiguous CUDA
+tensors (fp32 / int64); outputs are allocated with torch on the tensor's device and the kernels run on the current
+stream.  No computation happens in torch.
 """
 import ctypes as C
 
@@ -9,7 +12,7 @@ import torch
 
 from . import _lib
 from ._lib import (NL, PREC, V_DENSE, V_TOKEN, BackwardArgs, OnehotArgs, OnehotBackwardArgs, RecurrenceArgs, check,
-                   fn)
+                   fn, tops)
 
 _LAUNCHES = {'n': 0}   # launch counter read by bench.py ("gpu_launches")
 
@@ -114,6 +117,15 @@ def decompose_recurrence(x, lengths, L, vtab, gtab, S1, S2, W, o, h0, hT, Wss1, 
         a.u_save, a.a_save = _f32(saves['u']), _f32(saves['a'])
         a.zsave = _f32(saves['z']) if saves['z'] is not None else None
         a.rsave = _f32(saves['r']) if saves['r'] is not None else None
+    if not save_for_backward and not zero_fill:
+        # inference: the registered custom op (allocates alpha / beta and the workspace itself)
+        for t in (lengths, vtab, S1, S2, W, o, h0, hT):
+            _p(t)
+        alpha, beta = tops.ifst_decompose_forward(x, lengths, vtab, gtab, S1, S2, W, o, h0, hT, Wss1, Wss2, L, a.Lpad, farnn,
+                                                  a.update_nonlinear, a.precision, v_mode, bool(full_pad),
+                                                  float(sigmoid_exponent), bool(max_semiring))
+        _count(3 if max_semiring else fn['re2nn_decompose_recurrence_launches'](C.byref(a)))
+        return alpha, beta, None
     a.x = _i64(x) if x is not None else None
     a.lengths = _i64(lengths)
     a.vtab, a.gtab = _f32(vtab), (_f32(gtab) if gtab is not None else None)
@@ -140,13 +152,20 @@ def onehot_recurrence(x, lengths, L, language, W, o, h0, hT, update_nonlinear, m
                       presummed=False):
     B, Lpad = x.shape
     S = language.shape[1]
+    if presummed:
+        for t in (x, lengths, language, o, h0, hT):
+            _p(t)
+        alpha, beta = tops.ifst_onehot_forward(x, lengths, language, o, h0, hT, L, NL[update_nonlinear], bool(max_semiring),
+                                               bool(full_pad))
+        _count(1)
+        return alpha, beta
     a = OnehotArgs()
     a.B, a.Lpad, a.L, a.S = B, Lpad, L, S
     a.update_nonlinear, a.max_semiring, a.full_pad = NL[update_nonlinear], int(max_semiring), int(full_pad)
     alpha = torch.zeros((B, L, S), dtype=torch.float32, device=language.device)
     beta = torch.zeros((B, L, S), dtype=torch.float32, device=language.device)
     a.x, a.lengths = _i64(x), _i64(lengths)
-    a.language, a.W, a.o, a.h0, a.hT = _f32(language), (_f32(W) if not presummed else None), _f32(o), _f32(h0), _f32(hT)
+    a.language, a.W, a.o, a.h0, a.hT = _f32(language), _f32(W), _f32(o), _f32(h0), _f32(hT)
     a.alpha, a.beta = _f32(alpha), _f32(beta)
     check(fn['re2nn_onehot_recurrence'](C.byref(a), _stream()), 'onehot_recurrence')
     _count(1)
@@ -155,73 +174,44 @@ def onehot_recurrence(x, lengths, L, language, W, o, h0, hT, update_nonlinear, m
 
 def label_scores(alpha, beta, lengths, C_mat, priority_mat=None, priority_bias=None, full_pad=False,
                  precision='fp32'):
-    B, L, S = alpha.shape
-    Cn = C_mat.shape[0]
-    scores = torch.empty((B, L, Cn), dtype=torch.float32, device=alpha.device)
-    has_pr = priority_mat is not None
-    need = fn['re2nn_label_scores_workspace'](B, L, S, Cn, PREC[precision], int(has_pr))
-    ws = torch.empty((need,), dtype=torch.uint8, device=alpha.device)
-    check(fn['re2nn_label_scores'](_f32(alpha), _f32(beta), _i64(lengths), B, L, S, _f32(C_mat), Cn,
-                                   _f32(priority_mat) if has_pr else None,
-                                   _f32(priority_bias) if priority_bias is not None else None,
-                                   int(full_pad), PREC[precision], _f32(scores), C.c_void_p(ws.data_ptr()), need,
-                                   _stream()), 'label_scores')
-    _count((1 if precision == 'fp32' else 3) + (1 if has_pr else 0))
+    for t in (alpha, beta, lengths, C_mat):
+        _p(t)
+    scores = tops.label_scores(alpha, beta, lengths, C_mat, priority_mat, priority_bias, bool(full_pad), PREC[precision])
+    _count((1 if precision == 'fp32' else 3) + (1 if priority_mat is not None else 0))
     return scores
 
 
 def argmax_decode(scores, lengths, offsets, n_flat, clamp_col, threshold, o_idx, want_flat=True, want_padded=False,
                   flat_out=None):
     """flat_out: optional shared int64 buffer the flat predictions are scattered into (through `offsets`)."""
-    B, L, Cn = scores.shape
-    flat = (flat_out if flat_out is not None else torch.empty((n_flat,), dtype=torch.int64, device=scores.device)) \
-        if want_flat else None
-    padded = torch.empty((B, L), dtype=torch.int64, device=scores.device) if want_padded else None
-    check(fn['re2nn_argmax_decode'](_f32(scores), _i64(lengths), _i64(offsets) if offsets is not None else None,
-                                    B, L, Cn, clamp_col, float(threshold), int(o_idx),
-                                    _i64(flat) if flat is not None else None,
-                                    _i64(padded) if padded is not None else None, _stream()), 'argmax_decode')
+    for t in (scores, lengths):
+        _p(t)
+    flat, padded = tops.argmax_decode(scores, lengths, offsets, int(n_flat), int(clamp_col), float(threshold), int(o_idx),
+                                      bool(want_flat), bool(want_padded), flat_out)
     _count(1)
-    return flat, padded
+    return ((flat_out if flat_out is not None else flat) if want_flat else None), (padded if want_padded else None)
 
 
 def crf_viterbi(feats, transitions, lengths, offsets=None, n_flat=0, clamp_col=-1, threshold=0.0, o_idx=0,
                 want_flat=False, want_padded=True, flat_out=None):
-    B, L, T = feats.shape
-    dev = feats.device
-    flat = (flat_out if flat_out is not None else torch.empty((n_flat,), dtype=torch.int64, device=dev)) \
-        if want_flat else None
-    padded = torch.empty((B, L), dtype=torch.int64, device=dev) if want_padded else None
-    bp = torch.empty((B * L * T,), dtype=torch.float32, device=dev)     # partition history (no back-pointers)
-    check(fn['re2nn_crf_viterbi'](_f32(feats), _f32(transitions), _i64(lengths),
-                                  _i64(offsets) if offsets is not None else None, B, L, T, clamp_col,
-                                  float(threshold), int(o_idx), _i64(padded) if padded is not None else None,
-                                  _i64(flat) if flat is not None else None, C.c_void_p(bp.data_ptr()), _stream()),
-          'crf_viterbi')
+    for t in (feats, transitions, lengths):
+        _p(t)
+    flat, padded = tops.crf_viterbi(feats, transitions, lengths, offsets, int(n_flat), int(clamp_col), float(threshold),
+                                    int(o_idx), bool(want_flat), bool(want_padded), flat_out)
     _count(1)
-    return flat, padded
+    return ((flat_out if flat_out is not None else flat) if want_flat else None), (padded if want_padded else None)
 
 
 def crf_nll(feats, transitions, lengths, tags, save=False):
-    B, L, T = feats.shape
-    dev = feats.device
-    per_seq = torch.empty((B,), dtype=torch.float32, device=dev)
-    loss = torch.empty((), dtype=torch.float32, device=dev)
-    part = torch.empty((B, L, T), dtype=torch.float32, device=dev) if save else None
-    check(fn['re2nn_crf_nll'](_f32(feats), _f32(transitions), _i64(lengths), _i64(tags), B, L, tags.shape[1], T,
-                              _f32(per_seq), _f32(loss), _f32(part) if part is not None else None, _stream()),
-          'crf_nll')
+    for t in (feats, transitions, lengths, tags):
+        _p(t)
+    loss, per_seq, part = tops.crf_nll(feats, transitions, lengths, tags, bool(save))
     _count(2)
-    return loss, per_seq, part
+    return loss, per_seq, (part if save else None)
 
 
 def crf_nll_backward(feats, transitions, lengths, tags, part, gscale):
-    B, L, T = feats.shape
-    dfeats = torch.empty_like(feats)
-    dtrans = torch.empty((T, T), dtype=torch.float32, device=feats.device)
-    check(fn['re2nn_crf_nll_backward'](_f32(feats), _f32(transitions), _i64(lengths), _i64(tags), _f32(part),
-                                       _f32(gscale), B, L, tags.shape[1], T, _f32(dfeats), _f32(dtrans), _stream()),
-          'crf_nll_backward')
+    dfeats, dtrans = tops.crf_nll_backward(feats, transitions, lengths, tags, part, gscale)
     _count(1)
     return dfeats, dtrans
 

@@ -39,3 +39,20 @@ def test_no_oracle_in_product():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 txt = open(os.path.join(root, f)).read()
                 assert 'import oracle' not in txt and 'from oracle' not in txt and 're2nn_oracle' not in txt, f
+
+
+def test_torch_library_registration():
+    """TORCH_LIBRARY(re2nn, ...): the hot-path ops are registered PyTorch custom ops with CUDA kernels only
+    (csrc/torch_ops.cpp); calling one with CPU tensors fails loudly instead of falling back."""
+    import pytest
+    import torch
+    from re2nn_seq_b200 import _lib
+    assert int(_lib.tops.abi_version()) == 2
+    for name in ('ifst_decompose_forward', 'ifst_onehot_forward', 'label_scores', 'argmax_decode', 'crf_viterbi', 'crf_nll',
+                 'crf_nll_backward'):
+        assert hasattr(_lib.tops, name), name
+        schema = str(getattr(_lib.tops, name).default._schema)
+        assert schema.startswith('re2nn::' + name + '('), schema
+    f = torch.zeros(2, 3, 5)
+    with pytest.raises((RuntimeError, NotImplementedError)):       # no CPU implementation is registered
+        _lib.tops.crf_viterbi(f, torch.zeros(5, 5), torch.tensor([3, 2]), None, 0, -1, 0.0, 0, False, True, None)

@@ -137,9 +137,10 @@ def test_decompose_cfg2_shapes_vs_oracle(farnn, crf):
     assert mism == 0, 'decoded tags differ at %d of %d positions' % (mism, len(o_pred))
 
 
-@pytest.mark.parametrize('name', [n for n in DEC if 'max' not in n])
+@pytest.mark.parametrize('name', DEC)
 def test_decompose_gradients_golden(name):
-    """loss.backward() through the CUDA backward vs the reference's autograd gradients."""
+    """loss.backward() through the CUDA backward vs the reference's autograd gradients (train_mode = 'max' included:
+    its gradient follows the argmax saved by re2nn_batched_vecmat)."""
     z, meta = load_golden(name)
     m = build_module(name, z, meta).cuda()
     x, lab, lens = _t(z['x']), _t(z['labels']), _t(z['lengths'])
@@ -194,11 +195,7 @@ def test_onehot_gradients_golden(name):
     x, lab, lens = torch.from_numpy(z['x']), torch.from_numpy(z['labels']), torch.from_numpy(z['lengths'])
     loss, _, _ = m.forward_local(x, lab, lens, train=True)
     assert rel_err(loss.item(), z['loss']) < TOL
-    if meta['flags'].get('train_mode') == 'max':
-        with pytest.raises(NotImplementedError):
-            loss.backward()
-        return
-    loss.backward()
+    loss.backward()                          # train_mode = 'max' included (argmax-routed gradient)
     gold = golden_grads(z)
     assert list(gold) == ['language_tensor']
     err = rel_err(m.language_tensor.grad.cpu().numpy(), gold['language_tensor'])
