@@ -146,3 +146,138 @@ def test_longest_first_order_is_invisible():
     assert abs(l1 - l0) <= 1e-5 * abs(l0)
     for k in g0:
         assert rel_err(g1[k], g0[k]) < 2e-5, k
+
+
+# ---- the exact benchmarked paths ------------------------------------------------------------------
+def _reference_tags(cfg_flags, f, x, lab, lens, crf_seed):
+    """Decoded tags of the UNMODIFIED reference (oracle/_ref, torch CPU fp32) for the given rows."""
+    from oracle import make_ref
+    why = make_ref.verify()
+    if why:
+        pytest.skip(why)
+    make_ref.import_reference()
+    from src_seq.farnn.model_decompose_single import FARNN_S_D_W_I_S as RefModel
+    from re2nn_seq_b200 import synth
+    torch.manual_seed(crf_seed)
+    ref = RefModel(V=f['V'], S1=f['S1'], S2=f['S2'], C_output_mat=f['C_output_mat'], wildcard_mat=f['wildcard_mat'],
+                   wildcard_output_vector=f['wildcard_output_vector'], final_vector=f['final_vector'],
+                   start_vector=f['start_vector'], pretrained_word_embed=f['pretrained_word_embed'], priority_mat=None,
+                   args=synth.make_args(**cfg_flags), o_idx=0, is_cuda=False)
+    with torch.no_grad():
+        ref.crf.transitions.copy_(torch.from_numpy(synth.crf_transitions(crf_seed, ref.C)))
+    ref.eval()
+    Lm = int(lens.max())
+    with torch.no_grad():
+        _, pred, _ = ref.forward_local(torch.from_numpy(x[:, :Lm].copy()), torch.from_numpy(lab[:, :Lm].copy()),
+                                       torch.from_numpy(lens.copy()), train=False)
+    return pred.numpy()
+
+
+def test_cfg2_benchmarked_path_vs_reference():
+    """cfg2 exactly as bench.py times it: B=4096, precision='auto' (fp16x3), CUDA graph replay, resident kernel,
+    four chunk streams.  Decoded tags of a 128-row slice of EVERY chunk of the length-sorted batch against the
+    unmodified reference classes, bit-exact."""
+    import re2nn_seq_b200 as r
+    from re2nn_seq_b200 import ops, synth
+    if not ops.has_tcgen05():
+        pytest.skip('no tcgen05')
+    flags = dict(farnn=0, use_crf=1, update_nonlinear='tanh', beta=0.1)
+    args = synth.make_args(**flags)
+    f = synth.make_decompose_factors(0, 12000, 300, 200, 72, 100, dtype=np.float32)
+    x, lens, lab = synth.make_batch(1000, 4096, 35, 12000, 72)
+    torch.manual_seed(13)
+    m = r.FARNN_S_D_W_I_S(args=args, o_idx=0, **f)
+    with torch.no_grad():
+        m.crf.transitions.copy_(torch.from_numpy(synth.crf_transitions(13, m.C)))
+    m = m.cuda().eval()
+    m.precision = 'auto'
+    m.infer_chunks = 4
+    xt, lt, yt = _t(x), _t(lens), _t(lab)
+    with torch.no_grad():
+        for _ in range(3):                      # second sighting captures the graph, third replays it
+            _, pred, _ = m.forward_local(xt, yt, lt, train=False)
+        assert m._resolved_precision() == 'fp16x3' and ops.recurrence_is_resident(300, 200, 0, 'fp16x3')
+        chunks = m._infer_chunks(4096)
+    assert getattr(m, '_graphs', None), 'the CUDA-graph path was not taken'
+    pred = pred.cpu().numpy()
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    order = np.argsort(-lens, kind='stable')        # the module's longest-first processing order
+    assert chunks is not None and len(chunks) == 4
+    for b0, b1 in chunks:
+        rows = order[b0:b0 + 128]
+        want = _reference_tags(flags, f, x[rows], lab[rows], lens[rows], 13)
+        got = np.concatenate([pred[offs[b]:offs[b + 1]] for b in rows])
+        mism = int((got != want).sum())
+        assert mism == 0, 'chunk [%d,%d): %d of %d tags differ from the reference' % (b0, b1, mism, len(want))
+
+
+@pytest.mark.parametrize('prec', ['fp16x3', 'tf32x3'])
+def test_cfg5_shapes_decoded_tags_vs_reference(prec):
+    """S=1024, R=512, C=128, len=64: decoded tags (Viterbi over T=131) of the parity-grade modes against the unmodified
+    reference on a 48-sequence slice, bit-exact; scores against the fp64 oracle."""
+    from re2nn_seq_b200 import ops, synth
+    if not ops.has_tcgen05():
+        pytest.skip('no tcgen05')
+    flags = dict(farnn=0, use_crf=1, update_nonlinear='tanh', beta=0.1)
+    m, args, x, lens, lab = _decompose(12, 900, 1024, 512, 128, 100, 300, 64, fixed_len=True, **flags)
+    m.precision = prec
+    with torch.no_grad():
+        _, pred, _ = m.forward_local(_t(x), _t(lab), _t(lens), train=False)
+    f = synth.make_decompose_factors(12, 900, 1024, 512, 128, 100, dtype=np.float32)
+    want = _reference_tags(flags, f, x[:48], lab[:48], lens[:48], 12)
+    got = pred.cpu().numpy()[:48 * 64]
+    assert int((got != want).sum()) == 0
+
+
+def test_onehot_s1024_exact():
+    """Onehot at the scale-sweep state count (S=1024, small vocabulary): integer path counts, bit-exact scores and tags."""
+    import re2nn_seq_b200 as r
+    from re2nn_seq_b200 import synth
+    args = synth.make_args(method='onehot', rand_constant=0.0)
+    a = synth.make_onehot_automaton(23, 12, 1024, 128, lang_frac=0.5, dtype=np.float32)
+    x, lens, lab = synth.make_batch(24, 6, 12, 12, 128)
+    m = r.FARNN_S_O_I_S(a['language_tensor'], a['output_mat'], a['wildcard_mat'], a['output_wildcard_vector'],
+                        a['final_vector'], a['start_vector'], None, args, 0, False)
+    with torch.no_grad():
+        loss, pred, true = m.forward_local(torch.from_numpy(x), torch.from_numpy(lab), torch.from_numpy(lens), train=False)
+        sc = m.forward_score(torch.from_numpy(x), None, torch.from_numpy(lens)).numpy()
+    p = {k: v for k, v in a.items() if k != 'language_rows'}
+    p.update(h0=a['start_vector'], hT=a['final_vector'])
+    o_sc = orc.onehot_scores(p, x, lens, args)
+    assert np.isfinite(sc).all() and sc.max() < 2 ** 24
+    np.testing.assert_array_equal(sc, o_sc)
+    _, o_pred, _, _ = orc.onehot_forward_local(p, x, lab, lens, args, 0, train=False)
+    np.testing.assert_array_equal(pred.numpy(), o_pred)
+
+
+def test_cfg3_full_batch_gradients_vs_fp64_oracle(capsys):
+    """cfg3 as bench.py trains it: B=1024, forward GEMMs in the `auto` training precision (fp16x3), BPTT GEMMs 3xTF32.
+    Every parameter gradient against the float64 autograd oracle over the SAME 1024 sequences; the measured
+    per-parameter errors are printed (they are the evidence for the bound written in DESIGN.md section 2)."""
+    import re2nn_seq_b200 as r
+    from re2nn_seq_b200 import ops, synth
+    from oracle import re2nn_oracle_torch as ot
+    if not ops.has_tcgen05():
+        pytest.skip('no tcgen05')
+    flags = dict(farnn=0, use_crf=1, update_nonlinear='tanh', beta=0.1)
+    m, args, x, lens, lab = _decompose(7, 12000, 300, 200, 72, 100, 1024, 35, **flags)
+    m.train()
+    m.train_precision = 'auto'
+    loss, pred, _ = m.forward_local(_t(x), _t(lab), _t(lens), train=True)
+    loss.backward()
+    rename = {'embedding.weight': 'embedding', 'crf.transitions': 'crf_transitions',
+              'priority_layer.priority_mat': 'priority_mat', 'priority_layer.priority_bias': 'priority_bias'}
+    p = {rename.get(k, k): v.detach().cpu().numpy().astype(np.float64) for k, v in m.state_dict().items()}
+    names = [rename.get(k, k) for k, v in m.named_parameters() if v.requires_grad]
+    o_loss, o_grads = ot.grads(p, x, lab, lens, args, names=names)
+    assert abs(loss.item() - o_loss) <= 1e-5 * abs(o_loss)
+    errs = {}
+    for k, v in m.named_parameters():
+        if v.requires_grad:
+            ref = o_grads[rename.get(k, k)]
+            errs[k] = rel_err(v.grad.cpu().numpy(), ref)
+    with capsys.disabled():
+        print('\ncfg3 B=1024 gradient errors vs fp64 oracle (max-norm relative): ' +
+              ', '.join('%s %.2e' % kv for kv in sorted(errs.items())))
+    for k, e in errs.items():
+        assert e < 1e-4, '%s: %.3e' % (k, e)
