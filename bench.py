@@ -385,6 +385,10 @@ def leg_decompose(ctx, name, cfg, precision, farnn, steps, warmup, batch=0, ref_
         dom_name = 'tc_resident_kernel: all steps of both directions, G1 + G2 + fused epilogues (%s); %d launch(es) per step on ' \
                    'forked chunk streams, time = union of their intervals inside the replayed graph' % (prec, dom_n)
         dom_flops = n_tok * rec_flops_pos
+    elif farnn == 0 and graphed is not None and ops.recurrence_fuses(S, R, farnn, prec) and getattr(m, 'use_cuda_graph', True):
+        dom_name = 'tc_gemm_kernel<EpiH>: step GEMM2 [Q | Hbar] @ [S^T ; W] + state epilogue, ONE direction per launch (%s; the ' \
+                   'forward direction writes the fused alpha*beta label-score operand)' % prec
+        dom_flops = 2.0 * c['B'] * S * (R + S)
     else:
         dom_name = 'tc_gemm_kernel<EpiH>: step GEMM2 [Q | Hbar] @ [S^T ; W] + state epilogue, both directions per launch (%s)' % prec
         dom_flops = 2 * 2.0 * c['B'] * S * (R + S)

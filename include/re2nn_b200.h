@@ -150,6 +150,15 @@ typedef struct re2nn_recurrence_args {
   float* rsave;                /* 2 x L x B x S      reset gate (farnn==2) or NULL                      */
   void* ws;                    /* scratch, >= re2nn_decompose_recurrence_workspace() bytes */
   size_t ws_bytes;
+  /* Fused label-score operand (optional; inference, farnn == 0, tensor-core precisions, per-step path).  When
+   * non-NULL the backward direction runs first and the state epilogue of the FORWARD direction multiplies every
+   * alpha element by the stored beta and writes the product in the precision's operand format
+   * ((B*L) rows x operand_ld(S), split formats: second plane at B*L*ld elements) -- what re2nn_label_scores would
+   * otherwise rebuild by re-reading alpha and beta (model_decompose_single.py:202-205,263-269).  alpha is then never
+   * written and may be NULL; rows past the length are left untouched.  Feed the buffer to re2nn_label_scores_ab.
+   * Size: re2nn_label_scores_ab_bytes().  Ignored (alpha / beta written as usual) when the call takes the resident
+   * kernel: query re2nn_decompose_recurrence_fuses(). */
+  void* ab_out;
 } re2nn_recurrence_args;
 
 size_t re2nn_decompose_recurrence_workspace(const re2nn_recurrence_args* a);
@@ -157,6 +166,8 @@ int re2nn_decompose_recurrence(const re2nn_recurrence_args* a, void* stream);
 /* Number of kernels re2nn_decompose_recurrence launches for this argument block (inference without gates on the
  * tensor-core paths runs ALL steps in one resident kernel; otherwise 2-3 step GEMMs per step). */
 int re2nn_decompose_recurrence_launches(const re2nn_recurrence_args* a);
+/* 1 when a call with these arguments (and a non-NULL ab_out) would write the fused (alpha*beta) operand. */
+int re2nn_decompose_recurrence_fuses(const re2nn_recurrence_args* a);
 /* 1 when the call would take the resident single-launch path (only precision, S, R, farnn and save_for_backward of
  * the block are read): callers use it to decide whether splitting a batch over streams pays off. */
 int re2nn_decompose_recurrence_resident(const re2nn_recurrence_args* a);
@@ -287,6 +298,13 @@ int re2nn_argmax_decode(const float* scores, const int64_t* lengths, const int64
  * the Python loop over the batch (padded rows have stride Lrow, the first L columns are considered). */
 int re2nn_flatten_i64(const int64_t* padded, const int64_t* lengths, const int64_t* offsets, int B, int Lrow,
                       int L, int64_t* flat, void* stream);
+
+/* Label scores from the fused operand written by re2nn_decompose_recurrence (ab_out): scores = ab @ C^T [@ P + b].
+ * ws: re2nn_label_scores_workspace(..) bytes with the same arguments. */
+size_t re2nn_label_scores_ab_bytes(int B, int L, int S, int precision);
+int re2nn_label_scores_ab(const void* ab, int B, int L, int S, const float* C_mat, int C, const float* priority_mat,
+                          const float* priority_bias, int precision, float* scores, void* ws, size_t ws_bytes,
+                          void* stream);
 
 /* ---- CRF Viterbi ------------------------------------------------------------------------------------
  * replaces CRF._viterbi_decode (baselines/crf.py:102-195) plus decode()'s CRF branch

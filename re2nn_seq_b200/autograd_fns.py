@@ -47,12 +47,21 @@ class _DecomposeScores(torch.autograd.Function):
             need_grad = False        # inference-only semiring; backward raises
         vtab, gtab, o = _prepare(consts, p, dense_v, None if need_grad else cache)
         Lpad = x.shape[1] if dense_v is None else dense_v.shape[1]
+        pm, pb = (pr if consts['use_priority'] else (None, None))
+        if consts.get('fuse_scores') and not need_grad and not mx and consts['farnn'] == 0 and not consts['full_pad'] \
+                and consts['precision'] != 'fp32':
+            # decode-only inference: (alpha * beta) comes straight out of the forward direction's epilogue
+            fused = ops.decompose_recurrence_fused(x, lengths, L, vtab, p['S1'], p['S2'], p['wildcard_mat'], o, p['h0'],
+                                                   p['hT'], consts['update_nonlinear'], consts['precision'],
+                                                   v_mode=V_TOKEN if dense_v is None else V_DENSE, Lpad=Lpad)
+            if fused is not None:
+                B, S = lengths.shape[0], p['S1'].shape[0]
+                return ops.label_scores_ab(fused[0], B, L, S, p['C_output_mat'], pm, pb, consts['precision'])
         alpha, beta, saves = ops.decompose_recurrence(
             x, lengths, L, vtab, gtab, p['S1'], p['S2'], p['wildcard_mat'], o, p['h0'], p['hT'],
             p.get('Wss1'), p.get('Wss2'), consts['farnn'], consts['update_nonlinear'], consts['sigmoid_exponent'],
             precision=consts['precision'], v_mode=V_TOKEN if dense_v is None else V_DENSE,
             full_pad=consts['full_pad'], save_for_backward=need_grad, Lpad=Lpad, max_semiring=mx)
-        pm, pb = (pr if consts['use_priority'] else (None, None))
         scores = ops.label_scores(alpha, beta, lengths, p['C_output_mat'], pm, pb, full_pad=consts['full_pad'],
                                   precision='fp32' if mx else consts['precision'])
         if need_grad:

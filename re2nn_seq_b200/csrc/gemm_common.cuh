@@ -28,6 +28,10 @@ struct GemmProblem {
 template <int PREC> struct OperandFmt;
 template <> struct OperandFmt<RE2NN_PREC_FP32> {
   static constexpr int kElemBytes = 4, kPlanes = 1, kLdAlign = 1;
+  __device__ static __forceinline__ void store16(void* base, size_t idx, size_t, const float (&v)[16]) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) ((float*)base)[idx + j] = v[j];
+  }
   __device__ static __forceinline__ void store(void* base, size_t idx, size_t, float v) { ((float*)base)[idx] = v; }
   // conversion unconditional, stores predicated: keeps unrolled epilogue batches branch-free
   __device__ static __forceinline__ void store_if(bool on, void* base, size_t idx, size_t, float v) {
@@ -38,8 +42,24 @@ template <> struct OperandFmt<RE2NN_PREC_FP32> {
     *reinterpret_cast<float4*>((float*)base + idx) = v;
   }
 };
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {      // a -> low half, b -> high half
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
 template <> struct OperandFmt<RE2NN_PREC_BF16> {
   static constexpr int kElemBytes = 2, kPlanes = 1, kLdAlign = 8;
+  // sixteen consecutive elements of one row, idx % 8 == 0 and 16-byte aligned rows: two 16-byte stores
+  __device__ static __forceinline__ void store16(void* base, size_t idx, size_t, const float (&v)[16]) {
+    uint4* d = reinterpret_cast<uint4*>((__nv_bfloat16*)base + idx);
+    d[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    d[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+  }
   __device__ static __forceinline__ void store(void* base, size_t idx, size_t, float v) {
     ((__nv_bfloat16*)base)[idx] = __float2bfloat16_rn(v);
   }
@@ -62,6 +82,17 @@ __device__ __forceinline__ float tf32_hi(float v) {   // round-to-nearest onto t
 }
 template <> struct OperandFmt<RE2NN_PREC_TF32X3> {
   static constexpr int kElemBytes = 4, kPlanes = 2, kLdAlign = 4;
+  __device__ static __forceinline__ void store16(void* base, size_t idx, size_t plane, const float (&v)[16]) {
+    float4* dh = reinterpret_cast<float4*>((float*)base + idx);
+    float4* dl = reinterpret_cast<float4*>((float*)base + idx + plane);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float4 h = make_float4(tf32_hi(v[4 * g]), tf32_hi(v[4 * g + 1]), tf32_hi(v[4 * g + 2]), tf32_hi(v[4 * g + 3]));
+      dh[g] = h;
+      dl[g] = make_float4(tf32_hi(v[4 * g] - h.x), tf32_hi(v[4 * g + 1] - h.y), tf32_hi(v[4 * g + 2] - h.z),
+                          tf32_hi(v[4 * g + 3] - h.w));
+    }
+  }
   __device__ static __forceinline__ void store(void* base, size_t idx, size_t plane, float v) {
     float hi = tf32_hi(v);
     ((float*)base)[idx] = hi;
@@ -86,6 +117,21 @@ template <> struct OperandFmt<RE2NN_PREC_TF32X3> {
 constexpr float kFp16LoScale = 2048.f;
 template <> struct OperandFmt<RE2NN_PREC_FP16X3> {
   static constexpr int kElemBytes = 2, kPlanes = 2, kLdAlign = 8;
+  __device__ static __forceinline__ void store16(void* base, size_t idx, size_t plane, const float (&v)[16]) {
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      h[g] = pack_f16x2(v[2 * g], v[2 * g + 1]);
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h[g]));
+      l[g] = pack_f16x2((v[2 * g] - f.x) * kFp16LoScale, (v[2 * g + 1] - f.y) * kFp16LoScale);
+    }
+    uint4* dh = reinterpret_cast<uint4*>((__half*)base + idx);
+    uint4* dl = reinterpret_cast<uint4*>((__half*)base + idx + plane);
+    dh[0] = make_uint4(h[0], h[1], h[2], h[3]);
+    dh[1] = make_uint4(h[4], h[5], h[6], h[7]);
+    dl[0] = make_uint4(l[0], l[1], l[2], l[3]);
+    dl[1] = make_uint4(l[4], l[5], l[6], l[7]);
+  }
   __device__ static __forceinline__ void store(void* base, size_t idx, size_t plane, float v) {
     const __half hi = __float2half_rn(v);
     ((__half*)base)[idx] = hi;
@@ -150,9 +196,13 @@ struct StepParams {
   float* HbarSaveNext[2];                         // training on tensor cores: fp32 copy of the next operand
   float* HbarSaveCur[2];                          // training on tensor cores, farnn==2: fp32 copy of this step's operand
   int dir;                                        // set by bind(): the direction this CTA works on
+  int dir_base;                                   // single-direction launches: tile direction index z means z + dir_base
+  void* AB; int ldab; size_t ab_plane;            // fused label-score operand (alpha * beta), (B*L) x ldab
+  const float* beta_in;                           // beta as written by the backward direction (fused scoring)
   // Move direction z into slot 0 so the epilogue addresses plain members (registers after inlining)
   // instead of indexing the constant bank with a run-time z for every element.
-  __device__ __forceinline__ void bind(int z) {
+  __device__ __forceinline__ void bind(int zt) {
+    const int z = zt + dir_base;
     dir = z;
     hinit[0] = hinit[z]; Q[0] = Q[z]; Hbar_next[0] = Hbar_next[z]; Hbar_cur[0] = Hbar_cur[z];
     Hst[0] = Hst[z]; H[0] = H[z]; Z[0] = Z[z]; Rg[0] = Rg[z]; out[0] = out[z];
@@ -177,7 +227,7 @@ __device__ __forceinline__ RowCtx make_row(const StepParams& p, int z, int m) {
 
 // is any row of 128-row tile `mt` still alive at this step?  (one load; every warp role can ask independently)
 __device__ __forceinline__ bool tile_alive(const StepParams& p, int z, int mt) {
-  return p.full_pad || p.k <= __ldg(p.tile_last[z] + mt);
+  return p.full_pad || p.k <= __ldg(p.tile_last[z + p.dir_base] + mt);
 }
 
 // Every epilogue functor is split so the mainloops can (a) hoist per-column constants, (b) put all of a
@@ -204,6 +254,31 @@ template <int PREC, bool TRAIN = false> struct EpiQ {
   __device__ __forceinline__ void apply(const Col& c, const RowCtx& r, int m, int n, float acc, const Pre& pre) const {
     store(c, r, m, n, compute(c, acc, pre), acc, pre);
   }
+  // ---- quad form (tc_epilogue_quads): four consecutive columns nb .. nb+3 of row m per call -----------------------
+  static constexpr bool kRows = !TRAIN && PREC != RE2NN_PREC_FP32;
+  __device__ __forceinline__ bool rows_vec() const {       // 16-byte vector access to the gathered rows is legal
+    return (p.R & 3) == 0 && (reinterpret_cast<uintptr_t>(p.vtab) & 15) == 0;
+  }
+  __device__ __forceinline__ float4 col4(int, int, bool) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ float4 pre4(const RowCtx& r, int, int nb, int ncols, bool vec) const {
+    const float* src = p.vtab + (size_t)((uint32_t)r.vrow * (uint32_t)p.R + (uint32_t)nb);
+    if (vec && ncols == 4) return __ldg(reinterpret_cast<const float4*>(src));
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ncols > 0) v.x = __ldg(src);
+    if (ncols > 1) v.y = __ldg(src + 1);
+    if (ncols > 2) v.z = __ldg(src + 2);
+    if (ncols > 3) v.w = __ldg(src + 3);
+    return v;
+  }
+  __device__ __forceinline__ void apply4(const RowCtx&, int m, int nb, int ncols, bool, float4 acc, float4 v, float4) const {
+    const float4 q = make_float4(acc.x * v.x, acc.y * v.y, acc.z * v.z, acc.w * v.w);
+    const size_t idx = (size_t)((uint32_t)m * (uint32_t)p.ldq + (uint32_t)nb);
+    if (nb + 4 <= p.ldq) OperandFmt<PREC>::store4(p.Q[0], idx, p.q_plane, q);      // columns past R are K padding
+    else {
+      const float qa[4] = {q.x, q.y, q.z, q.w};
+      for (int j = 0; j < ncols; ++j) OperandFmt<PREC>::store(p.Q[0], idx + j, p.q_plane, qa[j]);
+    }
+  }
   __device__ __forceinline__ void store(const Col&, const RowCtx& r, int m, int n, float q, float acc, const Pre&) const {
     OperandFmt<PREC>::store(p.Q[0], (uint32_t)m * (uint32_t)p.ldq + (uint32_t)n, p.q_plane, q);
     if constexpr (TRAIN) {
@@ -216,7 +291,9 @@ template <int PREC, bool TRAIN = false> struct EpiQ {
 // E2: h_next = phi((Q @ S2^T + Hbar @ W) [* o]) ; gate blend ; write alpha/beta + next operands
 // (model_decompose_single.py:172-173,177-199).  NL / FARNN >= 0 fix update_nonlinear / farnn at compile
 // time (the hot configurations), -1 reads them from StepParams.
-template <int PREC, int NL = -1, int FARNN = -1, bool TRAIN = false> struct EpiH {
+// FUSE (forward direction, farnn == 0, inference): instead of the alpha row write alpha * beta in operand format
+// for the label-score GEMM (beta was completed by the backward direction, which ran first).
+template <int PREC, int NL = -1, int FARNN = -1, bool TRAIN = false, bool FUSE = false> struct EpiH {
   static constexpr bool kFast = PREC == RE2NN_PREC_BF16;
   StepParams p;
   __device__ __forceinline__ EpiH for_dir(int z) const { EpiH e = *this; e.p.bind(z); return e; }
@@ -225,12 +302,76 @@ template <int PREC, int NL = -1, int FARNN = -1, bool TRAIN = false> struct EpiH
   __device__ __forceinline__ int farnn() const { return FARNN >= 0 ? FARNN : p.farnn; }
   __device__ __forceinline__ int nl() const { return NL >= 0 ? NL : p.nl; }
   __device__ __forceinline__ Col col(int n) const { return Col{__ldg(p.o + n), 0.f}; }
-  __device__ __forceinline__ Pre prefetch(const RowCtx&, int m, int n) const {
+  __device__ __forceinline__ Pre prefetch(const RowCtx& r, int m, int n) const {
     if (farnn() >= 1) {
       const uint32_t si = (uint32_t)m * (uint32_t)p.S + (uint32_t)n;
       return Pre{p.Z[0][si], p.H[0][si]};
     }
+    if constexpr (FUSE)      // rows without an output read (and drop) their row 0
+      return Pre{__ldg(p.beta_in + ((size_t)m * (uint32_t)p.L + (uint32_t)max(r.orow, 0)) * (uint32_t)p.S + (uint32_t)n), 0.f};
     return Pre{0.f, 0.f};
+  }
+  // ---- quad form (tc_epilogue_quads), plain recurrence only (no gates, no training saves) ---------------------------
+  static constexpr bool kRows = !TRAIN && FARNN == 0 && PREC != RE2NN_PREC_FP32;
+  __device__ __forceinline__ bool rows_vec() const {
+    bool ok = (p.S & 3) == 0 && (reinterpret_cast<uintptr_t>(p.o) & 15) == 0;
+    if (FUSE) ok = ok && (reinterpret_cast<uintptr_t>(p.beta_in) & 15) == 0;
+    else ok = ok && (reinterpret_cast<uintptr_t>(p.out[0]) & 15) == 0;
+    return ok;
+  }
+  __device__ __forceinline__ float4 col4(int nb, int ncols, bool vec) const {       // o[nb .. nb+3]
+    if (vec && ncols == 4) return __ldg(reinterpret_cast<const float4*>(p.o + nb));
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ncols > 0) v.x = __ldg(p.o + nb);
+    if (ncols > 1) v.y = __ldg(p.o + nb + 1);
+    if (ncols > 2) v.z = __ldg(p.o + nb + 2);
+    if (ncols > 3) v.w = __ldg(p.o + nb + 3);
+    return v;
+  }
+  __device__ __forceinline__ float4 pre4(const RowCtx& r, int m, int nb, int ncols, bool vec) const {
+    if constexpr (FUSE) {      // beta row of this position (rows without an output read and drop their row 0)
+      const float* src = p.beta_in + ((size_t)m * (uint32_t)p.L + (uint32_t)max(r.orow, 0)) * (uint32_t)p.S + (uint32_t)nb;
+      if (vec && ncols == 4) return __ldg(reinterpret_cast<const float4*>(src));
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ncols > 0) v.x = __ldg(src);
+      if (ncols > 1) v.y = __ldg(src + 1);
+      if (ncols > 2) v.z = __ldg(src + 2);
+      if (ncols > 3) v.w = __ldg(src + 3);
+      return v;
+    }
+    return make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __device__ __forceinline__ void apply4(const RowCtx& r, int m, int nb, int ncols, bool vec, float4 acc, float4 pre, float4 oc) const {
+    float4 hn, nx;
+    if (p.dir == 0) { acc.x *= oc.x; acc.y *= oc.y; acc.z *= oc.z; acc.w *= oc.w; }
+    hn.x = apply_nl_t<kFast>(acc.x, nl()); hn.y = apply_nl_t<kFast>(acc.y, nl());
+    hn.z = apply_nl_t<kFast>(acc.z, nl()); hn.w = apply_nl_t<kFast>(acc.w, nl());
+    nx = hn;
+    if (p.dir == 1) { nx.x *= oc.x; nx.y *= oc.y; nx.z *= oc.z; nx.w *= oc.w; }
+    const size_t hidx = (size_t)((uint32_t)m * (uint32_t)p.ldh + (uint32_t)nb);
+    if (nb + 4 <= p.ldh) OperandFmt<PREC>::store4(p.Hbar_next[0], hidx, p.h_plane, nx);      // columns past S are K padding
+    else {
+      const float na[4] = {nx.x, nx.y, nx.z, nx.w};
+      for (int j = 0; j < ncols; ++j) OperandFmt<PREC>::store(p.Hbar_next[0], hidx + j, p.h_plane, na[j]);
+    }
+    if (r.orow < 0) return;
+    const size_t orow = (size_t)m * (uint32_t)p.L + (uint32_t)r.orow;
+    if constexpr (FUSE) {
+      const float4 ab = make_float4(hn.x * pre.x, hn.y * pre.y, hn.z * pre.z, hn.w * pre.w);
+      const size_t aidx = orow * (uint32_t)p.ldab + (uint32_t)nb;
+      if (nb + 4 <= p.ldab) OperandFmt<PREC>::store4(p.AB, aidx, p.ab_plane, ab);
+      else {
+        const float aa[4] = {ab.x, ab.y, ab.z, ab.w};
+        for (int j = 0; j < ncols; ++j) OperandFmt<PREC>::store(p.AB, aidx + j, p.ab_plane, aa[j]);
+      }
+    } else {
+      float* dst = p.out[0] + orow * (uint32_t)p.S + (uint32_t)nb;
+      if (vec && ncols == 4) *reinterpret_cast<float4*>(dst) = hn;
+      else {
+        const float ha[4] = {hn.x, hn.y, hn.z, hn.w};
+        for (int j = 0; j < ncols; ++j) dst[j] = ha[j];
+      }
+    }
   }
   // compute() is pure arithmetic so a mainloop can evaluate a batch of rows back to back (independent MUFU
   // chains) before any store is issued; store() does the memory side.
@@ -243,7 +384,7 @@ template <int PREC, int NL = -1, int FARNN = -1, bool TRAIN = false> struct EpiH
   __device__ __forceinline__ void apply(const Col& c, const RowCtx& r, int m, int n, float acc, const Pre& pre) const {
     store(c, r, m, n, compute(c, acc, pre), acc, pre);
   }
-  __device__ __forceinline__ void store(const Col& c, const RowCtx& r, int m, int n, float hnew, float acc, const Pre&) const {
+  __device__ __forceinline__ void store(const Col& c, const RowCtx& r, int m, int n, float hnew, float acc, const Pre& pre) const {
     const uint32_t hi = (uint32_t)m * (uint32_t)p.ldh + (uint32_t)n;
     const uint32_t si = (uint32_t)m * (uint32_t)p.S + (uint32_t)n;
     if constexpr (TRAIN) {
@@ -262,14 +403,31 @@ template <int PREC, int NL = -1, int FARNN = -1, bool TRAIN = false> struct EpiH
     }
     if (farnn() <= 1) OperandFmt<PREC>::store(p.Hbar_next[0], hi, p.h_plane, p.dir == 1 ? hnew * c.a : hnew);
     // address unconditionally, store conditionally: keeps the 16-row batches of the tcgen05 epilogue branch-free
-    float* dst = p.out[0] + (size_t)((uint32_t)m * (uint32_t)p.L + (uint32_t)(r.orow & 0x7fffffff)) * (uint32_t)p.S + (uint32_t)n;
-    if (r.orow >= 0) *dst = hnew;
+    if constexpr (FUSE) {
+      const size_t row = (size_t)m * (uint32_t)p.L + (uint32_t)max(r.orow, 0);
+      OperandFmt<PREC>::store_if(r.orow >= 0, p.AB, row * (uint32_t)p.ldab + (uint32_t)n, p.ab_plane, hnew * pre.a);
+    } else {
+      float* dst = p.out[0] + (size_t)((uint32_t)m * (uint32_t)p.L + (uint32_t)(r.orow & 0x7fffffff)) * (uint32_t)p.S + (uint32_t)n;
+      if (r.orow >= 0) *dst = hnew;
+    }
+  }
+};
+
+// Epilogues whose prefetch() reads a COLD array (one touch per element, straight from HBM) ask the mainloop to pull
+// the lines of a tile into L2 while its MMAs are still running: l2_line(row ctx, m, n) = address of the 128-byte line
+// holding column n of row m.  Default: nothing to do.
+template <class Epi> struct EpiL2Prefetch { static constexpr bool kOn = false; };
+template <int PREC, int NL, int FARNN, bool TRAIN> struct EpiL2Prefetch<EpiH<PREC, NL, FARNN, TRAIN, true>> {
+  static constexpr bool kOn = true;
+  __device__ static __forceinline__ const void* line(const EpiH<PREC, NL, FARNN, TRAIN, true>& e, const RowCtx& r, int m, int n) {
+    return e.p.beta_in + ((size_t)m * (uint32_t)e.p.L + (uint32_t)max(r.orow, 0)) * (uint32_t)e.p.S + (uint32_t)n;
   }
 };
 
 // EG: zt / rt gates and the reset-blended operand (model_decompose_single.py:147-157)
 // columns [0,S) = update gate pre-activation, [S,2S) = reset gate pre-activation (farnn==2)
 template <int PREC, bool TRAIN = false> struct EpiGate {
+  static constexpr bool kRows = false;
   static constexpr bool kFast = PREC == RE2NN_PREC_BF16;
   // inference on the split formats: few-ulp branch-free sigmoid; training keeps the exact one (its backward
   // differentiates the saved gate values, parity against the float64 oracle at 1e-4)
@@ -315,6 +473,7 @@ template <int PREC, bool TRAIN = false> struct EpiGate {
 
 // plain store epilogue (gate table, label scores, generic C = A*B [+ bias]); used off the step loop
 struct EpiStore {
+  static constexpr bool kRows = false;
   float* C;
   int ldc;
   const float* bias;      // per-column or NULL
@@ -334,6 +493,7 @@ struct EpiStore {
 
 // token table epilogue: table = V_embed*beta + phi(acc)*(1-beta)     (model_decompose.py:226-239)
 struct EpiTokenTable {
+  static constexpr bool kRows = false;
   float* table;
   const float* V_embed;
   const float* beta_vec;

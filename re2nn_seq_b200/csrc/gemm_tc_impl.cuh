@@ -15,6 +15,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "gemm_common.cuh"
 
@@ -283,9 +284,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// does the epilogue functor offer the row-per-thread form (pre16 / apply16)?
+template <class E, class = void> struct EpiHasRows { static constexpr bool value = false; };
+template <class E> struct EpiHasRows<E, std::void_t<decltype(E::kRows)>> { static constexpr bool value = E::kRows; };
+
 constexpr int kTcEpiWarps = 8;                       // two warps per TMEM lane quarter (16 measured slower: spills, fewer stages)
 constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;
-constexpr int kTcTbufBytes = kTcEpiWarps * 32 * 33 * 4;   // per-warp 32x33 fp32 transpose buffers
+constexpr int kTcTbufWords = 32 * 36;                     // per-warp transpose buffer: 32 rows, pitch 36 words (33 used by the chunked form)
+constexpr int kTcTbufBytes = kTcEpiWarps * kTcTbufWords * 4;
 constexpr int kTcCtxWords = 64;                          // per-warp row contexts: int vrow[32] | int orow[32]
 constexpr int kTcCtxBytes = kTcEpiWarps * kTcCtxWords * 4;
 constexpr int kTcSmemLimit = 227 * 1024;
@@ -342,6 +358,19 @@ __device__ __forceinline__ void tc_epilogue_chunks(const Epi epi, int M, int N, 
   const int* ctx_o = ctx + 32;
   bool acc_ready = false;
   const bool stamp = trace != nullptr && lane == 0;
+  if constexpr (EpiL2Prefetch<Epi>::kOn) {
+    // this warp's chunks of its 32 rows into L2 now -- the tile's MMAs are still running, the loads of phase 1 then
+    // hit L2 instead of paying the HBM latency once per chunk on the epilogue's critical path
+    const int nchunks = (bn + 31) / 32;
+    for (int idx = lane; idx < 32 * nchunks; idx += 32) {
+      const int i = idx / nchunks, ch = idx - i * nchunks;
+      const int n = n0 + ch * 32;
+      if ((ch % PARTS) == half && i < nrows && n < N) {
+        const void* ptr = EpiL2Prefetch<Epi>::line(epi, RowCtx{ctx[i], ctx_o[i], ctx_o[i] >= 0}, mrow0 + i, n);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+      }
+    }
+  }
 #pragma unroll 1
   for (int c0 = half * 32; c0 < bn; c0 += 32 * PARTS) {
     if (n0 + c0 >= N) break;     // warp-uniform
@@ -420,6 +449,91 @@ __device__ __forceinline__ void tc_epilogue_chunks(const Epi epi, int M, int N, 
           }
         }
       }
+    }
+    __syncwarp();
+  }
+  if (!acc_ready) {
+    mbar_wait(tfull, parity);
+    tc_fence_after();
+  }
+}
+
+// Quad epilogue.  tcgen05.ld hands lane i the 32 columns of accumulator row i; the block goes through the warp's
+// shared-memory transpose buffer as 16-byte pieces (row pitch 36 words: conflict-free both ways) and comes back with
+// lane = (row r0 + lane / 8, columns 4 * (lane % 8) .. + 3).  Every global access is then a 16-byte vector and a warp
+// request covers four FULL 128-byte row segments: coalesced like the element-per-lane form of tc_epilogue_chunks but
+// with a quarter of the load / store / address instructions, packed conversions, and no per-element predication.
+// (A thread-per-row variant without the transpose was measured 25-45 % SLOWER than the chunked form: 32 lanes x 16
+// bytes in 32 different lines serialise in the L1 tag stage.)
+// The warp takes the 32-column chunks half, half + PARTS, ... of its TMEM lane quarter, as the chunked form does.
+constexpr int kTbufPitch = 36;
+template <bool TWOACC, int PARTS, class Epi>
+__device__ __forceinline__ void tc_epilogue_quads(const Epi epi, int M, int N, int mrow0, int n0, int bn, uint32_t tmem_rows,
+                                                  uint32_t corr_off, int half, int lane, float* tbuf, const int* ctx,
+                                                  uint32_t tfull, uint32_t parity) {
+  const int nrows = min(32, M - mrow0);
+  const int* ctx_o = ctx + 32;
+  const bool vec = epi.rows_vec();
+  const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+  bool acc_ready = false;
+  if constexpr (EpiL2Prefetch<Epi>::kOn) {
+    const int nchunks = (bn + 31) / 32;
+    for (int idx = lane; idx < 32 * nchunks; idx += 32) {
+      const int i = idx / nchunks, ch = idx - i * nchunks;
+      const int n = n0 + ch * 32;
+      if ((ch % PARTS) == half && i < nrows && n < N) {
+        const void* ptr = EpiL2Prefetch<Epi>::line(epi, RowCtx{ctx[i], ctx_o[i], ctx_o[i] >= 0}, mrow0 + i, n);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+      }
+    }
+  }
+#pragma unroll 1
+  for (int c0 = half * 32; c0 < bn; c0 += 32 * PARTS) {
+    if (n0 + c0 >= N) break;     // warp-uniform
+    const int nb = n0 + c0 + c4;
+    const int ncols = max(0, min(4, min(N - nb, bn - (c0 + c4))));
+    const float4 oc = epi.col4(nb, ncols, vec);
+    // phase 1: the gathers of all eight row groups in flight before the accumulator is needed
+    float4 pre[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = 4 * k + rsub;
+      pre[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < nrows && ncols > 0) pre[k] = epi.pre4(RowCtx{ctx[i], ctx_o[i], ctx_o[i] >= 0}, mrow0 + i, nb, ncols, vec);
+    }
+    if (!acc_ready) {
+      mbar_wait(tfull, parity);
+      tc_fence_after();
+      acc_ready = true;
+    }
+    {
+      uint32_t r[32];
+      tmem_ld32(tmem_rows + (uint32_t)c0, r);
+      float4* row = reinterpret_cast<float4*>(tbuf + lane * kTbufPitch);
+      if (TWOACC) {
+        uint32_t r2[32];
+        tmem_ld32(tmem_rows + corr_off + (uint32_t)c0, r2);
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          row[g] = make_float4(fmaf(__uint_as_float(r2[4 * g]), 1.f / kFp16LoScale, __uint_as_float(r[4 * g])),
+                               fmaf(__uint_as_float(r2[4 * g + 1]), 1.f / kFp16LoScale, __uint_as_float(r[4 * g + 1])),
+                               fmaf(__uint_as_float(r2[4 * g + 2]), 1.f / kFp16LoScale, __uint_as_float(r[4 * g + 2])),
+                               fmaf(__uint_as_float(r2[4 * g + 3]), 1.f / kFp16LoScale, __uint_as_float(r[4 * g + 3])));
+      } else {
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          row[g] = make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
+                               __uint_as_float(r[4 * g + 3]));
+      }
+    }
+    __syncwarp();
+    // phase 2: lane = (row group member, column quad)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = 4 * k + rsub;
+      const float4 acc = *reinterpret_cast<const float4*>(tbuf + i * kTbufPitch + c4);
+      if (i < nrows && ncols > 0)
+        epi.apply4(RowCtx{ctx[i], ctx_o[i], ctx_o[i] >= 0}, mrow0 + i, nb, ncols, vec, acc, pre[k], oc);
     }
     __syncwarp();
   }
@@ -629,7 +743,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int ew = warp - 2;                // epilogue warp index 0..7
     const int half = ew >> 2;               // which interleaved set of 32-column chunks this warp takes
-    float* tbuf = tbuf_base + ew * (32 * 33);
+    float* tbuf = tbuf_base + ew * kTcTbufWords;
     int* ctx = ctx_base + ew * kTcCtxWords;  // int vrow[32] | short orow[32]
     int tcount = 0;
     griddep_wait();                         // state / gate buffers are written by the previous kernel
@@ -650,8 +764,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
         ctx[32 + lane] = mine.orow;
       }
       __syncwarp();
-      tc_epilogue_chunks<TWOACC>(epi, L.M, L.N, mrow0, n0, bn, tmem_acc + ((uint32_t)(q * 32) << 16), (uint32_t)BN, half, lane,
-                                 tbuf, ctx, tfull_bar(as), aph, (tcount == 0 && ew == 0) ? trace : nullptr);
+      if constexpr (EpiHasRows<Epi>::value)
+        tc_epilogue_quads<TWOACC, kTcEpiWarps / 4>(epi, L.M, L.N, mrow0, n0, bn, tmem_acc + ((uint32_t)(q * 32) << 16), (uint32_t)BN,
+                                                   half, lane, tbuf, ctx, tfull_bar(as), aph);
+      else
+        tc_epilogue_chunks<TWOACC>(epi, L.M, L.N, mrow0, n0, bn, tmem_acc + ((uint32_t)(q * 32) << 16), (uint32_t)BN, half, lane,
+                                   tbuf, ctx, tfull_bar(as), aph, (tcount == 0 && ew == 0) ? trace : nullptr);
       // this warp is done reading the accumulator set: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();

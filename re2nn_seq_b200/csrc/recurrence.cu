@@ -259,6 +259,45 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
     }
   }
 
+  if constexpr (PREC != RE2NN_PREC_FP32) {
+    // Fused label-score operand (ab_out): the backward direction first (beta complete), then the forward direction
+    // whose state epilogue writes alpha * beta in operand format -- alpha itself is never materialised and the
+    // (alpha, beta) re-read of re2nn_label_scores disappears.  Single-direction launches (ndir = 1, dir_base = z).
+    if (a.ab_out != nullptr && !a.save_for_backward && a.farnn == 0 && !a.full_pad) {
+      p.AB = a.ab_out; p.ldab = ldh; p.ab_plane = (size_t)B * L * ldh; p.beta_in = a.beta;
+      for (int z = 0; z < 2; ++z) { p.Z[z] = w.Z[z]; p.Rg[z] = nullptr; }
+      std::unique_ptr<TcLaunch[]> maps(new TcLaunch[8]);       // [z][par][g1 | g2]
+      GemmProblem g1d[2][2], g2d[2][2];
+      for (int z = 0; z < 2; ++z)
+        for (int par = 0; par < 2; ++par) {
+          g1d[z][par] = g_1[par]; g1d[z][par].ndir = 1; g1d[z][par].seg[0][0] = g_1[par].seg[z][0];
+          g2d[z][par] = g_2[par]; g2d[z][par].ndir = 1;
+          g2d[z][par].seg[0][0] = g_2[par].seg[z][0]; g2d[z][par].seg[0][1] = g_2[par].seg[z][1];
+          if (int rc = tc_make_launch<PREC>(g1d[z][par], &maps[(z * 2 + par) * 2])) return rc;
+          if (int rc = tc_make_launch<PREC>(g2d[z][par], &maps[(z * 2 + par) * 2 + 1])) return rc;
+        }
+      const bool th = a.update_nonlinear == RE2NN_NL_TANH;
+      for (int zi = 0; zi < 2; ++zi) {
+        const int z = 1 - zi;                                    // backward direction first
+        p.dir_base = z;
+        for (int k = 0; k < L; ++k) {
+          p.k = k;
+          const int par = k & 1;
+          for (int zz = 0; zz < 2; ++zz) { p.Hbar_cur[zz] = w.Hbar[par][zz]; p.Hbar_next[zz] = w.Hbar[par ^ 1][zz]; }
+          RE2NN_CUDA((launch_gemm<PREC>(1, g1d[z][par], EpiQ<PREC>{p}, &maps[(z * 2 + par) * 2], st)));
+          const TcLaunch* m2 = &maps[(z * 2 + par) * 2 + 1];
+          cudaError_t e;
+          if (z == 1) e = th ? launch_gemm<PREC>(2, g2d[z][par], EpiH<PREC, RE2NN_NL_TANH, 0>{p}, m2, st)
+                             : launch_gemm<PREC>(2, g2d[z][par], EpiH<PREC, -1, 0>{p}, m2, st);
+          else e = th ? launch_gemm<PREC>(2, g2d[z][par], EpiH<PREC, RE2NN_NL_TANH, 0, false, true>{p}, m2, st)
+                      : launch_gemm<PREC>(2, g2d[z][par], EpiH<PREC, -1, 0, false, true>{p}, m2, st);
+          RE2NN_CUDA(e);
+        }
+      }
+      return 0;
+    }
+  }
+
   TcRecurrenceMaps* tm = nullptr;
   std::unique_ptr<TcRecurrenceMaps> tm_hold;
   if constexpr (PREC != RE2NN_PREC_FP32) {
@@ -407,6 +446,23 @@ static int label_scores_tc(const float* alpha, const float* beta, const int64_t*
 }
 
 template <int PREC>
+static int label_scores_ab_tc(const void* ab, size_t M, int S, const float* C_mat, int C, float* out, char* ws, cudaStream_t st) {
+  const int ld = operand_ld(PREC, S);
+  void* Bop = ws;
+  const size_t pa = M * ld, pb = (size_t)C * ld;
+  convert_weight_kernel<PREC><<<(unsigned)(((size_t)C * ld + 255) / 256), 256, 0, st>>>(C_mat, C, S, S, 0, Bop, ld, pb, 0);
+  RE2NN_LAUNCH_CHECK();
+  GemmProblem g;
+  memset(&g, 0, sizeof(g));
+  g.M = (int)M; g.N = C; g.nseg = 1; g.ndir = 1;
+  g.seg[0][0] = GemmSeg{ab, Bop, ld, ld, S, 1, pa, pb};
+  TcLaunch Lc;
+  if (int rc = tc_make_launch<PREC>(g, &Lc)) return rc;
+  RE2NN_CUDA((launch_tc_gemm<PREC>(g, EpiStore{out, C, nullptr}, &Lc, st)));
+  return 0;
+}
+
+template <int PREC>
 static int gemm_nt_tc(const float* A, const float* B, int M, int N, int K, float* C, void* ws, cudaStream_t st) {
   const int ld = operand_ld(PREC, K);
   void* Ao = ws;
@@ -528,6 +584,16 @@ static bool takes_resident_path(const re2nn_recurrence_args& a) {
   return resident_supported(planes, a.S, a.R, a.precision != RE2NN_PREC_BF16);
 }
 
+// does a call with ab_out set write the fused (alpha * beta) operand?  (mirrors the test in run_recurrence)
+static bool decompose_fuses(const re2nn_recurrence_args& a) {
+  return a.precision != RE2NN_PREC_FP32 && !a.save_for_backward && a.farnn == 0 && !a.full_pad && !takes_resident_path(a);
+}
+
+int re2nn_decompose_recurrence_fuses(const re2nn_recurrence_args* a) {
+  if (!a) return 0;
+  return decompose_fuses(*a) ? 1 : 0;
+}
+
 int re2nn_decompose_recurrence_resident(const re2nn_recurrence_args* a) {
   if (!a) return 0;
   return takes_resident_path(*a) ? 1 : 0;
@@ -538,7 +604,8 @@ int re2nn_decompose_recurrence_launches(const re2nn_recurrence_args* a) {
   int n = 2;                                                     // tile_last + rec_init
   if (a->precision == RE2NN_PREC_FP32) n += a->farnn == 2 ? 1 : 0;   // [Wss1 | Wss2] concat
   else n += 6 + a->farnn;                                        // operand-format copies of the weights
-  n += takes_resident_path(*a) ? 1 : a->L * (2 + (a->farnn >= 1 ? 1 : 0));
+  if (a->ab_out && decompose_fuses(*a)) n += a->L * 4;          // single-direction launches, two directions
+  else n += takes_resident_path(*a) ? 1 : a->L * (2 + (a->farnn >= 1 ? 1 : 0));
   return n;
 }
 
@@ -551,7 +618,8 @@ int re2nn_decompose_recurrence(const re2nn_recurrence_args* a, void* stream) {
   RE2NN_CHECK(a->update_nonlinear >= RE2NN_NL_NONE && a->update_nonlinear <= RE2NN_NL_RELUTANH,
               "decompose_recurrence: unsupported update_nonlinear %d", a->update_nonlinear);
   RE2NN_CHECK(a->v_mode == RE2NN_V_DENSE || a->x != nullptr, "decompose_recurrence: token mode needs x");
-  RE2NN_CHECK(a->lengths && a->vtab && a->S1 && a->S2 && a->W && a->o && a->h0 && a->hT && a->alpha && a->beta,
+  RE2NN_CHECK(a->lengths && a->vtab && a->S1 && a->S2 && a->W && a->o && a->h0 && a->hT && a->beta &&
+                  (a->alpha || (a->ab_out && decompose_fuses(*a))),
               "decompose_recurrence: null tensor");
   RE2NN_CHECK(a->farnn == 0 || (a->gtab && a->Wss1), "decompose_recurrence: farnn>=1 needs gtab and Wss1");
   RE2NN_CHECK(a->farnn < 2 || a->Wss2, "decompose_recurrence: farnn==2 needs Wss2");
@@ -627,6 +695,41 @@ int re2nn_gate_table(const float* vtab, int rows, int R, int S, int farnn, const
     g.seg[0][0] = GemmSeg{vtab, gi == 0 ? Wrs1 : Wrs2, R, S, R, 0, 0, 0};
     EpiStore epi{gate + (size_t)gi * S, ldg, gi == 0 ? bs1 : bs2};
     RE2NN_CUDA(launch_simt_gemm(g, epi, ALoadPlain{}, (cudaStream_t)stream));
+  }
+  return 0;
+}
+
+size_t re2nn_label_scores_ab_bytes(int B, int L, int S, int precision) {
+  if (precision == RE2NN_PREC_FP32) return 0;
+  return operand_bytes(precision, (size_t)B * L, S);
+}
+
+int re2nn_label_scores_ab(const void* ab, int B, int L, int S, const float* C_mat, int C, const float* priority_mat,
+                          const float* priority_bias, int precision, float* scores, void* ws, size_t ws_bytes,
+                          void* stream) {
+  RE2NN_CHECK(ab && C_mat && scores && B > 0 && L > 0 && S > 0 && C > 0, "label_scores_ab: bad arguments");
+  RE2NN_CHECK(precision != RE2NN_PREC_FP32, "label_scores_ab: the fused operand exists for the tensor-core precisions only");
+  RE2NN_CHECK(re2nn_has_tcgen05(), "label_scores_ab: tcgen05 path needs an sm_100 device");
+  const size_t need = 256 + (priority_mat ? align_up((size_t)B * L * C * 4, 256) : 0) + operand_bytes(precision, C, S);
+  RE2NN_CHECK(ws && ws_bytes >= need, "label_scores_ab: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* wp = (char*)ws;
+  float* raw = scores;
+  if (priority_mat) {
+    raw = (float*)wp;
+    wp += align_up((size_t)B * L * C * 4, 256);
+  }
+  const size_t M = (size_t)B * L;
+  int rc = precision == RE2NN_PREC_BF16 ? label_scores_ab_tc<RE2NN_PREC_BF16>(ab, M, S, C_mat, C, raw, wp, st)
+           : precision == RE2NN_PREC_FP16X3 ? label_scores_ab_tc<RE2NN_PREC_FP16X3>(ab, M, S, C_mat, C, raw, wp, st)
+                                            : label_scores_ab_tc<RE2NN_PREC_TF32X3>(ab, M, S, C_mat, C, raw, wp, st);
+  if (rc) return rc;
+  if (priority_mat) {
+    GemmProblem g;
+    memset(&g, 0, sizeof(g));
+    g.M = B * L; g.N = C; g.nseg = 1; g.ndir = 1;
+    g.seg[0][0] = GemmSeg{raw, priority_mat, C, C, C, 0, 0, 0};
+    RE2NN_CUDA(launch_simt_gemm(g, EpiStore{scores, C, priority_bias}, ALoadPlain{}, st));
   }
   return 0;
 }

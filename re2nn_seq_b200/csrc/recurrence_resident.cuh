@@ -39,9 +39,9 @@ constexpr int kResEpiWarps = 12;        // at most three epilogue warps per TMEM
 // spill at the 128 registers twelve warps leave, so the gated kernels run 8
 __host__ __device__ constexpr int resident_epi_warps(int farnn) { return farnn == 0 ? 12 : 8; }
 constexpr int kResThreads = 64 + 32 * kResEpiWarps;
-constexpr int kResTbufBytes = kResEpiWarps * 32 * 33 * 4;
+constexpr int kResTbufBytes = kResEpiWarps * kTcTbufWords * 4;
 constexpr int kResCtxBytes = kResEpiWarps * kTcCtxWords * 4;
-constexpr int kResTbufPerStage = 7;     // 7 x 4224 B fit the 32 KB A region (two planes) of one stage
+constexpr int kResTbufPerStage = 7;     // 7 x 4608 B fit the 32 KB A region (two planes) of one stage
 constexpr uint32_t kResCorrOff = 256;   // TMEM column of the second (residual) accumulator of the fp16 split
 
 template <int PREC, int NL, int FARNN>
@@ -247,8 +247,8 @@ __global__ void __launch_bounds__(64 + 32 * resident_epi_warps(FARNN), 1) tc_res
     // ---- epilogue warps: warp w may touch TMEM lanes 32*(w%4) .. +31 ------------------------------------------
     const int q = warp & 3, ew = warp - 2, half = ew >> 2;
     float* tbuf = RL.alias_tbuf ? reinterpret_cast<float*>(gen_base + (size_t)(ew / kResTbufPerStage) * stage_bytes) +
-                                      (ew % kResTbufPerStage) * (32 * 33)
-                                : tbuf_base + ew * (32 * 33);
+                                      (ew % kResTbufPerStage) * kTcTbufWords
+                                : tbuf_base + ew * kTcTbufWords;
     int* ctx = ctx_base + ew * kTcCtxWords;
     const uint32_t tmem_rows = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t ready_mine = mapa_shared(ready_bar, (uint32_t)crank), ready_peer = mapa_shared(ready_bar, (uint32_t)(crank ^ 1));
@@ -298,13 +298,21 @@ __global__ void __launch_bounds__(64 + 32 * resident_epi_warps(FARNN), 1) tc_res
             release_and_publish();
           }
         }
-        tc_epilogue_chunks<TWOACC, EW / 4>(e1, M, R, mrow0, crank * bn1, bn1, tmem_rows, kResCorrOff, half, lane, tbuf, ctx,
-                                   tfull_bar, acc & 1u, nullptr);
+        if constexpr (EpiHasRows<EpiQ<PREC>>::value)
+          tc_epilogue_quads<TWOACC, EW / 4>(e1, M, R, mrow0, crank * bn1, bn1, tmem_rows, kResCorrOff, half, lane, tbuf, ctx,
+                                            tfull_bar, acc & 1u);
+        else
+          tc_epilogue_chunks<TWOACC, EW / 4>(e1, M, R, mrow0, crank * bn1, bn1, tmem_rows, kResCorrOff, half, lane, tbuf, ctx,
+                                             tfull_bar, acc & 1u, nullptr);
         if (tr) tc_stamp(trace, 18);
         release_and_publish();
         const EpiH<PREC, NL, FARNN> e2{ps};
-        tc_epilogue_chunks<TWOACC, EW / 4>(e2, M, S, mrow0, crank * bn2, bn2, tmem_rows, kResCorrOff, half, lane, tbuf, ctx,
-                                   tfull_bar, acc & 1u, nullptr);
+        if constexpr (EpiHasRows<EpiH<PREC, NL, FARNN>>::value)
+          tc_epilogue_quads<TWOACC, EW / 4>(e2, M, S, mrow0, crank * bn2, bn2, tmem_rows, kResCorrOff, half, lane, tbuf, ctx,
+                                            tfull_bar, acc & 1u);
+        else
+          tc_epilogue_chunks<TWOACC, EW / 4>(e2, M, S, mrow0, crank * bn2, bn2, tmem_rows, kResCorrOff, half, lane, tbuf, ctx,
+                                             tfull_bar, acc & 1u, nullptr);
         if (tr) tc_stamp(trace, 19);
         release_and_publish();
       }

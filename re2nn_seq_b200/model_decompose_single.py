@@ -190,7 +190,7 @@ class _DecomposeBase(nn.Module):
             offsets = offs0
         chunks = self._infer_chunks(B) if order is not None else None
         if chunks is None:
-            scores = self._scores_from(inp, lengths, (L, nmax))
+            scores = self._scores_from(inp, lengths, (L, nmax), fuse=True)      # scores feed the decoder only
             pred = self.decode(scores, None, None, lengths, _shape=(L, nmax), _offsets=offsets)
             return pred, true
         # Sequences are sorted longest-first, so the recurrence of a later chunk finishes earlier (its tiles stop at
@@ -208,7 +208,7 @@ class _DecomposeBase(nn.Module):
             st.wait_event(fork)
             with torch.cuda.stream(st):
                 lc = lengths[b0:b1]
-                sc = self._scores_from(inp[b0:b1], lc, (L, nmax))
+                sc = self._scores_from(inp[b0:b1], lc, (L, nmax), fuse=True)
                 self.decode(sc, None, None, lc, _shape=(L, nmax), _offsets=offsets[b0:b1], _flat_out=pred)
                 done = torch.cuda.Event()
                 done.record(st)
@@ -422,8 +422,10 @@ class FARNN_S_D_W_I_S(_DecomposeBase):
         tensors = [getattr(self, n) for n in names] + [self.embedding.weight]
         return names + ['embedding'], tensors
 
-    def forward_scores(self, input, lengths, shape=None):
-        """all_scores B x L x C (L = max length); differentiable w.r.t. the module parameters."""
+    def forward_scores(self, input, lengths, shape=None, fuse=False):
+        """all_scores B x L x C (L = max length); differentiable w.r.t. the module parameters.
+        fuse=True (decode-only callers): rows past the length may hold anything -- the label-score operand then comes
+        fused out of the recurrence (re2nn_decompose_recurrence ab_out) where the call allows it."""
         dev = self._device()
         x = input.to(dev).contiguous()
         lengths = lengths.to(dev).contiguous()
@@ -433,11 +435,11 @@ class FARNN_S_D_W_I_S(_DecomposeBase):
             from .model_fst import ifst_decompose_max_scores
             return ifst_decompose_max_scores(self, x, None, lengths, shape[0])
         pr = (self.priority_layer.priority_mat, self.priority_layer.priority_bias)
-        return autograd_fns.decompose_scores(self._recurrence_consts(), names, tensors, pr, x, None, lengths, shape[0],
-                                             cache=self._cache)
+        return autograd_fns.decompose_scores(dict(self._recurrence_consts(), fuse_scores=bool(fuse)), names, tensors, pr, x,
+                                             None, lengths, shape[0], cache=self._cache)
 
-    def _scores_from(self, inp, lengths, shape):
-        return self.forward_scores(inp, lengths, shape)
+    def _scores_from(self, inp, lengths, shape, fuse=False):
+        return self.forward_scores(inp, lengths, shape, fuse=fuse)
 
     def _warm_tables(self):
         names, tensors = self._fn_params()
@@ -503,7 +505,7 @@ class FARNN_S_SF(_DecomposeBase):
             nn.init.normal_(self.h0)
             nn.init.normal_(self.hT)
 
-    def forward_scores(self, input, lengths, shape=None):
+    def forward_scores(self, input, lengths, shape=None, fuse=False):
         dev = self._device()
         v = input.to(dev).float().contiguous()
         lengths = lengths.to(dev).contiguous()
@@ -514,10 +516,11 @@ class FARNN_S_SF(_DecomposeBase):
             from .model_fst import ifst_decompose_max_scores
             return ifst_decompose_max_scores(self, None, v, lengths, shape[0])
         pr = (self.priority_layer.priority_mat, self.priority_layer.priority_bias)
-        return autograd_fns.decompose_scores(self._recurrence_consts(), names, tensors, pr, None, v, lengths, shape[0])
+        return autograd_fns.decompose_scores(dict(self._recurrence_consts(), fuse_scores=bool(fuse)), names, tensors, pr, None,
+                                             v, lengths, shape[0])
 
-    def _scores_from(self, inp, lengths, shape):
-        return self.forward_scores(inp, lengths, shape)
+    def _scores_from(self, inp, lengths, shape, fuse=False):
+        return self.forward_scores(inp, lengths, shape, fuse=fuse)
 
     def forward(self, input, label, lengths, train=True, re_tags=None):
         """input: pre-computed rank factors B x L x R (model_decompose_single.py:483-580)."""

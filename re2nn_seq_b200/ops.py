@@ -148,6 +148,61 @@ def decompose_recurrence(x, lengths, L, vtab, gtab, S1, S2, W, o, h0, hT, Wss1, 
     return alpha, beta, saves
 
 
+def decompose_recurrence_fused(x, lengths, L, vtab, S1, S2, W, o, h0, hT, update_nonlinear, precision, v_mode=V_TOKEN,
+                               Lpad=None):
+    """Inference without gates on the per-step tensor-core path: the backward direction runs first and the forward
+    direction's state epilogue writes (alpha * beta) straight in operand format, so alpha is never materialised and
+    label scoring does not re-read the states.  -> (ab operand buffer, beta) or None when the call would not fuse
+    (fp32, resident kernel)."""
+    B = lengths.shape[0]
+    S, R = S1.shape
+    dev = S1.device
+    a = RecurrenceArgs()
+    a.B, a.L, a.S, a.R = B, L, S, R
+    a.Lpad = Lpad if Lpad is not None else (x.shape[1] if x is not None else L)
+    a.farnn, a.update_nonlinear, a.precision = 0, NL[update_nonlinear], PREC[precision]
+    a.v_mode, a.full_pad, a.save_for_backward = v_mode, 0, 0
+    if not fn['re2nn_decompose_recurrence_fuses'](C.byref(a)):
+        return None
+    nbytes = fn['re2nn_label_scores_ab_bytes'](B, L, S, PREC[precision])
+    ab = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    beta = torch.empty((B, L, S), dtype=torch.float32, device=dev)
+    a.ab_out = C.c_void_p(ab.data_ptr())
+    a.x = _i64(x) if x is not None else None
+    a.lengths = _i64(lengths)
+    a.vtab = _f32(vtab)
+    a.S1, a.S2, a.W, a.o, a.h0, a.hT = _f32(S1), _f32(S2), _f32(W), _f32(o), _f32(h0), _f32(hT)
+    a.beta = _f32(beta)
+    need = fn['re2nn_decompose_recurrence_workspace'](C.byref(a))
+    ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+    a.ws, a.ws_bytes = C.c_void_p(ws.data_ptr()), need
+    check(fn['re2nn_decompose_recurrence'](C.byref(a), _stream()), 'decompose_recurrence')
+    _count(fn['re2nn_decompose_recurrence_launches'](C.byref(a)))
+    return ab, beta
+
+
+def label_scores_ab(ab, B, L, S, C_mat, priority_mat=None, priority_bias=None, precision='bf16'):
+    """scores = ab @ C^T [@ P + b] from the fused operand of decompose_recurrence_fused."""
+    Cn = C_mat.shape[0]
+    scores = torch.empty((B, L, Cn), dtype=torch.float32, device=C_mat.device)
+    has_pr = priority_mat is not None
+    need = fn['re2nn_label_scores_workspace'](B, L, S, Cn, PREC[precision], int(has_pr))
+    ws = torch.empty((need,), dtype=torch.uint8, device=C_mat.device)
+    check(fn['re2nn_label_scores_ab'](C.c_void_p(ab.data_ptr()), B, L, S, _f32(C_mat), Cn,
+                                      _f32(priority_mat) if has_pr else None,
+                                      _f32(priority_bias) if priority_bias is not None else None, PREC[precision],
+                                      _f32(scores), C.c_void_p(ws.data_ptr()), need, _stream()), 'label_scores_ab')
+    _count(2 + (1 if has_pr else 0))
+    return scores
+
+
+def recurrence_fuses(S, R, farnn, precision):
+    """Would an inference call of this shape write the fused (alpha * beta) operand when asked to?"""
+    a = RecurrenceArgs()
+    a.S, a.R, a.farnn, a.precision, a.save_for_backward, a.full_pad = S, R, farnn, PREC[precision], 0, 0
+    return bool(fn['re2nn_decompose_recurrence_fuses'](C.byref(a)))
+
+
 def onehot_recurrence(x, lengths, L, language, W, o, h0, hT, update_nonlinear, max_semiring=False, full_pad=False,
                       presummed=False):
     B, Lpad = x.shape

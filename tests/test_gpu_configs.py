@@ -281,3 +281,25 @@ def test_cfg3_full_batch_gradients_vs_fp64_oracle(capsys):
               ', '.join('%s %.2e' % kv for kv in sorted(errs.items())))
     for k, e in errs.items():
         assert e < 1e-4, '%s: %.3e' % (k, e)
+
+
+@pytest.mark.parametrize('prec', ['bf16', 'fp16x3', 'tf32x3'])
+def test_fused_label_score_operand_is_bit_identical(prec):
+    """Per-step tensor-core path (S=1024: not resident): the (alpha * beta) operand written by the forward direction's
+    epilogue (re2nn_decompose_recurrence ab_out, backward direction first) gives exactly the scores of the unfused
+    path on every valid position, ragged lengths included."""
+    from re2nn_seq_b200 import ops
+    if not ops.has_tcgen05():
+        pytest.skip('no tcgen05')
+    m, args, x, lens, lab = _decompose(31, 900, 1024, 512, 128, 100, 200, 24, farnn=0, use_crf=1, update_nonlinear='tanh',
+                                       beta=0.1)
+    m.precision = prec
+    with torch.no_grad():
+        assert ops.recurrence_fuses(1024, 512, 0, prec)
+        l0 = ops.launches()
+        fused = m.forward_scores(_t(x), _t(lens), fuse=True).cpu().numpy()
+        n_fused = ops.launches() - l0
+        plain = m.forward_scores(_t(x), _t(lens)).cpu().numpy()
+    mask = orc.length_mask(lens, int(lens.max()))
+    np.testing.assert_array_equal(fused[mask], plain[mask])
+    assert n_fused > 4 * int(lens.max())          # single-direction launches: 4 per step
