@@ -86,14 +86,35 @@ __device__ __forceinline__ float tanh_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-template <bool FAST>
+// Branch-free tanh for the parity-grade tensor-core epilogues: |x| < 0.55 an odd polynomial (1.2 ulp), otherwise
+// 1 - 2 / (e^{2|x|} + 1) with ex2.approx / rcp.approx; <= 4e-7 relative overall (libm's tanhf is ~1e-7 but carries a
+// divergent branch per call: ~45 instructions per element against ~16).  A five-instruction form without the
+// polynomial (absolute error 2e-7, relative error unbounded near 0) was measured too: it breaks the 1e-5 score bound
+// of the 128-step recurrence (cfg4, tf32x3) and raises the cfg5 tag differences against the fp32 path from 52 to
+// 1092 of 4.2 M -- and buys nothing, the epilogue being bound by its L2 write traffic, not by issue slots.
+__device__ __forceinline__ float sigmoid_ulp(float x);
+__device__ __forceinline__ float tanh_bfree(float x) {
+  const float t = fabsf(x), u = x * x;
+  float q = fmaf(u, -6.615782622e-03f, 2.131276391e-02f);
+  q = fmaf(q, u, -5.391006917e-02f);
+  q = fmaf(q, u, 1.333311796e-01f);
+  q = fmaf(q, u, -3.333333135e-01f);
+  const float small = fmaf(x * u, q, x);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t * 2.885390082f));       // e^{2t}
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+  const float big = copysignf(fmaf(-2.f, r, 1.f), x);
+  return t < 0.55f ? small : big;
+}
+// MODE 0: libm (fp32 path, training), 1: MUFU tanh.approx (bf16 operands), 2: branch-free few-ulp (tf32x3 / fp16x3)
+template <int MODE>
 __device__ __forceinline__ float apply_nl_t(float x, int kind) {
-  if (!FAST) return apply_nl(x, kind);
+  if (MODE == 0) return apply_nl(x, kind);
   switch (kind) {
     case RE2NN_NL_RELU: return fmaxf(x, 0.f);
-    case RE2NN_NL_TANH: return tanh_fast(x);
-    case RE2NN_NL_RELUTANH: return tanh_fast(fmaxf(x, 0.f));
-    case RE2NN_NL_SIGMOID: return 0.5f * tanh_fast(0.5f * x) + 0.5f;
+    case RE2NN_NL_TANH: return MODE == 1 ? tanh_fast(x) : tanh_bfree(x);
+    case RE2NN_NL_RELUTANH: return MODE == 1 ? tanh_fast(fmaxf(x, 0.f)) : tanh_bfree(fmaxf(x, 0.f));
+    case RE2NN_NL_SIGMOID: return MODE == 1 ? 0.5f * tanh_fast(0.5f * x) + 0.5f : sigmoid_ulp(x);
     default: return x;
   }
 }

@@ -294,7 +294,9 @@ template <int PREC, bool TRAIN = false> struct EpiQ {
 // FUSE (forward direction, farnn == 0, inference): instead of the alpha row write alpha * beta in operand format
 // for the label-score GEMM (beta was completed by the backward direction, which ran first).
 template <int PREC, int NL = -1, int FARNN = -1, bool TRAIN = false, bool FUSE = false> struct EpiH {
-  static constexpr bool kFast = PREC == RE2NN_PREC_BF16;
+  // nonlinearity flavour: MUFU tanh for bf16 operands, branch-free few-ulp for the parity-grade tensor-core modes in
+  // inference, libm where gradients are taken (training saves) and on the fp32 CUDA-core path
+  static constexpr int kFast = PREC == RE2NN_PREC_BF16 ? 1 : ((PREC == RE2NN_PREC_FP32 || TRAIN) ? 0 : 2);
   StepParams p;
   __device__ __forceinline__ EpiH for_dir(int z) const { EpiH e = *this; e.p.bind(z); return e; }
   __device__ __forceinline__ bool tile_alive(int z, int mt) const { return re2nn::tile_alive(p, z, mt); }

@@ -470,10 +470,12 @@ constexpr int kTbufPitch = 36;
 template <bool TWOACC, int PARTS, class Epi>
 __device__ __forceinline__ void tc_epilogue_quads(const Epi epi, int M, int N, int mrow0, int n0, int bn, uint32_t tmem_rows,
                                                   uint32_t corr_off, int half, int lane, float* tbuf, const int* ctx,
-                                                  uint32_t tfull, uint32_t parity) {
+                                                  uint32_t tfull, uint32_t parity, unsigned long long* trace = nullptr) {
   const int nrows = min(32, M - mrow0);
   const int* ctx_o = ctx + 32;
   const bool vec = epi.rows_vec();
+  const bool stamp = trace != nullptr && lane == 0;
+  int dbg_s = 20;
   const int rsub = lane >> 3, c4 = (lane & 7) * 4;
   bool acc_ready = false;
   if constexpr (EpiL2Prefetch<Epi>::kOn) {
@@ -502,10 +504,13 @@ __device__ __forceinline__ void tc_epilogue_quads(const Epi epi, int M, int N, i
       if (i < nrows && ncols > 0) pre[k] = epi.pre4(RowCtx{ctx[i], ctx_o[i], ctx_o[i] >= 0}, mrow0 + i, nb, ncols, vec);
     }
     if (!acc_ready) {
+      if (stamp) tc_stamp(trace, 4);
       mbar_wait(tfull, parity);
       tc_fence_after();
       acc_ready = true;
+      if (stamp) tc_stamp(trace, 5);
     }
+    if (stamp && dbg_s < 26) tc_stamp(trace, dbg_s);
     {
       uint32_t r[32];
       tmem_ld32(tmem_rows + (uint32_t)c0, r);
@@ -527,6 +532,7 @@ __device__ __forceinline__ void tc_epilogue_quads(const Epi epi, int M, int N, i
       }
     }
     __syncwarp();
+    if (stamp && dbg_s < 26) tc_stamp(trace, dbg_s + 1);
     // phase 2: lane = (row group member, column quad)
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -536,6 +542,8 @@ __device__ __forceinline__ void tc_epilogue_quads(const Epi epi, int M, int N, i
         epi.apply4(RowCtx{ctx[i], ctx_o[i], ctx_o[i] >= 0}, mrow0 + i, nb, ncols, vec, acc, pre[k], oc);
     }
     __syncwarp();
+    if (stamp && dbg_s < 26) tc_stamp(trace, dbg_s + 2);
+    dbg_s += 3;
   }
   if (!acc_ready) {
     mbar_wait(tfull, parity);

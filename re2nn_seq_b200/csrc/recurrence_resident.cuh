@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(64 + 32 * resident_epi_warps(FARNN), 1) tc_res
           }
           // G1: A = Hbar[par], published by the previous phase (or rec_init_kernel for the first)
           const bool tr = tile == worker && (k == 2 || k == 3);     // debug trace: one steady-state step
-          const int tb = k == 2 ? 8 : 21;
+          const int tb = k == 2 ? 8 : 26;
           load_segment(RL.g1[par], RL.g1[par].seg[z][0], m0, crank * bn1, bn1, !first, tr ? tb : -1);
           if (tr && k == 2) tc_stamp(trace, 10);
           first = false;
@@ -309,12 +309,13 @@ __global__ void __launch_bounds__(64 + 32 * resident_epi_warps(FARNN), 1) tc_res
         const EpiH<PREC, NL, FARNN> e2{ps};
         if constexpr (EpiHasRows<EpiH<PREC, NL, FARNN>>::value)
           tc_epilogue_quads<TWOACC, EW / 4>(e2, M, S, mrow0, crank * bn2, bn2, tmem_rows, kResCorrOff, half, lane, tbuf, ctx,
-                                            tfull_bar, acc & 1u);
+                                            tfull_bar, acc & 1u, tr ? trace : nullptr);
         else
           tc_epilogue_chunks<TWOACC, EW / 4>(e2, M, S, mrow0, crank * bn2, bn2, tmem_rows, kResCorrOff, half, lane, tbuf, ctx,
                                              tfull_bar, acc & 1u, nullptr);
         if (tr) tc_stamp(trace, 19);
         release_and_publish();
+        if (tr) tc_stamp(trace, 30);
       }
     }
   }

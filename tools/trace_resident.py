@@ -38,7 +38,11 @@ names = {8: 'producer: G1 B tiles issued, waits for rows (step k)', 9: 'producer
          14: 'mma: first G1 k-block landed', 15: 'mma: G1 issued + committed', 18: 'epilogue: G1 tile stored',
          11: 'producer: G2 weight tiles issued, waits for Q', 12: 'producer: Q published (ready)', 13: 'producer: all G2 loads issued',
          16: 'mma: first G2 k-block landed', 17: 'mma: G2 issued + committed', 19: 'epilogue: G2 tile stored',
-         21: 'producer: next step waits for rows', 22: 'producer: rows of step k published (ready)'}
+         26: 'producer: next step waits for rows', 27: 'producer: rows of step k published (ready)',
+         4: 'epi warp0 G2: waits for accumulator', 5: 'epi warp0 G2: accumulator ready', 20: 'epi warp0 G2 chunk0: start',
+         23: 'epi warp0 G2 chunk1: start', 24: 'epi warp0 G2 chunk1: transposed', 25: 'epi warp0 G2 chunk1: stored',
+         30: 'epi warp0 G2: published'}
+names[21] = 'epi warp0 G2 chunk0: transposed'; names[22] = 'epi warp0 G2 chunk0: stored'
 ref = t[:, 9:10]
 order = sorted(names, key=lambda s: np.median(t[:, s] - ref[:, 0]))
 for s in order:
