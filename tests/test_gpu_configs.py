@@ -280,7 +280,7 @@ def test_cfg3_full_batch_gradients_vs_fp64_oracle(capsys):
         print('\ncfg3 B=1024 gradient errors vs fp64 oracle (max-norm relative): ' +
               ', '.join('%s %.2e' % kv for kv in sorted(errs.items())))
     for k, e in errs.items():
-        assert e < 1e-4, '%s: %.3e' % (k, e)
+        assert e < 2e-5, '%s: %.3e' % (k, e)         # the bound DESIGN.md section 2 states
 
 
 @pytest.mark.parametrize('prec', ['bf16', 'fp16x3', 'tf32x3'])
