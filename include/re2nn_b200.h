@@ -247,6 +247,9 @@ typedef struct re2nn_onehot_args {
   float* beta;                 /* B x L x S */
 } re2nn_onehot_args;
 int re2nn_onehot_recurrence(const re2nn_onehot_args* a, void* stream);
+/* debug / calibration: CTAs one (sequence, direction) slice is spread over (thread-block cluster, transition rows
+ * split, partial state vectors exchanged through distributed shared memory): 0 = pick by batch size, 1, 2, 4. */
+int re2nn_debug_set_onehot_cluster(int nc);
 /* out[v] = language[v] + W  (model_onehot.py:366 `sum_tensor`): the reference redoes this V*S*S add on every
  * forward; here it is done once per parameter version and the recurrence then streams a single tensor. */
 int re2nn_onehot_sum_tensor(const float* language, const float* W, int V1, int S, float* out, void* stream);

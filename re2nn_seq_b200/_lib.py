@@ -123,6 +123,7 @@ SYMBOLS = {
     're2nn_decompose_max_recurrence': (C.c_int, [C.POINTER(RecurrenceArgs), vp]),
     're2nn_batched_vecmat': (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     're2nn_onehot_recurrence': (C.c_int, [C.POINTER(OnehotArgs), vp]),
+    're2nn_debug_set_onehot_cluster': (C.c_int, [C.c_int]),
     're2nn_onehot_backward': (C.c_int, [C.POINTER(OnehotBackwardArgs), vp]),
     're2nn_onehot_sum_tensor': (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp]),
     're2nn_label_scores_backward': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp]),

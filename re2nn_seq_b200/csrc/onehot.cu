@@ -6,6 +6,8 @@
 // in shared memory; rows of the slice are read as full 128-byte lines (lanes along the contiguous
 // "to-state" index), W comes from L2.  language + W is formed on the fly in the reference's own
 // rounding order, so no V x S x S temporary is ever written (K1 in SURVEY.md §2.2).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace re2nn {
@@ -52,13 +54,43 @@ __device__ __forceinline__ float dot4(float acc, float4 h, float4 t) {
   return acc;
 }
 
+// (Measured dead end: a cp.async.bulk pipeline that streams 16-row stages of the slices ahead of the recurrence -- the
+// tokens are known up front -- through shared memory was 1.5-1.7x SLOWER than these direct 16-byte loads at every batch
+// size, B = 32: 1.14 vs 0.68 ms; the per-stage mbarrier round trips cost more than the load latency they hide.)
+// ---- cluster helpers: small batches (cfg1: B = 32 -> 64 (sequence, direction) slices for 148 SMs) spread every slice over
+// a thread-block cluster.  The S x S transition slice of a step is split by ROWS over the CTAs of the cluster (each
+// streams 1/nc of the bytes); the S-float partial results are exchanged through distributed shared memory with one
+// cluster barrier per step (double-buffered exchange arrays), and every CTA keeps a full copy of the state.
+__device__ __forceinline__ uint32_t oh_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t oh_cluster_size() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void oh_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float oh_ld_remote(const float* local, uint32_t rank) {
+  uint32_t la = (uint32_t)__cvta_generic_to_shared(local), ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+
 template <bool MAXP>
-__global__ void __launch_bounds__(kOhThreads) onehot_recurrence_kernel(const re2nn_onehot_args a) {
+__global__ void __launch_bounds__(kOhThreads) onehot_recurrence_kernel(const re2nn_onehot_args a, const int rows8) {
   extern __shared__ float smem[];
   const int S = a.S;
   float* h = smem;                 // S   current state (bwd: already multiplied by o)
   float* part = smem + S;          // kOhWarps * S partial results (fwd)
-  const int b = blockIdx.x, z = blockIdx.y;
+  float* xbuf = part + kOhWarps * S;   // 2 * S: this CTA's contribution to the cluster exchange, per step parity
+  const int nc = (int)oh_cluster_size(), cr = (int)oh_cluster_rank();
+  const int b = blockIdx.x / nc, z = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = (int)a.lengths[b];
   const float* __restrict__ W = a.W;
@@ -67,11 +99,14 @@ __global__ void __launch_bounds__(kOhThreads) onehot_recurrence_kernel(const re2
   const float init = MAXP ? -INFINITY : 0.f;
   // 16-byte path: rows start 16-byte aligned when S % 4 == 0 (cudaMalloc bases are 256-byte aligned)
   const bool vec4 = (S & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.language) | reinterpret_cast<uintptr_t>(W)) & 15) == 0;
+  // rows of the slice this CTA streams: [r0, r1)
+  const int rows_per = (S + nc - 1) / nc;
+  const int r0 = min(S, cr * rows_per), r1 = min(S, r0 + rows_per);
 
   for (int s = tid; s < S; s += kOhThreads) {
     float v = z == 0 ? a.h0[s] : a.hT[s];
     if (z == 1) {
-      if (n >= 1 && n <= a.L) out[((size_t)b * a.L + (n - 1)) * S + s] = v;   // beta_n = hT
+      if (cr == 0 && n >= 1 && n <= a.L) out[((size_t)b * a.L + (n - 1)) * S + s] = v;   // beta_n = hT
       v *= o[s];
     }
     h[s] = v;
@@ -82,144 +117,171 @@ __global__ void __launch_bounds__(kOhThreads) onehot_recurrence_kernel(const re2
     int tpos, orow;
     bool alive;
     step_pos(z, k, n, a.full_pad, tpos, orow, alive);
-    if (!alive) break;   // block-uniform
+    if (!alive) break;   // uniform over the block AND over the cluster (same sequence, same direction)
     const int64_t tok = a.x[(size_t)b * a.Lpad + tpos];
     const float* __restrict__ T = a.language + (size_t)tok * S * S;
-    if (z == 0 && vec4) {
-      // 16-byte loads, four rows in flight per lane: a CTA is one (sequence, direction), so at small batch the
-      // bytes in flight per SM decide the speed (8 KB with scalar loads = ~9 GB/s per SM).  Every column keeps the
-      // accumulation order of the scalar path (rows s = warp, warp + 16, ...; then warps in order): same bits.
-      for (int jb = 0; jb < S; jb += 128) {
-        const int j = jb + 4 * lane;
-        if (j < S) {
-          float4 acc = make_float4(init, init, init, init);
-          int s = warp;
-          for (; s + 3 * kOhWarps < S; s += 4 * kOhWarps) {
-            const float4 t0 = tw4(T, W, (size_t)s * S + j);
-            const float4 t1 = tw4(T, W, (size_t)(s + kOhWarps) * S + j);
-            const float4 t2 = tw4(T, W, (size_t)(s + 2 * kOhWarps) * S + j);
-            const float4 t3 = tw4(T, W, (size_t)(s + 3 * kOhWarps) * S + j);
-            acc = comb4<MAXP>(acc, h[s], t0);
-            acc = comb4<MAXP>(acc, h[s + kOhWarps], t1);
-            acc = comb4<MAXP>(acc, h[s + 2 * kOhWarps], t2);
-            acc = comb4<MAXP>(acc, h[s + 3 * kOhWarps], t3);
-          }
-          for (; s < S; s += kOhWarps) acc = comb4<MAXP>(acc, h[s], tw4(T, W, (size_t)s * S + j));
-          *reinterpret_cast<float4*>(part + warp * S + j) = acc;
-        }
-      }
-      __syncthreads();
-      for (int j = tid; j < S; j += kOhThreads) {
-        float acc = init;
+    float* xb = xbuf + (k & 1) * S;
+    if (z == 0) {
+      // out[j] = (+|max)_s h[s] * (T[s][j] + W[s][j]) over this CTA's rows s; warps stride over rows, lanes over columns
+      if (vec4) {
+        // 16-byte loads, four rows in flight per lane: a CTA is one (sequence, direction) slice, so at small batch the
+        // bytes in flight per SM decide the speed (8 KB with scalar loads = ~9 GB/s per SM)
+        for (int jb = 0; jb < S; jb += 128) {
+          const int j = jb + 4 * lane;
+          if (j < S) {
+            float4 acc = make_float4(init, init, init, init);
+            int s = r0 + warp;
+            for (; rows8 && s + 7 * kOhWarps < r1; s += 8 * kOhWarps) {      // eight rows in flight per lane
+              float4 t[8];
 #pragma unroll
-        for (int w = 0; w < kOhWarps; ++w) acc = MAXP ? fmaxf(acc, part[w * S + j]) : acc + part[w * S + j];
-        float v = apply_nl(acc * o[j], a.update_nonlinear);
-        h[j] = v;
-        if (orow >= 0) out[((size_t)b * a.L + orow) * S + j] = v;
-      }
-      __syncthreads();
-    } else if (z == 0) {
-      // out[j] = (+|max)_s h[s] * (T[s][j] + W[s][j]); warps stride over rows s, lanes over columns j
-      for (int jb = 0; jb < S; jb += 32) {
-        const int j = jb + lane;
-        float acc = init;
-        if (j < S) {
-          int s = warp;
-          for (; s + 3 * kOhWarps < S; s += 4 * kOhWarps) {
-            float t0 = tw(T, W, (size_t)s * S + j);
-            float t1 = tw(T, W, (size_t)(s + kOhWarps) * S + j);
-            float t2 = tw(T, W, (size_t)(s + 2 * kOhWarps) * S + j);
-            float t3 = tw(T, W, (size_t)(s + 3 * kOhWarps) * S + j);
-            acc = comb<MAXP>(acc, h[s], t0);
-            acc = comb<MAXP>(acc, h[s + kOhWarps], t1);
-            acc = comb<MAXP>(acc, h[s + 2 * kOhWarps], t2);
-            acc = comb<MAXP>(acc, h[s + 3 * kOhWarps], t3);
-          }
-          for (; s < S; s += kOhWarps)
-            acc = comb<MAXP>(acc, h[s], tw(T, W, (size_t)s * S + j));
-          part[warp * S + j] = acc;
-        }
-      }
-      __syncthreads();
-      for (int j = tid; j < S; j += kOhThreads) {
-        float acc = init;
+              for (int u = 0; u < 8; ++u) t[u] = tw4(T, W, (size_t)(s + u * kOhWarps) * S + j);
 #pragma unroll
-        for (int w = 0; w < kOhWarps; ++w) acc = MAXP ? fmaxf(acc, part[w * S + j]) : acc + part[w * S + j];
-        float v = apply_nl(acc * o[j], a.update_nonlinear);
-        h[j] = v;
-        if (orow >= 0) out[((size_t)b * a.L + orow) * S + j] = v;
-      }
-      __syncthreads();
-    } else if (vec4) {
-      // out[s] = (+|max)_j h[j] * (T[s][j] + W[s][j]); a warp takes two rows at a time, lanes take 4 columns per load
-      float* hn = part;   // S
-      for (int s = warp; s < S; s += 2 * kOhWarps) {
-        const int s1 = s + kOhWarps;
-        const bool two = s1 < S;
-        const float* __restrict__ Tr0 = T + (size_t)s * S;
-        const float* __restrict__ Tr1 = T + (size_t)(two ? s1 : s) * S;
-        const float* __restrict__ Wr0 = W ? W + (size_t)s * S : nullptr;
-        const float* __restrict__ Wr1 = W ? W + (size_t)(two ? s1 : s) * S : nullptr;
-        float acc0 = init, acc1 = init;
-        for (int j = 4 * lane; j < S; j += 256) {
-          const bool more = j + 128 < S;
-          const float4 a0 = tw4(Tr0, Wr0, j), b0 = tw4(Tr1, Wr1, j);
-          const float4 a1 = more ? tw4(Tr0, Wr0, j + 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 b1 = more ? tw4(Tr1, Wr1, j + 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 hv = *reinterpret_cast<const float4*>(h + j);
-          acc0 = dot4<MAXP>(acc0, hv, a0);
-          acc1 = dot4<MAXP>(acc1, hv, b0);
-          if (more) {
-            const float4 hw = *reinterpret_cast<const float4*>(h + j + 128);
-            acc0 = dot4<MAXP>(acc0, hw, a1);
-            acc1 = dot4<MAXP>(acc1, hw, b1);
+              for (int u = 0; u < 8; ++u) acc = comb4<MAXP>(acc, h[s + u * kOhWarps], t[u]);
+            }
+            for (; s + 3 * kOhWarps < r1; s += 4 * kOhWarps) {
+              const float4 t0 = tw4(T, W, (size_t)s * S + j);
+              const float4 t1 = tw4(T, W, (size_t)(s + kOhWarps) * S + j);
+              const float4 t2 = tw4(T, W, (size_t)(s + 2 * kOhWarps) * S + j);
+              const float4 t3 = tw4(T, W, (size_t)(s + 3 * kOhWarps) * S + j);
+              acc = comb4<MAXP>(acc, h[s], t0);
+              acc = comb4<MAXP>(acc, h[s + kOhWarps], t1);
+              acc = comb4<MAXP>(acc, h[s + 2 * kOhWarps], t2);
+              acc = comb4<MAXP>(acc, h[s + 3 * kOhWarps], t3);
+            }
+            for (; s < r1; s += kOhWarps) acc = comb4<MAXP>(acc, h[s], tw4(T, W, (size_t)s * S + j));
+            *reinterpret_cast<float4*>(part + warp * S + j) = acc;
           }
         }
-        acc0 = MAXP ? warp_max(acc0) : warp_sum(acc0);
-        acc1 = MAXP ? warp_max(acc1) : warp_sum(acc1);
-        if (lane == 0) {
-          hn[s] = acc0;
-          if (two) hn[s1] = acc1;
+      } else {
+        for (int jb = 0; jb < S; jb += 32) {
+          const int j = jb + lane;
+          float acc = init;
+          if (j < S) {
+            int s = r0 + warp;
+            for (; s + 3 * kOhWarps < r1; s += 4 * kOhWarps) {
+              float t0 = tw(T, W, (size_t)s * S + j);
+              float t1 = tw(T, W, (size_t)(s + kOhWarps) * S + j);
+              float t2 = tw(T, W, (size_t)(s + 2 * kOhWarps) * S + j);
+              float t3 = tw(T, W, (size_t)(s + 3 * kOhWarps) * S + j);
+              acc = comb<MAXP>(acc, h[s], t0);
+              acc = comb<MAXP>(acc, h[s + kOhWarps], t1);
+              acc = comb<MAXP>(acc, h[s + 2 * kOhWarps], t2);
+              acc = comb<MAXP>(acc, h[s + 3 * kOhWarps], t3);
+            }
+            for (; s < r1; s += kOhWarps) acc = comb<MAXP>(acc, h[s], tw(T, W, (size_t)s * S + j));
+            part[warp * S + j] = acc;
+          }
         }
       }
       __syncthreads();
-      for (int s = tid; s < S; s += kOhThreads) {
-        float v = apply_nl(hn[s], a.update_nonlinear);
-        if (orow >= 0) out[((size_t)b * a.L + orow) * S + s] = v;
-        h[s] = v * o[s];
+      if (nc == 1) {
+        for (int j = tid; j < S; j += kOhThreads) {
+          float acc = init;
+#pragma unroll
+          for (int w = 0; w < kOhWarps; ++w) acc = MAXP ? fmaxf(acc, part[w * S + j]) : acc + part[w * S + j];
+          float v = apply_nl(acc * o[j], a.update_nonlinear);
+          h[j] = v;
+          if (orow >= 0) out[((size_t)b * a.L + orow) * S + j] = v;
+        }
+        __syncthreads();
+      } else {
+        for (int j = tid; j < S; j += kOhThreads) {
+          float acc = init;
+#pragma unroll
+          for (int w = 0; w < kOhWarps; ++w) acc = MAXP ? fmaxf(acc, part[w * S + j]) : acc + part[w * S + j];
+          xb[j] = acc;                                  // this CTA's rows
+        }
+        oh_cluster_sync();
+        for (int j = tid; j < S; j += kOhThreads) {
+          float acc = init;
+          for (int c = 0; c < nc; ++c) {                // fixed rank order: every CTA forms the same sum
+            const float pv = oh_ld_remote(xb + j, (uint32_t)c);
+            acc = MAXP ? fmaxf(acc, pv) : acc + pv;
+          }
+          float v = apply_nl(acc * o[j], a.update_nonlinear);
+          h[j] = v;
+          if (cr == 0 && orow >= 0) out[((size_t)b * a.L + orow) * S + j] = v;
+        }
+        __syncthreads();
       }
-      __syncthreads();
     } else {
-      // out[s] = (+|max)_j h[j] * (T[s][j] + W[s][j]); one warp per row s, lanes along j
+      // out[s] = (+|max)_j h[j] * (T[s][j] + W[s][j]) for this CTA's rows s
       float* hn = part;   // S
-      for (int s = warp; s < S; s += kOhWarps) {
-        const float* __restrict__ Tr = T + (size_t)s * S;
-        const float* __restrict__ Wr = W ? W + (size_t)s * S : nullptr;
-        float acc = init;
-        int j = lane;
-        for (; j + 96 < S; j += 128) {
-          float t0 = tw(Tr, Wr, j);
-          float t1 = tw(Tr, Wr, j + 32);
-          float t2 = tw(Tr, Wr, j + 64);
-          float t3 = tw(Tr, Wr, j + 96);
-          acc = comb<MAXP>(acc, h[j], t0);
-          acc = comb<MAXP>(acc, h[j + 32], t1);
-          acc = comb<MAXP>(acc, h[j + 64], t2);
-          acc = comb<MAXP>(acc, h[j + 96], t3);
+      if (vec4) {
+        // a warp takes two rows at a time, lanes take 4 columns per load
+        for (int s = r0 + warp; s < r1; s += 2 * kOhWarps) {
+          const int s1 = s + kOhWarps;
+          const bool two = s1 < r1;
+          const float* __restrict__ Tr0 = T + (size_t)s * S;
+          const float* __restrict__ Tr1 = T + (size_t)(two ? s1 : s) * S;
+          const float* __restrict__ Wr0 = W ? W + (size_t)s * S : nullptr;
+          const float* __restrict__ Wr1 = W ? W + (size_t)(two ? s1 : s) * S : nullptr;
+          float acc0 = init, acc1 = init;
+          for (int j = 4 * lane; j < S; j += 256) {
+            const bool more = j + 128 < S;
+            const float4 a0 = tw4(Tr0, Wr0, j), b0 = tw4(Tr1, Wr1, j);
+            const float4 a1 = more ? tw4(Tr0, Wr0, j + 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 b1 = more ? tw4(Tr1, Wr1, j + 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 hv = *reinterpret_cast<const float4*>(h + j);
+            acc0 = dot4<MAXP>(acc0, hv, a0);
+            acc1 = dot4<MAXP>(acc1, hv, b0);
+            if (more) {
+              const float4 hw = *reinterpret_cast<const float4*>(h + j + 128);
+              acc0 = dot4<MAXP>(acc0, hw, a1);
+              acc1 = dot4<MAXP>(acc1, hw, b1);
+            }
+          }
+          acc0 = MAXP ? warp_max(acc0) : warp_sum(acc0);
+          acc1 = MAXP ? warp_max(acc1) : warp_sum(acc1);
+          if (lane == 0) {
+            hn[s] = acc0;
+            if (two) hn[s1] = acc1;
+          }
         }
-        for (; j < S; j += 32) acc = comb<MAXP>(acc, h[j], tw(Tr, Wr, j));
-        acc = MAXP ? warp_max(acc) : warp_sum(acc);
-        if (lane == 0) hn[s] = acc;
+      } else {
+        // one warp per row s, lanes along j
+        for (int s = r0 + warp; s < r1; s += kOhWarps) {
+          const float* __restrict__ Tr = T + (size_t)s * S;
+          const float* __restrict__ Wr = W ? W + (size_t)s * S : nullptr;
+          float acc = init;
+          int j = lane;
+          for (; j + 96 < S; j += 128) {
+            float t0 = tw(Tr, Wr, j);
+            float t1 = tw(Tr, Wr, j + 32);
+            float t2 = tw(Tr, Wr, j + 64);
+            float t3 = tw(Tr, Wr, j + 96);
+            acc = comb<MAXP>(acc, h[j], t0);
+            acc = comb<MAXP>(acc, h[j + 32], t1);
+            acc = comb<MAXP>(acc, h[j + 64], t2);
+            acc = comb<MAXP>(acc, h[j + 96], t3);
+          }
+          for (; j < S; j += 32) acc = comb<MAXP>(acc, h[j], tw(Tr, Wr, j));
+          acc = MAXP ? warp_max(acc) : warp_sum(acc);
+          if (lane == 0) hn[s] = acc;
+        }
       }
       __syncthreads();
-      for (int s = tid; s < S; s += kOhThreads) {
-        float v = apply_nl(hn[s], a.update_nonlinear);
-        if (orow >= 0) out[((size_t)b * a.L + orow) * S + s] = v;
-        h[s] = v * o[s];
+      if (nc == 1) {
+        for (int s = tid; s < S; s += kOhThreads) {
+          float v = apply_nl(hn[s], a.update_nonlinear);
+          if (orow >= 0) out[((size_t)b * a.L + orow) * S + s] = v;
+          h[s] = v * o[s];
+        }
+        __syncthreads();
+      } else {
+        for (int s = r0 + tid; s < r1; s += kOhThreads) xb[s] = hn[s];      // this CTA's rows are final
+        oh_cluster_sync();
+        for (int s = tid; s < S; s += kOhThreads) {
+          const float raw = oh_ld_remote(xb + s, (uint32_t)min(nc - 1, s / rows_per));
+          float v = apply_nl(raw, a.update_nonlinear);
+          if (cr == 0 && orow >= 0) out[((size_t)b * a.L + orow) * S + s] = v;
+          h[s] = v * o[s];
+        }
+        __syncthreads();
       }
-      __syncthreads();
     }
   }
+  if (nc > 1) oh_cluster_sync();      // no CTA may retire while a peer still reads its exchange arrays
 }
 
 // Backward of the sum-semiring recurrence for one (sequence, direction): walks the steps in reverse, keeps the
@@ -333,6 +395,14 @@ extern "C" int re2nn_onehot_backward(const re2nn_onehot_backward_args* a, void* 
   return 0;
 }
 
+static int g_onehot_cluster = 0;      // debug: 0 = pick by batch size; 1, 2, 4 = force the cluster size
+
+extern "C" int re2nn_debug_set_onehot_cluster(int nc) {
+  RE2NN_CHECK((nc & 7) == 0 || (nc & 7) == 1 || (nc & 7) == 2 || (nc & 7) == 4, "debug_set_onehot_cluster: expected 0, 1, 2 or 4 (+8: four instead of eight rows in flight)");
+  g_onehot_cluster = nc;
+  return 0;
+}
+
 extern "C" int re2nn_onehot_recurrence(const re2nn_onehot_args* a, void* stream) {
   RE2NN_CHECK(a != nullptr, "onehot_recurrence: null args");
   RE2NN_CHECK(a->B > 0 && a->L > 0 && a->S > 0 && a->L <= a->Lpad, "onehot_recurrence: bad dims");
@@ -340,16 +410,38 @@ extern "C" int re2nn_onehot_recurrence(const re2nn_onehot_args* a, void* stream)
               "onehot_recurrence: null tensor");
   RE2NN_CHECK(a->update_nonlinear >= RE2NN_NL_NONE && a->update_nonlinear <= RE2NN_NL_RELUTANH,
               "onehot_recurrence: unsupported update_nonlinear %d", a->update_nonlinear);
-  const size_t smem = (size_t)(1 + kOhWarps) * a->S * sizeof(float);
+  const size_t smem = (size_t)(3 + kOhWarps) * a->S * sizeof(float);
   RE2NN_CHECK(smem <= 220 * 1024, "onehot_recurrence: S=%d too large for the shared-memory state", a->S);
-  dim3 grid(a->B, 2);
   cudaStream_t st = (cudaStream_t)stream;
+  // cluster size: spread a (sequence, direction) slice over 2 / 4 CTAs while the batch alone cannot fill the machine
+  int nc = g_onehot_cluster & 7;
+  if (nc == 0) {
+    // measured (tools/bench_onehot_cluster.py, cfg1 shapes): B = 32: 0.69 ms alone, 0.42 ms on CTA pairs, 0.37-0.53 ms
+    // on clusters of four depending on the box; B = 64: pairs = single CTAs; B >= 128: single CTAs win
+    nc = 2L * a->B * 2 <= sm_count() ? 2 : 1;
+  }
+  const int rows8 = (g_onehot_cluster & 8) ? 0 : 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(a->B * nc), 2);
+  cfg.blockDim = dim3(kOhThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)nc;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (a->max_semiring) {
-    RE2NN_CUDA(cudaFuncSetAttribute(onehot_recurrence_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    onehot_recurrence_kernel<true><<<grid, kOhThreads, smem, st>>>(*a);
+    static int configured[kMaxDevices];
+    RE2NN_CUDA(ensure_dynamic_smem(onehot_recurrence_kernel<true>, (int)smem, configured));
+    RE2NN_CUDA(cudaLaunchKernelEx(&cfg, onehot_recurrence_kernel<true>, *a, rows8));
   } else {
-    RE2NN_CUDA(cudaFuncSetAttribute(onehot_recurrence_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    onehot_recurrence_kernel<false><<<grid, kOhThreads, smem, st>>>(*a);
+    static int configured[kMaxDevices];
+    RE2NN_CUDA(ensure_dynamic_smem(onehot_recurrence_kernel<false>, (int)smem, configured));
+    RE2NN_CUDA(cudaLaunchKernelEx(&cfg, onehot_recurrence_kernel<false>, *a, rows8));
   }
   RE2NN_LAUNCH_CHECK();
   return 0;
