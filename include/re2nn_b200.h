@@ -74,6 +74,10 @@ int re2nn_debug_set_tc_cta_group(int cta_group);
 /* debug / calibration: 1 (default) = inference without gates runs the whole recurrence in one resident launch
  * (a CTA pair per 128-row tile iterates over all steps); 0 = one launch per step GEMM. */
 int re2nn_debug_set_resident(int on);
+/* debug / calibration: 1 = large bf16 step GEMMs (N a multiple of 512) run on clusters of 2 x 2 CTAs that TMA-
+ * multicast their A row blocks and B column tiles (a quarter fewer operand bytes requested from L2); 0 (default) =
+ * CTA pairs (cta_group::2) only -- the multicast variant measured 5-10 % slower on B200. */
+int re2nn_debug_set_tc_multicast(int on);
 int re2nn_profile_read(double* ms_out_host, int64_t* count_out_host);
 /* Per-launch [start, end] of kernel class `cls` in ms relative to the earliest start of the class, for up to
  * `cap` launches recorded since the last clearing read.  The event pairs also work inside stream capture (they

@@ -507,6 +507,13 @@ int re2nn_debug_set_tc_cta_group(int cta_group) {
   return 0;
 }
 
+int re2nn_debug_set_tc_multicast(int on) {
+#ifdef RE2NN_HAVE_TC
+  g_tc_multicast = on != 0;
+#endif
+  return 0;
+}
+
 int re2nn_debug_set_resident(int on) {
   g_resident_on = on != 0;
   return 0;
