@@ -6,6 +6,7 @@ The headline line is BASELINE.json configs[1] ("cfg2": V=12000, C=72, S=300, R=2
 update, CRF, beta=0.1) in the parity-grade `auto` precision; the other BASELINE configurations ride on the same JSON
 line under "extra" (each with its own value / roofline / tag-mismatch count / clocks), measured the same way at
 every N:
+    cfg2_gated               cfg2 with farnn = 2 (update + reset gates: what every published .res configuration uses)
     cfg5_bf16, cfg5_parity   configs[4] north-star target: S=1024, R=512, C=128, B=65536, len=64 (bf16 with its
                              stated bound, and the parity-grade mode)
     cfg3_train               configs[2]: training step (fwd + CRF loss + bwd + gradient all-reduce), B=1024 per GPU
@@ -34,7 +35,7 @@ sys.path.insert(0, ROOT)
 METRIC = 'token positions/sec (decompose i-FST inference + Viterbi)'
 UNIT = 'tokens/s'
 METRIC_TRAIN = 'token positions/sec (decompose i-FST training step: fwd + CRF loss + bwd + grad all-reduce)'
-ALL_LEGS = ['cfg2', 'cfg5_bf16', 'cfg5_parity', 'cfg3_train', 'cfg1_onehot', 'cfg5_onehot']
+ALL_LEGS = ['cfg2', 'cfg2_gated', 'cfg5_bf16', 'cfg5_parity', 'cfg3_train', 'cfg1_onehot', 'cfg5_onehot']
 
 
 def parse():
@@ -619,6 +620,9 @@ def main():
         elif leg == 'cfg2':
             results[leg] = leg_decompose(ctx, leg, 'cfg2', a.precision, a.farnn, a.steps, a.warmup, batch=a.batch,
                                          ref_sample=ref_sample, ref_repeats=10, want_cpu_baseline=want_cpu)
+        elif leg == 'cfg2_gated':          # farnn = 2: the configuration of every published .res file
+            results[leg] = leg_decompose(ctx, leg, 'cfg2', a.precision, 2, a.steps, a.warmup, ref_sample=min(ref_sample, 256),
+                                         ref_repeats=1)
         elif leg in ('cfg5_bf16', 'cfg5_parity'):
             results[leg] = leg_decompose(ctx, leg, 'cfg5', 'bf16' if leg == 'cfg5_bf16' else 'auto', 0, max(3, min(ksteps, 5)), 3,
                                          ref_sample=min(ref_sample, 128), ref_repeats=1)

@@ -307,7 +307,11 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_nll_kernel(
   const float* tr = TS ? s_trans : trans_g;
   const int b = blockIdx.x * kCrfWarps + warp;
   if (b >= B) return;
-  const int n = (int)len[b];
+  const int n = min((int)len[b], L);      // lengths past the row are clamped
+  if (n <= 0) {                           // an empty sequence contributes nothing (the reference cannot express it)
+    if (lane == 0) per_seq[b] = 0.f;
+    return;
+  }
   float* pa = s_part + warp * 2 * Tp;
   float* pb = pa + Tp;
   const float* fb = feats + (size_t)b * L * T;
@@ -389,7 +393,11 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_nll_exp_kernel(
   __syncthreads();
   const int b = blockIdx.x * kCrfWarps + warp;
   if (b >= B) return;
-  const int n = (int)len[b];
+  const int n = min((int)len[b], L);      // lengths past the row are clamped
+  if (n <= 0) {                           // an empty sequence contributes nothing (the reference cannot express it)
+    if (lane == 0) per_seq[b] = 0.f;
+    return;
+  }
   float* pa = s_part + warp * 3 * Tp;
   float* pb = pa + Tp;
   float* E = pb + Tp;
@@ -494,8 +502,12 @@ __global__ void crf_nll_backward_kernel(
   const float gs = gscale ? *gscale : 1.f;
   float* dw = s_dtr + (size_t)warp * T * Tq;
   const int b = blockIdx.x * nw + warp;
-  if (b < B) {
-    const int n = (int)len[b];
+  if (b < B && min((int)len[b], L) <= 0) {      // empty sequence: no marginals, zero feature gradient
+    float* df0 = dfeats + (size_t)b * L * T;
+    for (int i = lane; i < L * T; i += 32) df0[i] = 0.f;
+  }
+  if (b < B && min((int)len[b], L) > 0) {
+    const int n = min((int)len[b], L);
     float* ba = s_beta + warp * 2 * Tp;   // beta_t
     float* bb = ba + Tp;                  // beta_{t-1}
     const float* fb = feats + (size_t)b * L * T;
@@ -596,8 +608,12 @@ __global__ void crf_nll_backward_exp_kernel(
   const float gs = gscale ? *gscale : 1.f;
   float* dw = s_dtr + (size_t)warp * T * Tq;
   const int b = blockIdx.x * nw + warp;
-  if (b < B) {
-    const int n = (int)len[b];
+  if (b < B && min((int)len[b], L) <= 0) {      // empty sequence: no marginals, zero feature gradient
+    float* df0 = dfeats + (size_t)b * L * T;
+    for (int i = lane; i < L * T; i += 32) df0[i] = 0.f;
+  }
+  if (b < B && min((int)len[b], L) > 0) {
+    const int n = min((int)len[b], L);
     float* ba = s_vec + warp * 3 * Tp;   // beta_t
     float* bb = ba + Tp;                 // beta_{t-1}
     float* W = bb + Tp;

@@ -92,3 +92,44 @@ def test_argument_errors_are_reported_not_fatal():
     with pytest.raises(KeyError):
         with torch.no_grad():
             m.forward_scores(_t(x), _t(lens))
+
+
+def test_crf_empty_and_overlong_lengths():
+    """A zero-length sequence contributes nothing to the CRF loss, gets a zero feature gradient and decodes to nothing;
+    lengths past the row are clamped; neighbouring sequences are untouched (the kernels used to index
+    position n - 1 = -1)."""
+    import re2nn_seq_b200 as r
+    from re2nn_seq_b200 import synth
+    rs = np.random.RandomState(3)
+    B, L, ntag = 9, 6, 7
+    T = ntag + 2
+    feats = rs.randn(B, L, T).astype(np.float32)
+    tags = rs.randint(0, ntag, size=(B, L)).astype(np.int64)
+    lens = rs.randint(1, L + 1, size=B).astype(np.int64)
+    crf = r.CRF(ntag, True).cuda()
+    with torch.no_grad():
+        crf.transitions.copy_(_t(synth.crf_transitions(1, T)))
+
+    def run(fe, tg, lengths):
+        f = _t(fe).requires_grad_(True)
+        crf.transitions.grad = None
+        loss = crf.neg_log_likelihood_loss(f, None, _t(tg), lengths=_t(lengths))
+        loss.backward()
+        return loss.item(), f.grad.cpu().numpy(), crf.transitions.grad.cpu().numpy().copy()
+
+    keep = np.arange(B) != 4
+    l2, g2, t2 = run(feats[keep], tags[keep], lens[keep])          # the same batch without sequence 4
+    lens0 = lens.copy()
+    lens0[4] = 0
+    l0, g0, t0 = run(feats, tags, lens0)
+    assert abs(l0 - l2) <= 1e-5 * abs(l2)
+    assert np.abs(g0[4]).max() == 0.0
+    np.testing.assert_allclose(g0[keep], g2, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(t0, t2, rtol=1e-4, atol=1e-5)
+    lens_big = lens.copy()
+    lens_big[2] = L + 5                                    # clamped to the row
+    lens_clamped = lens.copy()
+    lens_clamped[2] = L
+    la, ga, _ = run(feats, tags, lens_big)
+    lb, gb, _ = run(feats, tags, lens_clamped)
+    assert la == lb and np.array_equal(ga, gb)
