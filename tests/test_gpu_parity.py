@@ -293,12 +293,15 @@ def test_crf_viterbi_large_batch(B, ntag):
     np.testing.assert_array_equal(path.cpu().numpy(), want)
 
 
-@pytest.mark.parametrize('B,ntag,L', [(700, 129, 12), (300, 198, 7), (90, 258, 6)])
-def test_crf_viterbi_wide_tagsets(B, ntag, L):
+@pytest.mark.parametrize('seqs_per_warp', [1, 2])
+@pytest.mark.parametrize('B,ntag,L', [(700, 129, 12), (300, 198, 7), (90, 258, 6), (333, 34, 9)])
+def test_crf_viterbi_wide_tagsets(B, ntag, L, seqs_per_warp):
     """T = 131 (cfg5: five target tags per lane), T = 200 (generic shared-memory sweep) and T = 260 (transition table
     beyond shared memory: global-memory kernel), real-valued features with many exact ties, one empty sequence:
     paths bit-exact against the restatement of crf.py:102-195."""
     import re2nn_seq_b200 as r
+    from re2nn_seq_b200 import _lib
+    _lib.check(_lib.fn['re2nn_debug_set_viterbi_seqs'](seqs_per_warp), 'seqs')
     rs = np.random.RandomState(ntag)
     T = ntag + 2
     feats = (rs.randint(-8, 9, size=(B, L, T)) * 0.25).astype(np.float32)
@@ -325,3 +328,4 @@ def test_crf_viterbi_wide_tagsets(B, ntag, L):
     assert (p0[1] == 0).all()
     keep = np.arange(B) != 1
     np.testing.assert_array_equal(p0[keep], want[keep])
+    _lib.check(_lib.fn['re2nn_debug_set_viterbi_seqs'](0), 'seqs')
