@@ -7,6 +7,7 @@ update, CRF, beta=0.1) in the parity-grade `auto` precision; the other BASELINE 
 line under "extra" (each with its own value / roofline / tag-mismatch count / clocks), measured the same way at
 every N:
     cfg2_gated               cfg2 with farnn = 2 (update + reset gates: what every published .res configuration uses)
+    cfg4                     configs[3]: ATIS-ZH-shaped long recurrence (S=512, R=256, len<=128), B=4096
     cfg5_bf16, cfg5_parity   configs[4] north-star target: S=1024, R=512, C=128, B=65536, len=64 (bf16 with its
                              stated bound, and the parity-grade mode)
     cfg3_train               configs[2]: training step (fwd + CRF loss + bwd + gradient all-reduce), B=1024 per GPU
@@ -35,7 +36,7 @@ sys.path.insert(0, ROOT)
 METRIC = 'token positions/sec (decompose i-FST inference + Viterbi)'
 UNIT = 'tokens/s'
 METRIC_TRAIN = 'token positions/sec (decompose i-FST training step: fwd + CRF loss + bwd + grad all-reduce)'
-ALL_LEGS = ['cfg2', 'cfg2_gated', 'cfg5_bf16', 'cfg5_parity', 'cfg3_train', 'cfg1_onehot', 'cfg5_onehot']
+ALL_LEGS = ['cfg2', 'cfg2_gated', 'cfg4', 'cfg5_bf16', 'cfg5_parity', 'cfg3_train', 'cfg1_onehot', 'cfg5_onehot']
 
 
 def parse():
@@ -623,6 +624,9 @@ def main():
         elif leg == 'cfg2_gated':          # farnn = 2: the configuration of every published .res file
             results[leg] = leg_decompose(ctx, leg, 'cfg2', a.precision, 2, a.steps, a.warmup, ref_sample=min(ref_sample, 256),
                                          ref_repeats=1)
+        elif leg == 'cfg4':                # configs[3]: ATIS-ZH-shaped long recurrence (S=512, R=256, len<=128, B=4096)
+            results[leg] = leg_decompose(ctx, leg, 'cfg4', a.precision, 0, max(3, min(ksteps, 10)), 3,
+                                         ref_sample=min(ref_sample, 128), ref_repeats=1)
         elif leg in ('cfg5_bf16', 'cfg5_parity'):
             results[leg] = leg_decompose(ctx, leg, 'cfg5', 'bf16' if leg == 'cfg5_bf16' else 'auto', 0, max(3, min(ksteps, 5)), 3,
                                          ref_sample=min(ref_sample, 128), ref_repeats=1)
