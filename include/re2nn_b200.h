@@ -163,6 +163,10 @@ typedef struct re2nn_recurrence_args {
    * Size: re2nn_label_scores_ab_bytes().  Ignored (alpha / beta written as usual) when the call takes the resident
    * kernel: query re2nn_decompose_recurrence_fuses(). */
   void* ab_out;
+  /* Operand-format copies of S1 / S2 / W / gate weights prepared once by re2nn_decompose_weight_prep (optional, tensor-
+   * core precisions): when non-NULL the call skips its 6-8 conversion launches.  The caller keeps the buffer valid and
+   * re-prepares it when a parameter changes. */
+  const void* wprep;
 } re2nn_recurrence_args;
 
 size_t re2nn_decompose_recurrence_workspace(const re2nn_recurrence_args* a);
@@ -170,6 +174,9 @@ int re2nn_decompose_recurrence(const re2nn_recurrence_args* a, void* stream);
 /* Number of kernels re2nn_decompose_recurrence launches for this argument block (inference without gates on the
  * tensor-core paths runs ALL steps in one resident kernel; otherwise 2-3 step GEMMs per step). */
 int re2nn_decompose_recurrence_launches(const re2nn_recurrence_args* a);
+/* Converted weight copies for `wprep` (only S, R, farnn, precision and the weight pointers of the block are read). */
+size_t re2nn_decompose_weight_prep_bytes(const re2nn_recurrence_args* a);
+int re2nn_decompose_weight_prep(const re2nn_recurrence_args* a, void* out, void* stream);
 /* 1 when a call with these arguments (and a non-NULL ab_out) would write the fused (alpha*beta) operand. */
 int re2nn_decompose_recurrence_fuses(const re2nn_recurrence_args* a);
 /* 1 when the call would take the resident single-launch path (only precision, S, R, farnn and save_for_backward of

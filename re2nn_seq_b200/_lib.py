@@ -43,7 +43,7 @@ class RecurrenceArgs(C.Structure):
         ('x', vp), ('lengths', vp), ('vtab', vp), ('gtab', vp), ('S1', vp), ('S2', vp), ('W', vp),
         ('o', vp), ('h0', vp), ('hT', vp), ('Wss1', vp), ('Wss2', vp), ('alpha', vp), ('beta', vp),
         ('hbar_save', vp), ('hst_save', vp), ('u_save', vp), ('a_save', vp), ('zsave', vp), ('rsave', vp),
-        ('ws', vp), ('ws_bytes', sz), ('ab_out', vp),
+        ('ws', vp), ('ws_bytes', sz), ('ab_out', vp), ('wprep', vp),
     ]
 
 
@@ -113,6 +113,8 @@ SYMBOLS = {
     're2nn_decompose_recurrence_launches': (C.c_int, [C.POINTER(RecurrenceArgs)]),
     're2nn_decompose_recurrence_resident': (C.c_int, [C.POINTER(RecurrenceArgs)]),
     're2nn_decompose_recurrence_fuses': (C.c_int, [C.POINTER(RecurrenceArgs)]),
+    're2nn_decompose_weight_prep_bytes': (sz, [C.POINTER(RecurrenceArgs)]),
+    're2nn_decompose_weight_prep': (C.c_int, [C.POINTER(RecurrenceArgs), vp, vp]),
     're2nn_label_scores_ab_bytes': (sz, [C.c_int, C.c_int, C.c_int, C.c_int]),
     're2nn_label_scores_ab': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_int, vp, vp, sz, vp]),
     're2nn_decompose_recurrence': (C.c_int, [C.POINTER(RecurrenceArgs), vp]),

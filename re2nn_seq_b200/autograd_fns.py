@@ -35,6 +35,20 @@ def _prepare(consts, p, dense_v, cache):
     return vtab, gtab, o
 
 
+def _weight_prep(consts, p, cache):
+    """Operand-format weight copies, cached per parameter version (inference on the tensor-core precisions)."""
+    prec = consts['precision']
+    if cache is None or prec == 'fp32' or consts.get('max_semiring'):
+        return None
+    deps = [p[n] for n in ('S1', 'S2', 'wildcard_mat', 'Wss1', 'Wss2') if n in p]
+    key = (_key(deps), prec, consts['farnn'])
+    if cache.get('wkey') == key:
+        return cache['wprep']
+    buf = ops.weight_prep(p['S1'], p['S2'], p['wildcard_mat'], p.get('Wss1'), p.get('Wss2'), consts['farnn'], prec)
+    cache.update(wkey=key, wprep=buf)
+    return buf
+
+
 class _DecomposeScores(torch.autograd.Function):
     @staticmethod
     def forward(ctx, consts, names, pr, x, dense_v, lengths, L, cache, *tensors):
@@ -46,6 +60,7 @@ class _DecomposeScores(torch.autograd.Function):
         if mx:
             need_grad = False        # inference-only semiring; backward raises
         vtab, gtab, o = _prepare(consts, p, dense_v, None if need_grad else cache)
+        wprep = None if need_grad else _weight_prep(consts, p, cache)
         Lpad = x.shape[1] if dense_v is None else dense_v.shape[1]
         pm, pb = (pr if consts['use_priority'] else (None, None))
         if consts.get('fuse_scores') and not need_grad and not mx and consts['farnn'] == 0 and not consts['full_pad'] \
@@ -53,7 +68,7 @@ class _DecomposeScores(torch.autograd.Function):
             # decode-only inference: (alpha * beta) comes straight out of the forward direction's epilogue
             fused = ops.decompose_recurrence_fused(x, lengths, L, vtab, p['S1'], p['S2'], p['wildcard_mat'], o, p['h0'],
                                                    p['hT'], consts['update_nonlinear'], consts['precision'],
-                                                   v_mode=V_TOKEN if dense_v is None else V_DENSE, Lpad=Lpad)
+                                                   v_mode=V_TOKEN if dense_v is None else V_DENSE, Lpad=Lpad, wprep=wprep)
             if fused is not None:
                 B, S = lengths.shape[0], p['S1'].shape[0]
                 return ops.label_scores_ab(fused[0], B, L, S, p['C_output_mat'], pm, pb, consts['precision'])
@@ -61,7 +76,7 @@ class _DecomposeScores(torch.autograd.Function):
             x, lengths, L, vtab, gtab, p['S1'], p['S2'], p['wildcard_mat'], o, p['h0'], p['hT'],
             p.get('Wss1'), p.get('Wss2'), consts['farnn'], consts['update_nonlinear'], consts['sigmoid_exponent'],
             precision=consts['precision'], v_mode=V_TOKEN if dense_v is None else V_DENSE,
-            full_pad=consts['full_pad'], save_for_backward=need_grad, Lpad=Lpad, max_semiring=mx)
+            full_pad=consts['full_pad'], save_for_backward=need_grad, Lpad=Lpad, max_semiring=mx, wprep=wprep)
         scores = ops.label_scores(alpha, beta, lengths, p['C_output_mat'], pm, pb, full_pad=consts['full_pad'],
                                   precision='fp32' if mx else consts['precision'])
         if need_grad:

@@ -90,6 +90,14 @@ __global__ void convert_weight_kernel(const float* src, int N, int K, int ld_src
   }
 }
 
+// operand pointers of the tensor-core formats (the buffers hold the converted copies)
+inline void weight_prep_bind(WeightPrep& w, int farnn) {
+  w.g1[0] = w.buf[0]; w.g1[1] = w.buf[1];
+  w.g2q[0] = w.buf[2]; w.g2q[1] = w.buf[3];
+  w.g2w[0] = w.buf[4]; w.g2w[1] = w.buf[5];
+  if (farnn >= 1) w.gate = w.buf[6];
+}
+
 template <int PREC>
 inline int weight_prep_run(const re2nn_recurrence_args& a, WeightPrep& w, cudaStream_t st) {
   const int S = a.S, R = a.R;
@@ -120,14 +128,11 @@ inline int weight_prep_run(const re2nn_recurrence_args& a, WeightPrep& w, cudaSt
   RE2NN_CUDA(conv(a.S1, S, R, R, 0, w.buf[3], w.ldR, pl_g2q, 0));
   RE2NN_CUDA(conv(a.W, S, S, S, 1, w.buf[4], w.ldS, pl_ss, 0));    // fwd: B[k=s][n=j] = W[s][j] -> [n][k] = W^T
   RE2NN_CUDA(conv(a.W, S, S, S, 0, w.buf[5], w.ldS, pl_ss, 0));    // bwd: B[k][n] = W[n][k]   -> [n][k] = W
-  w.g1[0] = w.buf[0]; w.g1[1] = w.buf[1];
-  w.g2q[0] = w.buf[2]; w.g2q[1] = w.buf[3];
-  w.g2w[0] = w.buf[4]; w.g2w[1] = w.buf[5];
   if (a.farnn >= 1) {
     RE2NN_CUDA(conv(a.Wss1, S, S, S, 1, w.buf[6], w.ldS, pl_gate, 0));
     if (a.farnn == 2) RE2NN_CUDA(conv(a.Wss2, S, S, S, 1, w.buf[6], w.ldS, pl_gate, S));
-    w.gate = w.buf[6];
   }
+  weight_prep_bind(w, a.farnn);
   return 0;
 }
 

@@ -55,7 +55,10 @@ static size_t carve(const re2nn_recurrence_args& a, char* base, RecWs* ws) {
       w.Z[z] = (float*)take((size_t)a.B * a.S * 4);
     }
   }
-  off += weight_prep_carve(prec, a.S, a.R, a.farnn, base ? base + off : nullptr, &w.wp);
+  if (a.wprep != nullptr && prec != RE2NN_PREC_FP32)      // converted weights supplied by the caller (cached per parameter version)
+    weight_prep_carve(prec, a.S, a.R, a.farnn, (char*)a.wprep, &w.wp);
+  else
+    off += weight_prep_carve(prec, a.S, a.R, a.farnn, base ? base + off : nullptr, &w.wp);
   if (ws) *ws = w;
   return off;
 }
@@ -178,7 +181,8 @@ static int run_recurrence(const re2nn_recurrence_args& a, cudaStream_t st) {
   RE2NN_CHECK(PREC == RE2NN_PREC_FP32 || L < 32768, "decompose_recurrence: tensor-core paths keep output rows in 16 bits (L=%d)", L);
   const size_t h_plane = (size_t)B * ldh, q_plane = (size_t)B * ldq;
 
-  if (int rc = weight_prep_run<PREC>(a, w.wp, st)) return rc;
+  if (a.wprep != nullptr && PREC != RE2NN_PREC_FP32) weight_prep_bind(w.wp, a.farnn);
+  else if (int rc = weight_prep_run<PREC>(a, w.wp, st)) return rc;
   tile_last_kernel<<<cdiv(B, 128), 128, 0, st>>>(a.lengths, B, w.tile_last[0], w.tile_last[1]);
   RE2NN_LAUNCH_CHECK();
   {
@@ -606,11 +610,32 @@ int re2nn_decompose_recurrence_resident(const re2nn_recurrence_args* a) {
   return takes_resident_path(*a) ? 1 : 0;
 }
 
+size_t re2nn_decompose_weight_prep_bytes(const re2nn_recurrence_args* a) {
+  if (!a || a->precision == RE2NN_PREC_FP32) return 0;
+  return weight_prep_carve(a->precision, a->S, a->R, a->farnn, nullptr, nullptr);
+}
+
+int re2nn_decompose_weight_prep(const re2nn_recurrence_args* a, void* out, void* stream) {
+  RE2NN_CHECK(a && out && a->S1 && a->S2 && a->W, "decompose_weight_prep: null tensor");
+  RE2NN_CHECK(a->precision != RE2NN_PREC_FP32, "decompose_weight_prep: the fp32 path uses the parameters as they are");
+  RE2NN_CHECK(a->farnn == 0 || a->Wss1, "decompose_weight_prep: farnn>=1 needs Wss1");
+  RE2NN_CHECK(a->farnn < 2 || a->Wss2, "decompose_weight_prep: farnn==2 needs Wss2");
+  WeightPrep wp;
+  weight_prep_carve(a->precision, a->S, a->R, a->farnn, (char*)out, &wp);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (a->precision) {
+    case RE2NN_PREC_BF16: return weight_prep_run<RE2NN_PREC_BF16>(*a, wp, st);
+    case RE2NN_PREC_TF32X3: return weight_prep_run<RE2NN_PREC_TF32X3>(*a, wp, st);
+    case RE2NN_PREC_FP16X3: return weight_prep_run<RE2NN_PREC_FP16X3>(*a, wp, st);
+    default: return set_error("decompose_weight_prep: unknown precision %d", a->precision);
+  }
+}
+
 int re2nn_decompose_recurrence_launches(const re2nn_recurrence_args* a) {
   if (!a) return -1;
   int n = 2;                                                     // tile_last + rec_init
   if (a->precision == RE2NN_PREC_FP32) n += a->farnn == 2 ? 1 : 0;   // [Wss1 | Wss2] concat
-  else n += 6 + a->farnn;                                        // operand-format copies of the weights
+  else if (a->wprep == nullptr) n += 6 + a->farnn;               // operand-format copies of the weights
   if (a->ab_out && decompose_fuses(*a)) n += a->L * 4;          // single-direction launches, two directions
   else n += takes_resident_path(*a) ? 1 : a->L * (2 + (a->farnn >= 1 ? 1 : 0));
   return n;

@@ -52,7 +52,8 @@ std::tuple<Tensor, Tensor> ifst_decompose_forward(const optional<Tensor>& x, con
                                                   const Tensor& W, const Tensor& o, const Tensor& h0, const Tensor& hT,
                                                   const optional<Tensor>& Wss1, const optional<Tensor>& Wss2, int64_t L,
                                                   int64_t Lpad, int64_t farnn, int64_t update_nonlinear, int64_t precision,
-                                                  int64_t v_mode, bool full_pad, double sigmoid_exponent, bool max_semiring) {
+                                                  int64_t v_mode, bool full_pad, double sigmoid_exponent, bool max_semiring,
+                                                  const optional<Tensor>& wprep) {
   c10::cuda::CUDAGuard guard(S1.device());
   const int64_t B = lengths.size(0), S = S1.size(0), R = S1.size(1);
   re2nn_recurrence_args a;
@@ -66,6 +67,11 @@ std::tuple<Tensor, Tensor> ifst_decompose_forward(const optional<Tensor>& x, con
   a.S1 = f32(S1, "S1"); a.S2 = f32(S2, "S2"); a.W = f32(W, "wildcard_mat"); a.o = f32(o, "o");
   a.h0 = f32(h0, "h0"); a.hT = f32(hT, "hT"); a.Wss1 = f32(Wss1, "Wss1"); a.Wss2 = f32(Wss2, "Wss2");
   a.alpha = alpha.data_ptr<float>(); a.beta = beta.data_ptr<float>();
+  if (wprep.has_value() && !max_semiring) {      // operand-format weight copies prepared by re2nn_decompose_weight_prep
+    TORCH_CHECK(wprep->is_cuda() && wprep->is_contiguous(), "re2nn_b200: wprep must be a contiguous CUDA buffer");
+    TORCH_CHECK((size_t)wprep->nbytes() >= re2nn_decompose_weight_prep_bytes(&a), "re2nn_b200: wprep buffer too small");
+    a.wprep = wprep->data_ptr();
+  }
   if (max_semiring) {
     Tensor ws = bytes(re2nn_decompose_max_workspace((int)S, (int)R), S1);
     a.ws = ws.data_ptr(); a.ws_bytes = (size_t)ws.numel();
@@ -178,7 +184,7 @@ int64_t abi_version() { return re2nn_abi_version(); }
 TORCH_LIBRARY(re2nn, m) {
   m.def("ifst_decompose_forward(Tensor? x, Tensor lengths, Tensor vtab, Tensor? gtab, Tensor S1, Tensor S2, Tensor W, Tensor o, "
         "Tensor h0, Tensor hT, Tensor? Wss1, Tensor? Wss2, int L, int Lpad, int farnn, int update_nonlinear, int precision, "
-        "int v_mode, bool full_pad, float sigmoid_exponent, bool max_semiring) -> (Tensor, Tensor)");
+        "int v_mode, bool full_pad, float sigmoid_exponent, bool max_semiring, Tensor? wprep) -> (Tensor, Tensor)");
   m.def("ifst_onehot_forward(Tensor x, Tensor lengths, Tensor language_sum, Tensor o, Tensor h0, Tensor hT, int L, "
         "int update_nonlinear, bool max_semiring, bool full_pad) -> (Tensor, Tensor)");
   m.def("label_scores(Tensor alpha, Tensor beta, Tensor lengths, Tensor C_mat, Tensor? priority_mat, Tensor? priority_bias, "

@@ -233,8 +233,11 @@ class _DecomposeBase(nn.Module):
         return [(b0, min(B, b0 + per)) for b0 in range(0, B, per)]
 
     def _warm_tables(self):
-        """Token / gate tables and the output-vector sum into the per-module cache (no-op for dense factors)."""
-        return None
+        """Everything cached per parameter version, computed on the CURRENT stream before chunk streams fork: the
+        operand-format weight copies here, the token / gate tables and the output-vector sum in the subclass."""
+        names = self._params_for_fn()
+        p = {n: getattr(self, n).detach().contiguous() for n in names}
+        autograd_fns._weight_prep(self._recurrence_consts(), p, self._cache)
 
     # Capture policy.  An evaluation sweep (val.py:7-43 runs train / dev / test after every epoch) sees a new
     # (B, L) almost every batch and new parameter versions every epoch; capturing each of them would cost a warm-up
@@ -447,6 +450,7 @@ class FARNN_S_D_W_I_S(_DecomposeBase):
         names, tensors = self._fn_params()
         p = {n: t.detach().contiguous() for n, t in zip(names, tensors)}
         autograd_fns._prepare(self._recurrence_consts(), p, None, self._cache)
+        autograd_fns._weight_prep(self._recurrence_consts(), p, self._cache)
 
     def forward_local(self, input, label, lengths, train=True, re_tags=None):
         dev = self._device()
@@ -519,7 +523,7 @@ class FARNN_S_SF(_DecomposeBase):
             return ifst_decompose_max_scores(self, None, v, lengths, shape[0])
         pr = (self.priority_layer.priority_mat, self.priority_layer.priority_bias)
         return autograd_fns.decompose_scores(dict(self._recurrence_consts(), fuse_scores=bool(fuse)), names, tensors, pr, None,
-                                             v, lengths, shape[0])
+                                             v, lengths, shape[0], cache=self._cache)
 
     def _scores_from(self, inp, lengths, shape, fuse=False):
         return self.forward_scores(inp, lengths, shape, fuse=fuse)

@@ -93,7 +93,8 @@ def output_vector_sum(C_mat, wildcard_vec=None):
 
 def decompose_recurrence(x, lengths, L, vtab, gtab, S1, S2, W, o, h0, hT, Wss1, Wss2, farnn,
                          update_nonlinear, sigmoid_exponent, precision='fp32', v_mode=V_TOKEN,
-                         full_pad=False, save_for_backward=False, Lpad=None, max_semiring=False, zero_fill=False):
+                         full_pad=False, save_for_backward=False, Lpad=None, max_semiring=False, zero_fill=False,
+                         wprep=None):
     """Returns (alpha, beta, saves): alpha/beta B x L x S (pad rows undefined); saves = per-step slabs or None."""
     B = lengths.shape[0]
     S, R = S1.shape
@@ -121,9 +122,12 @@ def decompose_recurrence(x, lengths, L, vtab, gtab, S1, S2, W, o, h0, hT, Wss1, 
         # inference: the registered custom op (allocates alpha / beta and the workspace itself)
         for t in (lengths, vtab, S1, S2, W, o, h0, hT):
             _p(t)
+        if precision == 'fp32' or max_semiring:
+            wprep = None
         alpha, beta = tops.ifst_decompose_forward(x, lengths, vtab, gtab, S1, S2, W, o, h0, hT, Wss1, Wss2, L, a.Lpad, farnn,
                                                   a.update_nonlinear, a.precision, v_mode, bool(full_pad),
-                                                  float(sigmoid_exponent), bool(max_semiring))
+                                                  float(sigmoid_exponent), bool(max_semiring), wprep)
+        a.wprep = C.c_void_p(wprep.data_ptr()) if wprep is not None else None
         _count(3 if max_semiring else fn['re2nn_decompose_recurrence_launches'](C.byref(a)))
         return alpha, beta, None
     a.x = _i64(x) if x is not None else None
@@ -148,8 +152,24 @@ def decompose_recurrence(x, lengths, L, vtab, gtab, S1, S2, W, o, h0, hT, Wss1, 
     return alpha, beta, saves
 
 
+def weight_prep(S1, S2, W, Wss1, Wss2, farnn, precision):
+    """Operand-format copies of the recurrence weights for `wprep` (tensor-core precisions): 6-8 conversion launches
+    once per parameter version instead of once per call."""
+    S, R = S1.shape
+    a = RecurrenceArgs()
+    a.S, a.R, a.farnn, a.precision = S, R, farnn, PREC[precision]
+    a.S1, a.S2, a.W = _f32(S1), _f32(S2), _f32(W)
+    a.Wss1 = _f32(Wss1) if Wss1 is not None else None
+    a.Wss2 = _f32(Wss2) if Wss2 is not None else None
+    need = fn['re2nn_decompose_weight_prep_bytes'](C.byref(a))
+    buf = torch.empty((need,), dtype=torch.uint8, device=S1.device)
+    check(fn['re2nn_decompose_weight_prep'](C.byref(a), C.c_void_p(buf.data_ptr()), _stream()), 'decompose_weight_prep')
+    _count(6 + farnn)
+    return buf
+
+
 def decompose_recurrence_fused(x, lengths, L, vtab, S1, S2, W, o, h0, hT, update_nonlinear, precision, v_mode=V_TOKEN,
-                               Lpad=None):
+                               Lpad=None, wprep=None):
     """Inference without gates on the per-step tensor-core path: the backward direction runs first and the forward
     direction's state epilogue writes (alpha * beta) straight in operand format, so alpha is never materialised and
     label scoring does not re-read the states.  -> (ab operand buffer, beta) or None when the call would not fuse
@@ -173,6 +193,8 @@ def decompose_recurrence_fused(x, lengths, L, vtab, S1, S2, W, o, h0, hT, update
     a.vtab = _f32(vtab)
     a.S1, a.S2, a.W, a.o, a.h0, a.hT = _f32(S1), _f32(S2), _f32(W), _f32(o), _f32(h0), _f32(hT)
     a.beta = _f32(beta)
+    if wprep is not None:
+        a.wprep = C.c_void_p(wprep.data_ptr())
     need = fn['re2nn_decompose_recurrence_workspace'](C.byref(a))
     ws = torch.empty((need,), dtype=torch.uint8, device=dev)
     a.ws, a.ws_bytes = C.c_void_p(ws.data_ptr()), need
