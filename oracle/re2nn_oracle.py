@@ -178,6 +178,22 @@ def ce_loss(flat_scores, flat_labels):
     return (lse - picked).mean(dtype=flat_scores.dtype)
 
 
+def ml_loss(flat_scores, flat_labels, margin):
+    """nn.MultiMarginLoss(margin) (p = 1, mean): sum_{j != y} max(0, margin - x_y + x_j) / C per token
+    (local_loss_func == 'ML': model_decompose.py:84-85, model_onehot.py:61-62)."""
+    n, C = flat_scores.shape
+    picked = flat_scores[np.arange(n), flat_labels][:, None]
+    h = np.maximum(0, flat_scores.dtype.type(margin) - picked + flat_scores)
+    h[np.arange(n), flat_labels] = 0
+    return (h.sum(1, dtype=flat_scores.dtype) / flat_scores.dtype.type(C)).mean(dtype=flat_scores.dtype)
+
+
+def local_loss(flat_scores, flat_labels, args):
+    if args.local_loss_func == 'ML':
+        return ml_loss(flat_scores, flat_labels, args.margin)
+    return ce_loss(flat_scores, flat_labels)
+
+
 def decode(p, all_scores, lengths, args, C, o_idx, use_crf):
     """model_decompose.py:339-371 decode.  C already includes the +2 CRF tags when use_crf."""
     if use_crf:
@@ -210,7 +226,7 @@ def decompose_forward_local(p, x, label, lengths, args, o_idx=0, train=True, den
         if use_crf:
             loss = crf_nll(all_scores, length_mask(lengths), label, p['crf_transitions'])
         else:
-            loss = ce_loss(flatten_rows(all_scores, lengths), flat_true)
+            loss = local_loss(flatten_rows(all_scores, lengths), flat_true, args)
     pred = decode(p, all_scores, lengths, args, C, o_idx, use_crf)
     return loss, pred, flat_true, all_scores
 
@@ -266,7 +282,7 @@ def onehot_forward_local(p, x, label, lengths, args, o_idx=0, train=True):
     all_scores = onehot_scores(p, x, lengths, args)
     flat_true = flatten_rows(label, lengths)
     flat_scores = flatten_rows(all_scores, lengths)
-    loss = ce_loss(flat_scores, flat_true) if train else None
+    loss = local_loss(flat_scores, flat_true, args) if train else None
     pred = onehot_local_decode(flat_scores, args, p['output_mat'].shape[0], o_idx)
     return loss, pred, flat_true, all_scores
 

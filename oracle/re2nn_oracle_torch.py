@@ -107,6 +107,8 @@ def decompose_loss(p, x, labels, lengths, args, dense_v=None):
         return crf_nll(scores, lengths, labels, p['crf_transitions']), scores
     mask = torch.arange(L)[None, :] < lengths[:, None]
     flat = scores[mask]
+    if args.local_loss_func == 'ML':      # nn.MultiMarginLoss(margin)  (model_decompose.py:84-85)
+        return torch.nn.functional.multi_margin_loss(flat, labels[:, :L][mask], margin=float(args.margin)), scores
     return torch.nn.functional.cross_entropy(flat, labels[:, :L][mask]), scores
 
 

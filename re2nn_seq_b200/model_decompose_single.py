@@ -61,8 +61,8 @@ class _DecomposeBase(nn.Module):
         self.additional_nonlinear = a.additional_nonlinear
         if a.train_mode not in ('sum', 'max'):
             raise NotImplementedError()
-        if a.local_loss_func not in ('CE', 'CE1'):
-            raise NotImplementedError("re2nn_b200: only the cross-entropy local losses are built (CE, CE1)")
+        if a.local_loss_func not in ('CE', 'CE1', 'ML'):
+            raise NotImplementedError()
         if a.sigmoid_exponent <= 0 and a.farnn:
             raise AssertionError("sigmoid_exponent must be positive")
         # inference default: the fastest PARITY-GRADE mode of the device (split-fp16 / 3xTF32 tensor cores: scores within
@@ -339,6 +339,9 @@ class _DecomposeBase(nn.Module):
             lab = label.contiguous()
             if self.use_crf:
                 loss = self.crf.neg_log_likelihood_loss(all_scores, None, lab, lengths=lengths)
+            elif self.args.local_loss_func == 'ML':
+                from .kd import ml_loss
+                loss = ml_loss(all_scores, lengths, lab, self.args.margin)
             else:
                 # under data parallelism every rank divides by the GLOBAL token count (re2nn_seq_b200/dist.py)
                 loss = autograd_fns.ce_loss(all_scores, lengths, lab, getattr(self, 'global_tokens', None) or N)

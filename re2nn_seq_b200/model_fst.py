@@ -545,8 +545,8 @@ class FARNN_S_O(nn.Module):
     def initialize(self):
         a = self.args
         self.t = 1
-        if a.local_loss_func not in ('CE', 'CE1'):
-            raise NotImplementedError("re2nn_b200: only the cross-entropy local losses are built (CE, CE1)")
+        if a.local_loss_func not in ('CE', 'CE1', 'ML'):
+            raise NotImplementedError()
 
     def _device(self):
         ops.require_cuda()
@@ -611,7 +611,10 @@ class FARNN_S_O(nn.Module):
         label = label.to(dev)
         flattened_true_labels = flatten(label, dl)
         loss = None
-        if train:
+        if train and self.args.local_loss_func == 'ML':
+            from .kd import ml_loss
+            loss = ml_loss(scores, dl, label, self.args.margin)
+        elif train:
             loss = autograd_fns.ce_loss(scores, dl, label.contiguous(), N)
         with torch.no_grad():
             ce1 = self.args.local_loss_func == 'CE1'

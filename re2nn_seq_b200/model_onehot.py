@@ -49,8 +49,8 @@ class FARNN_S_O_I_S(nn.Module):
     def initialize(self):
         a = self.args
         self.t = 1
-        if a.local_loss_func not in ('CE', 'CE1'):
-            raise NotImplementedError("re2nn_b200: only the cross-entropy local losses are built (CE, CE1)")
+        if a.local_loss_func not in ('CE', 'CE1', 'ML'):
+            raise NotImplementedError()
         self.full_pad = False
 
     def invalidate_caches(self):
@@ -131,7 +131,10 @@ class FARNN_S_O_I_S(nn.Module):
         label = label.to(dev)
         flattened_true_labels = flatten(label, dl)
         loss = None
-        if train:
+        if train and self.args.local_loss_func == 'ML':
+            from .kd import ml_loss
+            loss = ml_loss(scores, dl, label, self.args.margin)
+        elif train:
             loss = autograd_fns.ce_loss(scores, dl, label.contiguous(), N)
         with torch.no_grad():
             ce1 = self.args.local_loss_func == 'CE1'

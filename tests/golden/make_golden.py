@@ -210,6 +210,8 @@ def main():
                                                      marryup_type='kd', c1_kdpr=2.0, c2_kdpr=0.4), marry=True)
     decompose_case('dec_f2_tanh_crf_pr', 22, dims, dict(farnn=2, update_nonlinear='tanh', use_crf=1, beta=0.2,
                                                       marryup_type='pr', c1_kdpr=1.5, c2_kdpr=0.3, c3_pr=0.9), marry=True)
+    decompose_case('dec_f0_tanh_ml', 23, dims, dict(farnn=0, update_nonlinear='tanh', use_crf=0, beta=0.3,
+                                                  local_loss_func='ML', margin=0.3))
     decompose_case('sf_f2_tanh_crf', 19, dims, dict(farnn=2, update_nonlinear='tanh', use_crf=1), sf=True)
     decompose_case('sf_f0_relu_ce', 20, dims, dict(farnn=0, update_nonlinear='relu', use_crf=0), sf=True)
     odims = (25, 11, 4, 6, 8)          # V, S, C, B, Lmax
@@ -218,6 +220,7 @@ def main():
     onehot_case('one_max_relu', 32, odims, dict(update_nonlinear='relu', train_mode='max'), noise=1e-2)
     onehot_case('one_sum_relutanh_ce_prio', 33, odims, dict(update_nonlinear='relutanh', local_loss_func='CE',
                                                            use_priority=1), noise=1e-2, priority=True)
+    onehot_case('one_sum_relu_ml', 34, odims, dict(update_nonlinear='relu', local_loss_func='ML', margin=0.5), noise=1e-2)
     crf_case('crf_rand', 40, 6, 9, 11)
     crf_case('crf_ties', 41, 5, 8, 7, integer_feats=True)
     crf_case('crf_single', 42, 3, 1, 1)

@@ -47,10 +47,10 @@ def golden_seed(name):
     """Seed used by tests/golden/make_golden.py for this case (see its main())."""
     order = ['dec_f0_tanh_crf', 'dec_f0_none_ce', 'dec_f1_relu_ce', 'dec_f2_tanh_crf_add', 'dec_f2_relutanh_ce_all',
              'dec_f0_tanh_max', 'dec_f0_prio_crf_sig', 'dec_f1_tanh_ce_plain', 'dec_f2_none_crf_relutanh',
-             'sf_f2_tanh_crf', 'sf_f0_relu_ce', 'dec_f0_tanh_ce_kd', 'dec_f2_tanh_crf_pr']
+             'sf_f2_tanh_crf', 'sf_f0_relu_ce', 'dec_f0_tanh_ce_kd', 'dec_f2_tanh_crf_pr', 'dec_f0_tanh_ml']
     if name in order:
         return 10 + order.index(name)
-    return {'one_sum_none': 30, 'one_sum_tanh_noise': 31, 'one_max_relu': 32, 'one_sum_relutanh_ce_prio': 33}[name]
+    return {'one_sum_none': 30, 'one_sum_tanh_noise': 31, 'one_max_relu': 32, 'one_sum_relutanh_ce_prio': 33, 'one_sum_relu_ml': 34}[name]
 
 
 def build_module(name, z, meta, load_state=True):
