@@ -202,3 +202,52 @@ def test_chunked_multi_stream_inference_precomputed_factors():
         m.use_cuda_graph = False
         _, pred_e, _ = m(v, yt, lt, train=False)
     assert torch.equal(out[1], pred_e) and torch.equal(out[4], pred_e)
+
+
+def test_graph_policy_over_an_evaluation_sweep():
+    """val.py-style sweep: batch shapes change from batch to batch and the parameters change between sweeps.  A key is
+    captured only on its second sighting, captures are bounded and evicted (stale parameter versions first), in-place
+    `.data` writes are picked up after invalidate_caches(), and every result equals the eager path."""
+    import re2nn_seq_b200 as r
+    from re2nn_seq_b200 import synth
+    args = synth.make_args(farnn=0, use_crf=1, update_nonlinear='tanh', beta=0.1)
+    f = synth.make_decompose_factors(3, 300, 96, 64, 9, 16, dtype=np.float32)
+    torch.manual_seed(3)
+    m = r.FARNN_S_D_W_I_S(args=args, o_idx=0, **f)
+    with torch.no_grad():
+        m.crf.transitions.copy_(torch.from_numpy(synth.crf_transitions(3, m.C)))
+    m = m.cuda().eval()
+    rs = np.random.RandomState(0)
+    shapes = [(256, 9), (256, 12), (130, 9), (256, 9), (256, 12), (256, 9), (384, 7), (256, 12)] + \
+             [(256, int(l)) for l in rs.randint(5, 20, size=14)]
+
+    def sweep():
+        out = []
+        for i, (B, Lmax) in enumerate(shapes):
+            x, lens, lab = synth.make_batch(100 + i, B, Lmax, 300, 9)
+            xt, lt, yt = _t(x), _t(lens), _t(lab)
+            with torch.no_grad():
+                _, pred, _ = m.forward_local(xt, yt, lt, train=False)
+                m.use_cuda_graph = False
+                _, want, _ = m.forward_local(xt, yt, lt, train=False)
+                m.use_cuda_graph = True
+            assert torch.equal(pred, want), 'batch %d (B=%d, L<=%d)' % (i, B, Lmax)
+            out.append(pred.clone())
+        return out
+
+    first = sweep()
+    assert 1 <= len(m._graphs) <= m._GRAPH_MAX_ENTRIES          # repeated keys were captured, the rest ran eagerly
+    n_captured = len(m._graphs)
+    again = sweep()                                              # same parameters: captures are reused / extended, bounded
+    assert len(m._graphs) <= m._GRAPH_MAX_ENTRIES and len(m._graphs) >= n_captured
+    for a, b in zip(first, again):
+        assert torch.equal(a, b)
+    with torch.no_grad():                                        # an in-place write that does NOT bump _version ...
+        m.S1.data.mul_(1.5)
+    m.invalidate_caches()                                        # ... needs the documented call
+    assert len(m._graphs) == 0
+    changed = sweep()
+    assert any(not torch.equal(a, b) for a, b in zip(first, changed))
+    m.train()                                                    # train() / eval() invalidate on their own
+    m.eval()
+    assert len(m._graphs) == 0
