@@ -57,7 +57,7 @@ def parse():
     ap.add_argument('--resident', type=int, default=1, help='debug: 0 = one launch per step GEMM instead of the resident kernel')
     ap.add_argument('--backward-tc', type=int, default=1, help='debug: 0 = BPTT step GEMMs on fp32 CUDA cores')
     ap.add_argument('--infer-chunks', type=int, default=4, help='streams the graphed inference body forks into (1 = single stream)')
-    ap.add_argument('--cpu-sample', type=int, default=1024, help='sequences of the batch the CPU reference runs (baseline + tag check)')
+    ap.add_argument('--cpu-sample', type=int, default=4096, help='sequences of the batch the CPU reference runs (baseline + tag check)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
 
@@ -620,7 +620,7 @@ def main():
                                          ref_sample=ref_sample, ref_repeats=3, want_cpu_baseline=want_cpu)
         elif leg == 'cfg2':
             results[leg] = leg_decompose(ctx, leg, 'cfg2', a.precision, a.farnn, a.steps, a.warmup, batch=a.batch,
-                                         ref_sample=ref_sample, ref_repeats=10, want_cpu_baseline=want_cpu)
+                                         ref_sample=ref_sample, ref_repeats=15, want_cpu_baseline=want_cpu)   # ~10-15 s of CPU work
         elif leg == 'cfg2_gated':          # farnn = 2: the configuration of every published .res file
             results[leg] = leg_decompose(ctx, leg, 'cfg2', a.precision, 2, a.steps, a.warmup, ref_sample=min(ref_sample, 256),
                                          ref_repeats=1)
