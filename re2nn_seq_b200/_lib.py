@@ -97,6 +97,8 @@ SYMBOLS = {
     're2nn_debug_set_tc_timeline': (C.c_int, [vp]),
     're2nn_debug_set_tc_cta_group': (C.c_int, [C.c_int]),
     're2nn_debug_set_resident': (C.c_int, [C.c_int]),
+    're2nn_debug_set_resident_train': (C.c_int, [C.c_int]),
+    're2nn_debug_set_tn_tc': (C.c_int, [C.c_int]),
     're2nn_debug_set_tc_multicast': (C.c_int, [C.c_int]),
     're2nn_debug_set_backward_tc': (C.c_int, [C.c_int]),
     're2nn_debug_set_viterbi_seqs': (C.c_int, [C.c_int]),

@@ -199,8 +199,11 @@ struct StepParams {
   int dir_base;                                   // single-direction launches: tile direction index z means z + dir_base
   void* AB; int ldab; size_t ab_plane;            // fused label-score operand (alpha * beta), (B*L) x ldab
   const float* beta_in;                           // beta as written by the backward direction (fused scoring)
-  // Move direction z into slot 0 so the epilogue addresses plain members (registers after inlining)
-  // instead of indexing the constant bank with a run-time z for every element.
+  // Move direction z into slot 0 so the epilogue addresses plain members instead of indexing the constant bank with
+  // a run-time z for every element.
+  // bind(): run-time index into the by-value copy.  That keeps the copy in LOCAL memory (the epilogues re-load the
+  // fields they use), which the register-starved kernels want: the plain inference epilogues of the resident kernel
+  // (twelve epilogue warps, 128 registers) measured 8-10 % slower with the fields held in registers.
   __device__ __forceinline__ void bind(int zt) {
     const int z = zt + dir_base;
     dir = z;
@@ -208,6 +211,19 @@ struct StepParams {
     Hst[0] = Hst[z]; H[0] = H[z]; Z[0] = Z[z]; Rg[0] = Rg[z]; out[0] = out[z];
     Usave[0] = Usave[z]; Asave[0] = Asave[z]; HstNext[0] = HstNext[z];
     HbarSaveNext[0] = HbarSaveNext[z]; HbarSaveCur[0] = HbarSaveCur[z];
+  }
+  // bind_const(): selects between CONSTANT indices, so the copy is scalarised into registers.  For the kernels with
+  // registers to spare (eight epilogue warps: gates, training saves): their epilogues touch most fields, and with
+  // 225 KB of the SM given to shared memory there is next to no L1 left to catch local-memory loads.
+  __device__ __forceinline__ void bind_const(int zt) {
+    const bool one = (zt + dir_base) != 0;
+    dir = one ? 1 : 0;
+#define RE2NN_BIND(f) f[0] = one ? f[1] : f[0]
+    RE2NN_BIND(hinit); RE2NN_BIND(Q); RE2NN_BIND(Hbar_next); RE2NN_BIND(Hbar_cur);
+    RE2NN_BIND(Hst); RE2NN_BIND(H); RE2NN_BIND(Z); RE2NN_BIND(Rg); RE2NN_BIND(out);
+    RE2NN_BIND(Usave); RE2NN_BIND(Asave); RE2NN_BIND(HstNext);
+    RE2NN_BIND(HbarSaveNext); RE2NN_BIND(HbarSaveCur);
+#undef RE2NN_BIND
   }
 };
 
@@ -416,13 +432,14 @@ template <int PREC, int NL = -1, int FARNN = -1, bool TRAIN = false, bool FUSE =
 };
 
 // Epilogues whose prefetch() reads a COLD array (one touch per element, straight from HBM) ask the mainloop to pull
-// the lines of a tile into L2 while its MMAs are still running: l2_line(row ctx, m, n) = address of the 128-byte line
-// holding column n of row m.  Default: nothing to do.
+// the lines of a tile into L2 while its MMAs are still running.  Default: nothing to do.
 template <class Epi> struct EpiL2Prefetch { static constexpr bool kOn = false; };
+__device__ __forceinline__ void l2_prefetch(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 template <int PREC, int NL, int FARNN, bool TRAIN> struct EpiL2Prefetch<EpiH<PREC, NL, FARNN, TRAIN, true>> {
   static constexpr bool kOn = true;
-  __device__ static __forceinline__ const void* line(const EpiH<PREC, NL, FARNN, TRAIN, true>& e, const RowCtx& r, int m, int n) {
-    return e.p.beta_in + ((size_t)m * (uint32_t)e.p.L + (uint32_t)max(r.orow, 0)) * (uint32_t)e.p.S + (uint32_t)n;
+  // issue(e, row ctx, m, n): pull what prefetch() will read for the 32 columns starting at n of row m into L2
+  __device__ static __forceinline__ void issue(const EpiH<PREC, NL, FARNN, TRAIN, true>& e, const RowCtx& r, int m, int n) {
+    l2_prefetch(e.p.beta_in + ((size_t)m * (uint32_t)e.p.L + (uint32_t)max(r.orow, 0)) * (uint32_t)e.p.S + (uint32_t)n);
   }
 };
 

@@ -395,8 +395,7 @@ __device__ __forceinline__ void tc_epilogue_chunks(const Epi epi, int M, int N, 
       const int i = idx / nchunks, ch = idx - i * nchunks;
       const int n = n0 + ch * 32;
       if ((ch % PARTS) == half && i < nrows && n < N) {
-        const void* ptr = EpiL2Prefetch<Epi>::line(epi, RowCtx{ctx[i], ctx_o[i], ctx_o[i] >= 0}, mrow0 + i, n);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+        EpiL2Prefetch<Epi>::issue(epi, RowCtx{ctx[i], ctx_o[i], ctx_o[i] >= 0}, mrow0 + i, n);
       }
     }
   }
@@ -513,8 +512,7 @@ __device__ __forceinline__ void tc_epilogue_quads(const Epi epi, int M, int N, i
       const int i = idx / nchunks, ch = idx - i * nchunks;
       const int n = n0 + ch * 32;
       if ((ch % PARTS) == half && i < nrows && n < N) {
-        const void* ptr = EpiL2Prefetch<Epi>::line(epi, RowCtx{ctx[i], ctx_o[i], ctx_o[i] >= 0}, mrow0 + i, n);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+        EpiL2Prefetch<Epi>::issue(epi, RowCtx{ctx[i], ctx_o[i], ctx_o[i] >= 0}, mrow0 + i, n);
       }
     }
   }
