@@ -95,18 +95,8 @@ class ClockSampler:
         self.power = []
 
     def _loop(self):
-        import pynvml as nv
+        nv, h = self.nv, self.h
         try:
-            nv.nvmlInit()
-            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
-            idx = self.index
-            if vis:
-                try:
-                    idx = int(vis.split(',')[self.index])
-                except Exception:
-                    pass
-            h = nv.nvmlDeviceGetHandleByIndex(idx)
-            self.max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
             while not self.stop_flag:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
                 try:
@@ -125,6 +115,24 @@ class ClockSampler:
             self.err = str(e)
 
     def start(self):
+        # import / nvmlInit / handle lookup HERE, before the timed region: done inside the sampling thread they held the
+        # import lock and the GIL for 50-500 ms while the first timed steps were being launched (seen as a single
+        # outlier step in the launch-bound training leg)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(',')[self.index])
+                except Exception:
+                    pass
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception as e:   # noqa
+            self.err = str(e)
+            return self
         self.th = threading.Thread(target=self._loop, daemon=True)
         self.th.start()
         return self
@@ -257,7 +265,7 @@ class Ctx:
 
 
 def stats(ms):
-    return {'min': float(np.min(ms)), 'median': float(np.median(ms)), 'max': float(np.max(ms))}
+    return {'min': float(np.min(ms)), 'median': float(np.median(ms)), 'max': float(np.max(ms)), 'argmax': int(np.argmax(ms))}
 
 
 # ---- decompose inference leg ------------------------------------------------------------------------------------------

@@ -379,6 +379,59 @@ __global__ void bwd_e3_kernel(const BwdCtx c) {
   }
 }
 
+// farnn = 0: E3 of step k and E1 of step k-1 touch the same element and nothing runs between them (no gate GEMM), so
+// they are one launch: the carry g stays in a register, the GA / g round trip disappears.  Same arithmetic, same order.
+__global__ void bwd_e31_kernel(const BwdCtx c) {
+  const size_t total = (size_t)2 * c.B * c.S;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int s = (int)(i % c.S);
+    const size_t rr = i / c.S;
+    const int b = (int)(rr % c.B), z = (int)(rr / c.B);
+    const int n = (int)c.len[b];
+    int tpos, orow;
+    bool alive;
+    step_pos(z, c.k, n, c.full_pad, tpos, orow, alive);
+    const size_t e = (size_t)b * c.S + s;
+    const size_t gi = (size_t)z * c.B * c.S + e;
+    const float on = c.o[s];
+    // ---- E3 of step k
+    float g;
+    if (!alive) {
+      g = c.g[gi];                       // keeps whatever it had (0 until the row's last live step)
+      if (z == 1) c.DOprod[slab(c, z, c.k, c.S) + e] = 0.f;
+    } else {
+      const float dhb = c.DHb[gi];
+      g = dhb;
+      if (z == 1) {
+        g = dhb * on;
+        c.DOprod[slab(c, z, c.k, c.S) + e] = dhb * c.hst_save[slab1(c, z, c.k, c.S) + e];
+      }
+      g = 0.f + g;                       // the carry is GA + gB with GA = 0 without gates
+      if (c.k == 0) c.g[gi] = g;         // the final carry feeds dh0 / dhT
+    }
+    if (c.k == 0) continue;
+    // ---- E1 of step k-1
+    const int k1 = c.k - 1;
+    step_pos(z, k1, n, c.full_pad, tpos, orow, alive);
+    const size_t sl = slab(c, z, k1, c.S) + e;
+    if (!alive) {
+      c.DA[sl] = 0.f;
+      if (c.DAop[0]) OperandFmt<RE2NN_PREC_TF32X3>::store(c.DAop[z], (size_t)b * c.ldS + s, c.da_plane, 0.f);
+      if (z == 0) c.DOprod[sl] = 0.f;
+      continue;
+    }
+    const float* dout = z == 0 ? c.dalpha : c.dbeta;
+    const float G = g + (orow >= 0 ? dout[((size_t)b * c.L + orow) * c.S + s] : 0.f);
+    const float a = c.a_save[sl];
+    const float hhat = apply_nl(z == 0 ? a * on : a, c.nl);
+    const float dpre = G * nl_grad_from_out(hhat, c.nl);
+    const float da = z == 0 ? dpre * on : dpre;
+    c.DA[sl] = da;
+    if (z == 0) c.DOprod[sl] = dpre * a;
+    if (c.DAop[0]) OperandFmt<RE2NN_PREC_TF32X3>::store(c.DAop[z], (size_t)b * c.ldS + s, c.da_plane, da);
+  }
+}
+
 // dgtab[token] += [dz | dr] of this step (after the gate slab is complete)
 __global__ void bwd_gate_scatter_kernel(const BwdCtx c) {
   const int gw = c.S * c.farnn;
@@ -825,8 +878,10 @@ static int run_backward(const re2nn_backward_args& a, cudaStream_t st) {
   }
   for (int k = L - 1; k >= 0 && !resident; --k) {
     c.k = k;
-    bwd_e1_kernel<<<grid_for((size_t)2 * B * S), 256, 0, st>>>(c);
-    RE2NN_LAUNCH_CHECK();
+    if (k == L - 1 || a.farnn >= 1) {      // without gates E1 of the later steps rides in bwd_e31_kernel
+      bwd_e1_kernel<<<grid_for((size_t)2 * B * S), 256, 0, st>>>(c);
+      RE2NN_LAUNCH_CHECK();
+    }
     // dq = DA[k] @ S2 (fwd) | S1 (bwd)
     memset(&g, 0, sizeof(g));
     g.M = B; g.N = R; g.nseg = 1; g.ndir = 2;
@@ -849,7 +904,8 @@ static int run_backward(const re2nn_backward_args& a, cudaStream_t st) {
       RE2NN_CUDA((launch_tc_gemm<RE2NN_PREC_TF32X3>(g, EpiStore2{{c.DHb, c.DHb + (size_t)B * S}, S, 0}, th.get(), st)));
     else
       RE2NN_CUDA(launch_simt_gemm(g, EpiStore2{{c.DHb, c.DHb + (size_t)B * S}, S, 0}, ALoadPlain{}, st));
-    bwd_e3_kernel<<<grid_for((size_t)2 * B * S), 256, 0, st>>>(c);
+    if (a.farnn == 0) bwd_e31_kernel<<<grid_for((size_t)2 * B * S), 256, 0, st>>>(c);
+    else bwd_e3_kernel<<<grid_for((size_t)2 * B * S), 256, 0, st>>>(c);
     RE2NN_LAUNCH_CHECK();
     if (a.farnn >= 1) {
       // g += [dz | dr] @ [Wss1 | Wss2]^T
