@@ -77,7 +77,7 @@ struct YLoadPlain {
   __device__ __forceinline__ float operator()(const TnPair& pr, size_t m, int q) const { return __ldg(pr.Y + m * pr.ldy + q); }
 };
 struct YLoadAlphaBeta {
-  static constexpr bool kPlain = false;      // forms alpha * beta on the fly: stays on the CUDA-core kernel
+  static constexpr bool kPlain = false;      // CUDA-core kernel: forms the masked alpha * beta itself (the tcgen05 one reads Y2 / mask_len)
   const float* beta; const int64_t* len; int L, full_pad;
   __device__ __forceinline__ float operator()(const TnPair& pr, size_t m, int q) const {
     int b = (int)(m / L), t = (int)(m - (size_t)b * L);
@@ -168,7 +168,7 @@ static cudaError_t run_tn(const TnProblem& prob, float* partial, float* out, int
   for (int i = 0; i < prob.npairs; ++i) rows += prob.pair[i].rows;
 #ifdef RE2NN_HAVE_TC
   // tensor cores once the reduction is long enough to fill a pipeline per CTA (the partial buffer holds kTnSplit slices)
-  if (YLoad::kPlain && g_tn_tc && re2nn_has_tcgen05() != 0 && rows >= 4096 && prob.P >= 16 && prob.Q >= 16) {
+  if ((YLoad::kPlain || prob.Y2 != nullptr) && g_tn_tc && re2nn_has_tcgen05() != 0 && rows >= 4096 && prob.P >= 16 && prob.Q >= 16) {
     const TnTcPlan pl = tn_tc_plan(prob, kTnSplit);
     if (pl.stages >= 2) {
       if (cudaError_t e = launch_tn_tc(prob, partial, pl, st)) return e;
@@ -791,12 +791,14 @@ static int run_backward(const re2nn_backward_args& a, cudaStream_t st) {
     g.seg[0][0] = GemmSeg{draw, a.C_mat, C, S, C, 0, 0, 0};
     RE2NN_CUDA(launch_simt_gemm(g, EpiDAB{a.alpha, a.beta, a.lengths, dalpha, dbeta, L, S, a.full_pad}, ALoadPlain{}, st));
   }
-  // 2. dC = draw^T @ (alpha * beta)
+  // 2. dC = draw^T @ (alpha * beta)   (the tensor-core kernel forms the masked product itself: Y2 / mask_len)
   if (!direct && a.dC) {
     TnProblem t;
     memset(&t, 0, sizeof(t));
     t.P = C; t.Q = S; t.npairs = 1;
     t.pair[0] = TnPair{draw, a.alpha, C, S, M};
+    t.Y2 = a.beta;
+    if (!a.full_pad) { t.mask_len = a.lengths; t.mask_L = L; }
     RE2NN_CUDA(run_tn(t, partial, a.dC, 0, YLoadAlphaBeta{a.beta, a.lengths, L, a.full_pad}, st));
   }
   // 3. sweep

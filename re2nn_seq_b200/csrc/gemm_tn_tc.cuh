@@ -17,7 +17,10 @@
 namespace re2nn {
 
 struct TnPair { const float* X; const float* Y; int ldx, ldy; size_t rows; };
-struct TnProblem { int P, Q, npairs; TnPair pair[2]; };
+// Y2 (optional, tensor-core kernel only): the right operand is Y * Y2 element-wise (same layout as pair 0's Y), and
+// with mask_len row m = b * mask_L + t only counts when t < mask_len[b] -- dC = draw^T (alpha * beta) over the valid
+// positions without materialising the product (pad rows of alpha / beta are undefined, possibly NaN).
+struct TnProblem { int P, Q, npairs; TnPair pair[2]; const float* Y2; const int64_t* mask_len; int mask_L; };
 
 constexpr int kTnLoaderWarps = 8;
 // eight warps, all loaders (two per scheduler: 255 registers each -- a ninth warp for the MMAs capped everybody at 168
@@ -147,7 +150,15 @@ __global__ void __launch_bounds__(kTnThreads, 1) tn_tc_kernel(const TnProblem pr
         if (tl + 256 * j < bn * 8) yact |= 1u << j;        // warp-uniform: bn * 8 is a multiple of 128
       }
       // loads of the k-block the pointers stand on, then advance them
+      const ptrdiff_t y2off = prob.Y2 != nullptr ? prob.Y2 - pr.Y : 0;
       auto load_blk = [&](Blk& b, size_t m0) {
+        uint32_t rowmask = 0xffffffffu;                    // bit r: row m0 + r counts (every warp works it out for itself)
+        if (prob.mask_len != nullptr) {
+          const size_t m = m0 + lane;
+          const size_t bb = m / (size_t)prob.mask_L;
+          const bool ok = m < pr.rows && (int)(m - bb * prob.mask_L) < (int)__ldg(prob.mask_len + bb);
+          rowmask = __ballot_sync(0xffffffffu, ok);
+        }
         if (m0 + kTnKBlock <= r1) {                        // whole k-block (all but a pair's last one): no row checks
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -160,6 +171,13 @@ __global__ void __launch_bounds__(kTnThreads, 1) tn_tc_kernel(const TnProblem pr
             if (yact >> j & 1u) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) b.y[j][i] = __ldg(py[j] + i * ldy);
+              if (y2off != 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float w = __ldg(py[j] + y2off + i * ldy);
+                  b.y[j][i] = (rowmask >> (4 * (ys[j] & 7u) + i) & 1u) ? b.y[j][i] * w : 0.f;
+                }
+              }
             }
             py[j] += kTnKBlock * ldy;
           }
@@ -173,7 +191,11 @@ __global__ void __launch_bounds__(kTnThreads, 1) tn_tc_kernel(const TnProblem pr
           for (int j = 0; j < kYU; ++j)
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              b.y[j][i] = ((yact >> j & 1u) && 4 * (int)(ys[j] & 7u) + i < left) ? __ldg(py[j] + i * ldy) : 0.f;
+              b.y[j][i] = ((yact >> j & 1u) && 4 * (int)(ys[j] & 7u) + i < left)
+                              ? ((rowmask >> (4 * (ys[j] & 7u) + i) & 1u)
+                                     ? __ldg(py[j] + i * ldy) * (y2off != 0 ? __ldg(py[j] + y2off + i * ldy) : 1.f)
+                                     : 0.f)
+                              : 0.f;
         }
       };
       auto store_blk = [&](const Blk& b, uint8_t* sa) {
