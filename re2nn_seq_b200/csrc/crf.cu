@@ -661,7 +661,17 @@ __global__ void crf_nll_backward_exp_kernel(
         for (int j = 0; j < T; ++j) S = fmaf(tei[j], W[j], S);
         if (S > 1e-30f) {
           const float A = gs * expf(((pp[i] - logZ) + rmax[i]) + Mw);
-          for (int j = 0; j < T; ++j) dwi[j] = fmaf(A * tei[j], W[j], dwi[j]);
+          // batches of eight: all loads of a batch before its stores (element by element the compiler must assume the
+          // store to dwi[j] aliases the next loads and serialises one shared-memory round trip per tag pair)
+          int j = 0;
+          for (; j + 8 <= T; j += 8) {
+            float d[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) d[q] = fmaf(A * tei[j + q], W[j + q], dwi[j + q]);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dwi[j + q] = d[q];
+          }
+          for (; j < T; ++j) dwi[j] = fmaf(A * tei[j], W[j], dwi[j]);
           bb[i] = (rmax[i] + Mw) + logf(S);
         } else {                                 // underflow: exact log-domain evaluation of this row
           float mx = -INFINITY;
