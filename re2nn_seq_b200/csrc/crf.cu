@@ -633,6 +633,14 @@ __global__ void crf_nll_backward_exp_kernel(
     for (int i = lane; i < T; i += 32) ba[i] = tr[i * T + (T - 1)];
     __syncwarp();
     for (int t = n - 1; t >= 0; --t) {
+      // The sweep is one dependent chain per sequence and every step used to pay three or four HBM round trips in
+      // sequence (partition row, feature row, tags: nobody has touched them since the forward pass).  Pull the rows of
+      // the NEXT step into L1 now; they arrive while this step's T x T loops run.
+      if (t >= 1 && lane < 8) {
+        const int part = (lane & 3) * 32;                       // a row is T floats: up to four 128-byte lines
+        const float* row = lane < 4 ? fb + (size_t)(t - 1) * T : ps + (size_t)(t >= 2 ? t - 2 : 0) * T;
+        if (part < T) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + part));
+      }
       const float* pt = ps + (size_t)t * T;
       const int gold = (int)tg[t];
       for (int j = lane; j < T; j += 32) {
@@ -654,38 +662,99 @@ __global__ void crf_nll_backward_exp_kernel(
       Mw = warp_max(Mw);
       for (int j = lane; j < T; j += 32) W[j] = expf((__ldg(ft + j) + ba[j]) - Mw);
       __syncwarp();
-      for (int i = lane; i < T; i += 32) {      // lane owns source rows i
-        const float* tei = te + i * T;
+      // lane owns source rows lane, lane + 32, lane + 64
+      auto row_exact = [&](int i) {      // underflow: exact log-domain evaluation of this row
         float* dwi = dw + i * Tq;
-        float S = 0.f;
-        for (int j = 0; j < T; ++j) S = fmaf(tei[j], W[j], S);
-        if (S > 1e-30f) {
-          const float A = gs * expf(((pp[i] - logZ) + rmax[i]) + Mw);
-          // batches of eight: all loads of a batch before its stores (element by element the compiler must assume the
-          // store to dwi[j] aliases the next loads and serialises one shared-memory round trip per tag pair)
-          int j = 0;
-          for (; j + 8 <= T; j += 8) {
-            float d[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) d[q] = fmaf(A * tei[j + q], W[j + q], dwi[j + q]);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) dwi[j + q] = d[q];
-          }
-          for (; j < T; ++j) dwi[j] = fmaf(A * tei[j], W[j], dwi[j]);
-          bb[i] = (rmax[i] + Mw) + logf(S);
-        } else {                                 // underflow: exact log-domain evaluation of this row
-          float mx = -INFINITY;
-          for (int j = 0; j < T; ++j) mx = fmaxf(mx, (tr[i * T + j] + __ldg(ft + j)) + ba[j]);
-          float sm = 0.f;
-          const float pi = pp[i] - logZ;
-          for (int j = 0; j < T; ++j) {
-            const float e = (tr[i * T + j] + __ldg(ft + j)) + ba[j];
-            sm += expf(e - mx);
-            dwi[j] += gs * expf(pi + e);
-          }
-          bb[i] = mx + logf(sm);
+        float mx = -INFINITY;
+        for (int j = 0; j < T; ++j) mx = fmaxf(mx, (tr[i * T + j] + __ldg(ft + j)) + ba[j]);
+        float sm = 0.f;
+        const float pi = pp[i] - logZ;
+        for (int j = 0; j < T; ++j) {
+          const float e = (tr[i * T + j] + __ldg(ft + j)) + ba[j];
+          sm += expf(e - mx);
+          dwi[j] += gs * expf(pi + e);
         }
-        if (i == gprev) dwi[gold] -= gs;
+        bb[i] = mx + logf(sm);
+      };
+      if (T <= 96) {
+        // the (up to) three rows of a lane side by side: three independent FMA chains per W[j] load instead of three
+        // dependent shared-memory round trips in sequence (the sweep is one latency-bound chain per sequence).  Every
+        // row keeps its own left-to-right summation order: same bits as the row-by-row form.
+        const int i0 = lane, i1 = lane + 32, i2 = lane + 64;
+        const bool v0 = i0 < T, v1 = i1 < T, v2 = i2 < T;
+        const float* t0 = te + (v0 ? i0 : 0) * T;
+        const float* t1 = te + (v1 ? i1 : 0) * T;
+        const float* t2 = te + (v2 ? i2 : 0) * T;
+        float S0 = 0.f, S1 = 0.f, S2 = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < T; ++j) {
+          const float w = W[j];
+          S0 = fmaf(t0[j], w, S0);
+          S1 = fmaf(t1[j], w, S1);
+          S2 = fmaf(t2[j], w, S2);
+        }
+        const bool f0 = v0 && S0 > 1e-30f, f1 = v1 && S1 > 1e-30f, f2 = v2 && S2 > 1e-30f;
+        const float A0 = f0 ? gs * expf(((pp[i0] - logZ) + rmax[i0]) + Mw) : 0.f;
+        const float A1 = f1 ? gs * expf(((pp[i1] - logZ) + rmax[i1]) + Mw) : 0.f;
+        const float A2 = f2 ? gs * expf(((pp[i2] - logZ) + rmax[i2]) + Mw) : 0.f;
+        float* d0 = dw + (v0 ? i0 : 0) * Tq;
+        float* d1 = dw + (v1 ? i1 : 0) * Tq;
+        float* d2 = dw + (v2 ? i2 : 0) * Tq;
+        int j = 0;
+        for (; j + 4 <= T; j += 4) {     // all loads of a batch before its stores (stores may alias the next loads)
+          float a[4], b[4], c[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float w = W[j + q];
+            a[q] = fmaf(A0 * t0[j + q], w, d0[j + q]);
+            b[q] = fmaf(A1 * t1[j + q], w, d1[j + q]);
+            c[q] = fmaf(A2 * t2[j + q], w, d2[j + q]);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (f0) d0[j + q] = a[q];
+            if (f1) d1[j + q] = b[q];
+            if (f2) d2[j + q] = c[q];
+          }
+        }
+        for (; j < T; ++j) {
+          const float w = W[j];
+          if (f0) d0[j] = fmaf(A0 * t0[j], w, d0[j]);
+          if (f1) d1[j] = fmaf(A1 * t1[j], w, d1[j]);
+          if (f2) d2[j] = fmaf(A2 * t2[j], w, d2[j]);
+        }
+        if (f0) bb[i0] = (rmax[i0] + Mw) + logf(S0);
+        if (f1) bb[i1] = (rmax[i1] + Mw) + logf(S1);
+        if (f2) bb[i2] = (rmax[i2] + Mw) + logf(S2);
+        if (v0 && !f0) row_exact(i0);
+        if (v1 && !f1) row_exact(i1);
+        if (v2 && !f2) row_exact(i2);
+        if (v0 && i0 == gprev) d0[gold] -= gs;
+        if (v1 && i1 == gprev) d1[gold] -= gs;
+        if (v2 && i2 == gprev) d2[gold] -= gs;
+      } else {
+        for (int i = lane; i < T; i += 32) {
+          const float* tei = te + i * T;
+          float* dwi = dw + i * Tq;
+          float S = 0.f;
+          for (int j = 0; j < T; ++j) S = fmaf(tei[j], W[j], S);
+          if (S > 1e-30f) {
+            const float A = gs * expf(((pp[i] - logZ) + rmax[i]) + Mw);
+            int j = 0;
+            for (; j + 8 <= T; j += 8) {
+              float d[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) d[q] = fmaf(A * tei[j + q], W[j + q], dwi[j + q]);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) dwi[j + q] = d[q];
+            }
+            for (; j < T; ++j) dwi[j] = fmaf(A * tei[j], W[j], dwi[j]);
+            bb[i] = (rmax[i] + Mw) + logf(S);
+          } else {
+            row_exact(i);
+          }
+          if (i == gprev) dwi[gold] -= gs;
+        }
       }
       __syncwarp();
       float* tmp = ba; ba = bb; bb = tmp;
@@ -946,7 +1015,10 @@ int re2nn_crf_nll_backward(const float* feats, const float* transitions, const i
     const size_t pw = ((size_t)T * Tq + 3 * Tp) * 4;
     const size_t fixed = 2 * tr_bytes + (size_t)Tp * 4;
     if (fixed + 2 * pw <= kSmemLimit) {
-      const int nwe = (int)std::min<size_t>(kCrfWarps, (kSmemLimit - fixed) / pw);
+      // one CTA per SM either way (the per-warp accumulators fill the shared memory): take everything the SM has, so
+      // that e.g. B = 1024 at T = 74 is 147 CTAs of seven sequences = ONE wave instead of 171 CTAs of six = two
+      const size_t smem_all = 226 * 1024;
+      const int nwe = (int)std::min<size_t>(kCrfWarps, (smem_all - fixed) / pw);
       const size_t smem_e = fixed + nwe * pw;
       RE2NN_CUDA(cudaFuncSetAttribute(crf_nll_backward_exp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
       crf_nll_backward_exp_kernel<<<cdiv(B, nwe), nwe * 32, smem_e, st>>>(feats, transitions, lengths, tags, part_save,
