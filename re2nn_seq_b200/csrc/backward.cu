@@ -66,6 +66,12 @@ struct EpiDAB {
     dalpha[i] = r.orow < 0 ? 0.f : acc * pre.b;
     dbeta[i] = r.orow < 0 ? 0.f : acc * pre.a;
   }
+  // compute / store split of the tcgen05 epilogue (batches of rows: all arithmetic, then all stores)
+  static constexpr bool kRows = false;
+  __device__ __forceinline__ float compute(const Col&, float acc, const Pre&) const { return acc; }
+  __device__ __forceinline__ void store(const Col& c, const RowCtx& r, int m, int n, float v, float, const Pre& pre) const {
+    apply(c, r, m, n, v, pre);
+  }
 };
 
 // ---- transposed ("TN") GEMM: C[P x Q] = sum over pairs, rows m:  X[m, p] * Y[m, q]  ---------------------------
@@ -249,6 +255,7 @@ struct BwdCtx {
   // resident sweep: second DA operand buffer (ping-pong between steps) and the per-tile last live step
   void* DAop1[2];
   int* tile_last[2];
+  void* DrawOp; void* CmatOp;                        // tensor-core label-score backward: operand-format draw / C_mat^T
 };
 
 __device__ __forceinline__ size_t slab(const BwdCtx& c, int z, int k, int width) {
@@ -730,6 +737,10 @@ static size_t bwd_carve(const re2nn_backward_args& a, char* base, BwdCtx* c, flo
       x.DAop1[z] = take(operand_bytes(P, B, (int)S) / 4);
       x.tile_last[z] = (int*)take((B + 127) / 128);
     }
+    if (a.C > 0) {        // label-score backward on tensor cores: draw (B*L x C) and C_mat^T (S x C) in operand format
+      x.DrawOp = take(operand_bytes(P, B * L, a.C) / 4);
+      x.CmatOp = take(operand_bytes(P, S, a.C) / 4);
+    }
     for (int z = 0; z < 2 && a.farnn >= 1; ++z) {
       x.DZop[z] = take(operand_bytes(P, B, (int)S) / 4);
       if (a.farnn == 2) x.DRop[z] = take(operand_bytes(P, B, (int)S) / 4);
@@ -786,10 +797,29 @@ static int run_backward(const re2nn_backward_args& a, cudaStream_t st) {
   }
   // 1. dAB = draw @ C  ->  dAlpha, dBeta
   if (!direct) {
-    memset(&g, 0, sizeof(g));
-    g.M = (int)M; g.N = S; g.nseg = 1; g.ndir = 1;
-    g.seg[0][0] = GemmSeg{draw, a.C_mat, C, S, C, 0, 0, 0};
-    RE2NN_CUDA(launch_simt_gemm(g, EpiDAB{a.alpha, a.beta, a.lengths, dalpha, dbeta, L, S, a.full_pad}, ALoadPlain{}, st));
+    const EpiDAB edab{a.alpha, a.beta, a.lengths, dalpha, dbeta, L, S, a.full_pad};
+    if (tc && c.DrawOp != nullptr) {
+      // 3xTF32 on tcgen05: the GEMM is tiny (K = C), what matters is the coalesced epilogue over alpha / beta / dalpha / dbeta
+      constexpr int P = RE2NN_PREC_TF32X3;
+      const int ldc = operand_ld(P, C);
+      const size_t pa = M * ldc, pb = (size_t)S * ldc;
+      convert_weight_kernel<P><<<(unsigned)std::min<size_t>((M * ldc + 255) / 256, (size_t)sm_count() * 32), 256, 0, st>>>(
+          draw, (int)M, C, C, 0, c.DrawOp, ldc, pa, 0);
+      RE2NN_LAUNCH_CHECK();
+      convert_weight_kernel<P><<<(unsigned)(((size_t)S * ldc + 255) / 256), 256, 0, st>>>(a.C_mat, S, C, S, 1, c.CmatOp, ldc, pb, 0);
+      RE2NN_LAUNCH_CHECK();
+      memset(&g, 0, sizeof(g));
+      g.M = (int)M; g.N = S; g.nseg = 1; g.ndir = 1;
+      g.seg[0][0] = GemmSeg{c.DrawOp, c.CmatOp, ldc, ldc, C, 1, pa, pb};
+      std::unique_ptr<TcLaunch> tl(new TcLaunch);
+      if (int rc = tc_make_launch<P>(g, tl.get())) return rc;
+      RE2NN_CUDA((launch_tc_gemm<P>(g, edab, tl.get(), st)));
+    } else {
+      memset(&g, 0, sizeof(g));
+      g.M = (int)M; g.N = S; g.nseg = 1; g.ndir = 1;
+      g.seg[0][0] = GemmSeg{draw, a.C_mat, C, S, C, 0, 0, 0};
+      RE2NN_CUDA(launch_simt_gemm(g, edab, ALoadPlain{}, st));
+    }
   }
   // 2. dC = draw^T @ (alpha * beta)   (the tensor-core kernel forms the masked product itself: Y2 / mask_len)
   if (!direct && a.dC) {
