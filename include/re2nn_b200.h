@@ -82,6 +82,9 @@ int re2nn_debug_set_resident_train(int on);
 /* debug / calibration: 1 (default) = the weight-gradient GEMMs (X^T Y over every (step, sequence) row) run on tcgen05 in
  * 3xTF32 with the operands transposed on the fly; 0 = the CUDA-core kernel. */
 int re2nn_debug_set_tn_tc(int on);
+/* debug / calibration: 1 (default) = the CRF backward sweep gives each sequence three warps (one transition row per
+ * lane, named barriers between them) when the tag set has at most 96 entries; 0 = one warp per sequence. */
+int re2nn_debug_set_crf_backward_split(int on);
 /* debug / calibration: 1 = large bf16 step GEMMs (N a multiple of 512) run on clusters of 2 x 2 CTAs that TMA-
  * multicast their A row blocks and B column tiles (a quarter fewer operand bytes requested from L2); 0 (default) =
  * CTA pairs (cta_group::2) only -- the multicast variant measured 5-10 % slower on B200. */

@@ -99,6 +99,7 @@ SYMBOLS = {
     're2nn_debug_set_resident': (C.c_int, [C.c_int]),
     're2nn_debug_set_resident_train': (C.c_int, [C.c_int]),
     're2nn_debug_set_tn_tc': (C.c_int, [C.c_int]),
+    're2nn_debug_set_crf_backward_split': (C.c_int, [C.c_int]),
     're2nn_debug_set_tc_multicast': (C.c_int, [C.c_int]),
     're2nn_debug_set_backward_tc': (C.c_int, [C.c_int]),
     're2nn_debug_set_viterbi_seqs': (C.c_int, [C.c_int]),

@@ -770,6 +770,157 @@ __global__ void crf_nll_backward_exp_kernel(
   }
 }
 
+// The same sweep with THREE warps per sequence (T <= 96): warp `part` of a sequence owns transition rows / tag columns
+// part*32 + lane, so a lane has one row instead of three and the per-step chain is a third as long; the warps of a
+// sequence meet at a named barrier twice per step (W complete; beta_{t-1} complete).  The sweep is latency-bound --
+// one dependent chain per sequence, seven sequences per SM because of the T x T accumulators -- so the step latency is
+// the kernel time.  Same arithmetic per element and the same left-to-right row sums as crf_nll_backward_exp_kernel.
+// dynamic smem: trans T*T | table T*T | rmax Tp | per SEQUENCE: dtrans accumulator T*Tq, beta a / b, W (3 * Tp)
+__global__ void crf_nll_backward_exp3_kernel(
+    const float* __restrict__ feats, const float* __restrict__ trans_g, const int64_t* __restrict__ len,
+    const int64_t* __restrict__ tags, const float* __restrict__ part_save, const float* __restrict__ gscale, int B,
+    int L, int Ltags, int T, float* __restrict__ dfeats, float* __restrict__ dtrans) {
+  extern __shared__ float smem[];
+  const int nseq = (blockDim.x >> 5) / 3;
+  const int Tp = (T + 31) & ~31;
+  const int Tq = T | 1;
+  float* tr = smem;
+  float* te = tr + T * T;
+  float* rmax = te + T * T;
+  float* s_dtr = rmax + Tp;
+  float* s_vec = s_dtr + (size_t)nseq * T * Tq;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < T * T; i += blockDim.x) tr[i] = trans_g[i];
+  for (int i = threadIdx.x; i < nseq * T * Tq; i += blockDim.x) s_dtr[i] = 0.f;
+  __syncthreads();
+  for (int i = threadIdx.x; i < Tp; i += blockDim.x) {
+    float m = -INFINITY;
+    if (i < T)
+      for (int j = 0; j < T; ++j) m = fmaxf(m, tr[i * T + j]);
+    rmax[i] = m;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * T; i += blockDim.x) te[i] = expf(tr[i] - rmax[i / T]);
+  __syncthreads();
+  const float gs = gscale ? *gscale : 1.f;
+  const int seq = warp / 3, part = warp - seq * 3;
+  const int own = part * 32 + lane;            // the row / column this lane owns
+  const bool has = own < T;
+  const int tid96 = part * 32 + lane;          // index among the 96 threads of the sequence
+  auto seq_sync = [&]() { asm volatile("bar.sync %0, 96;" ::"r"(seq + 1) : "memory"); };
+  float* dw = s_dtr + (size_t)seq * T * Tq;
+  const int b = blockIdx.x * nseq + seq;
+  if (b < B && min((int)len[b], L) <= 0) {      // empty sequence: no marginals, zero feature gradient
+    float* df0 = dfeats + (size_t)b * L * T;
+    for (int i = tid96; i < L * T; i += 96) df0[i] = 0.f;
+  }
+  if (b < B && min((int)len[b], L) > 0) {       // uniform over the three warps of a sequence
+    const int n = min((int)len[b], L);
+    float* ba = s_vec + seq * 3 * Tp;    // beta_t
+    float* bb = ba + Tp;                 // beta_{t-1}
+    float* W = bb + Tp;
+    const float* fb = feats + (size_t)b * L * T;
+    const float* ps = part_save + (size_t)b * L * T;
+    float* df = dfeats + (size_t)b * L * T;
+    const int64_t* tg = tags + (size_t)b * Ltags;
+    const float* pl = ps + (size_t)(n - 1) * T;
+    // log Z: every warp for itself (same operations, same result)
+    float m = -INFINITY;
+    for (int i = lane; i < T; i += 32) m = fmaxf(m, tr[i * T + (T - 1)] + pl[i]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int i = lane; i < T; i += 32) s += expf((tr[i * T + (T - 1)] + pl[i]) - m);
+    s = warp_sum(s);
+    const float logZ = m + logf(s);
+    if (has) ba[own] = tr[own * T + (T - 1)];
+    seq_sync();
+    const float* tei = te + (has ? own : 0) * T;
+    float* dwi = dw + (has ? own : 0) * Tq;
+    for (int t = n - 1; t >= 0; --t) {
+      // rows of the NEXT step into L1 while this step's loops run (see crf_nll_backward_exp_kernel)
+      if (t >= 1 && part == 0 && lane < 8) {
+        const int seg = (lane & 3) * 32;
+        const float* row = lane < 4 ? fb + (size_t)(t - 1) * T : ps + (size_t)(t >= 2 ? t - 2 : 0) * T;
+        if (seg < T) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + seg));
+      }
+      // every global value of the step is requested here, ahead of the barriers (the compiler cannot move a load
+      // above a bar.sync): partition rows t and t-1, feature row t, the two tags
+      const float* pt = ps + (size_t)t * T;
+      const float* pp = ps + (size_t)(t >= 1 ? t - 1 : 0) * T;
+      const float* ft = fb + (size_t)t * T;
+      const int oc = has ? own : 0;
+      const float ptv = pt[oc], ppv = pp[oc], ftv = __ldg(ft + oc);
+      float ftm[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) ftm[q] = lane + 32 * q < T ? __ldg(ft + lane + 32 * q) : 0.f;
+      const int gold = (int)tg[t];
+      const int gprev = (int)tg[t >= 1 ? t - 1 : 0];
+      float d = 0.f;
+      if (has) {
+        d = gs * (expf(ptv + ba[own] - logZ) - (own == gold ? 1.f : 0.f));
+        df[(size_t)t * T + own] = d;
+        if (t == n - 1) dwi[T - 1] += d;
+      }
+      if (t == 0) {
+        // row T-2 belongs to one warp of the sequence, but its sweep over that row ended at the barrier that closed
+        // the previous step; every lane adds to its own column.  A one-token sequence (t == n-1 == 0) has just added
+        // to column T-1 of every row, row T-2 included: order the two updates of that element.
+        if (n == 1) seq_sync();
+        if (has) dw[(T - 2) * Tq + own] += d;
+        break;
+      }
+      // W_j = exp(feat_t[j] + beta_t[j] - Mw): the maximum by every warp for itself, W by column owners
+      float Mw = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        if (lane + 32 * q < T) Mw = fmaxf(Mw, ftm[q] + ba[lane + 32 * q]);
+      Mw = warp_max(Mw);
+      if (has) W[own] = expf((ftv + ba[own]) - Mw);
+      seq_sync();
+      if (has) {
+        float S = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < T; ++j) S = fmaf(tei[j], W[j], S);
+        if (S > 1e-30f) {
+          const float A = gs * expf(((ppv - logZ) + rmax[own]) + Mw);
+          int j = 0;
+          for (; j + 8 <= T; j += 8) {     // all loads of a batch before its stores
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = fmaf(A * tei[j + q], W[j + q], dwi[j + q]);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dwi[j + q] = v[q];
+          }
+          for (; j < T; ++j) dwi[j] = fmaf(A * tei[j], W[j], dwi[j]);
+          bb[own] = (rmax[own] + Mw) + logf(S);
+        } else {                           // underflow: exact log-domain evaluation of this row
+          float mx = -INFINITY;
+          for (int j = 0; j < T; ++j) mx = fmaxf(mx, (tr[own * T + j] + __ldg(ft + j)) + ba[j]);
+          float sm = 0.f;
+          const float pi = ppv - logZ;
+          for (int j = 0; j < T; ++j) {
+            const float e = (tr[own * T + j] + __ldg(ft + j)) + ba[j];
+            sm += expf(e - mx);
+            dwi[j] += gs * expf(pi + e);
+          }
+          bb[own] = mx + logf(sm);
+        }
+        if (own == gprev) dwi[gold] -= gs;
+      }
+      seq_sync();                          // beta_{t-1} complete, nobody reads beta_t / W any more
+      float* tmp = ba; ba = bb; bb = tmp;
+    }
+    for (int i = n * T + tid96; i < L * T; i += 96) df[i] = 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
+    const int r = i / T, c = i - r * T;
+    float v = 0.f;
+    for (int w = 0; w < nseq; ++w) v += s_dtr[(size_t)w * T * Tq + r * Tq + c];
+    if (v != 0.f) atomicAdd(dtrans + i, v);
+  }
+}
+
 // deterministic sum of n floats (double accumulation), scaled
 __global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restrict__ v, size_t n, double scale,
                                                           float* __restrict__ out) {
@@ -881,6 +1032,7 @@ __global__ void flatten_i64_kernel(const int64_t* __restrict__ padded, const int
 }
 
 static const size_t kSmemLimit = 200 * 1024;
+static bool g_crf_bwd_split = true;      // CRF backward: three warps per sequence when T <= 96 (re2nn_debug_set_crf_backward_split)
 
 }  // namespace re2nn
 
@@ -954,6 +1106,11 @@ int re2nn_crf_viterbi(const float* feats, const float* transitions, const int64_
   return 0;
 }
 
+int re2nn_debug_set_crf_backward_split(int on) {
+  g_crf_bwd_split = on != 0;
+  return 0;
+}
+
 int re2nn_debug_set_viterbi_seqs(int ns) {
   RE2NN_CHECK(ns == 0 || ns == 1 || ns == 2 || ns == 4, "debug_set_viterbi_seqs: expected 0, 1, 2 or 4");
   g_viterbi_ns = ns;
@@ -1019,6 +1176,14 @@ int re2nn_crf_nll_backward(const float* feats, const float* transitions, const i
       // that e.g. B = 1024 at T = 74 is 147 CTAs of seven sequences = ONE wave instead of 171 CTAs of six = two
       const size_t smem_all = 226 * 1024;
       const int nwe = (int)std::min<size_t>(kCrfWarps, (smem_all - fixed) / pw);
+      if (T <= 96 && g_crf_bwd_split) {      // three warps per sequence: a third of the per-step latency
+        const size_t smem_3 = fixed + nwe * pw;
+        RE2NN_CUDA(cudaFuncSetAttribute(crf_nll_backward_exp3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_3));
+        crf_nll_backward_exp3_kernel<<<cdiv(B, nwe), nwe * 96, smem_3, st>>>(feats, transitions, lengths, tags, part_save,
+                                                                             gscale, B, L, Ltags, T, dfeats, dtrans);
+        RE2NN_LAUNCH_CHECK();
+        return 0;
+      }
       const size_t smem_e = fixed + nwe * pw;
       RE2NN_CUDA(cudaFuncSetAttribute(crf_nll_backward_exp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
       crf_nll_backward_exp_kernel<<<cdiv(B, nwe), nwe * 32, smem_e, st>>>(feats, transitions, lengths, tags, part_save,

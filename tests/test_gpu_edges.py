@@ -133,3 +133,40 @@ def test_crf_empty_and_overlong_lengths():
     la, ga, _ = run(feats, tags, lens_big)
     lb, gb, _ = run(feats, tags, lens_clamped)
     assert la == lb and np.array_equal(ga, gb)
+
+
+@pytest.mark.parametrize('ntag', [3, 30, 72, 94])
+def test_crf_backward_three_warps_per_sequence_matches_one(ntag):
+    """CRF backward with three warps per sequence (T <= 96: one transition row per lane, named barriers) against the
+    one-warp-per-sequence sweep: same feature gradients bit for bit, transition gradients up to the order of the final
+    atomic adds; ragged lengths incl. one-token and empty sequences, hard-constrained (-1e4) transitions."""
+    import re2nn_seq_b200 as r
+    from re2nn_seq_b200 import _lib
+    rs = np.random.RandomState(ntag)
+    B, L, T = 61, 11, ntag + 2
+    feats = (rs.randn(B, L, T) * 3.0).astype(np.float32)
+    lens = rs.randint(0, L + 1, size=B).astype(np.int64)
+    lens[:4] = [L, 1, 0, 2]
+    tags = rs.randint(0, ntag, size=(B, L)).astype(np.int64)
+    trans = rs.randn(T, T).astype(np.float32)
+    trans[rs.rand(T, T) < 0.2] = -10000.0
+    trans[:, T - 2] = -10000.0
+    trans[T - 1, :] = -10000.0
+    mask = (np.arange(L)[None, :] < lens[:, None])
+    out = {}
+    try:
+        for split in (1, 0):
+            _lib.check(_lib.fn['re2nn_debug_set_crf_backward_split'](split), 'crf split')
+            crf = r.CRF(ntag, True).cuda()
+            with torch.no_grad():
+                crf.transitions.copy_(torch.from_numpy(trans).cuda())
+            f = torch.from_numpy(feats).cuda().requires_grad_(True)
+            loss = crf.neg_log_likelihood_loss(f, torch.from_numpy(mask).cuda(), torch.from_numpy(tags).cuda())
+            loss.backward()
+            out[split] = (loss.item(), f.grad.clone(), crf.transitions.grad.clone())
+    finally:
+        _lib.check(_lib.fn['re2nn_debug_set_crf_backward_split'](1), 'crf split')
+    assert out[1][0] == out[0][0]
+    assert torch.equal(out[1][1], out[0][1])
+    scale = out[0][2].abs().max().item() + 1e-30
+    assert (out[1][2] - out[0][2]).abs().max().item() / scale < 2e-6
