@@ -1,4 +1,7 @@
-// Resident decompose recurrence (inference, farnn = 0 / 1 / 2): ONE launch runs every step of both directions.
+// Resident decompose recurrence (farnn = 0 / 1 / 2): ONE launch runs every step of both directions.  Inference is the
+// default user; the same kernel takes the training forward (save slabs) and the BPTT sweep as epilogue policies
+// (ResidentForward<.., TRAIN>, backward.cu: ResidentBackward) -- measured slower than per-step launches at B = 1024 and
+// therefore off by default (re2nn_debug_set_resident_train).
 //
 // The per-step launches of recurrence.cu are bound by what happens BETWEEN the GEMMs, not by the GEMMs: every
 // step boundary is a grid-wide dependency (drain the epilogue stores, resolve the launch, refill the operand
