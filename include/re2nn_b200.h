@@ -319,6 +319,15 @@ int re2nn_argmax_decode(const float* scores, const int64_t* lengths, const int64
                         int B, int L, int C, int clamp_col, float threshold, int64_t o_idx,
                         int64_t* flat_pred, int64_t* padded_pred, void* stream);
 
+/* Longest-first schedule of a batch in one launch (no reference counterpart: the reference computes every pad position
+ * of model_decompose_single.py:236-249 and needs no order; here 128-row tiles stop at their own last step, so tiles of
+ * similar length finish together).  order = the permutation torch.sort(lengths, descending=True, stable=True) returns,
+ * offsets = exclusive prefix sums of the lengths in the caller's order (start of each sequence in the flattened
+ * valid-only layout of utils.py:153-164), lengths_sorted / offsets_sorted = both gathered through `order`; all int64[B].
+ * Single CTA: re2nn_length_order_supported(B, L) tells whether the call is in range (B <= 16384, lengths <= L < 256). */
+int re2nn_length_order_supported(int B, int L);
+int re2nn_length_order(const int64_t* lengths, int B, int L, int64_t* order, int64_t* lengths_sorted, int64_t* offsets,
+                       int64_t* offsets_sorted, void* stream);
 /* flat[offsets[b] + t] = padded[b, t] for t < lengths[b]: utils.py:153-164 `flatten` for int64 labels, without
  * the Python loop over the batch (padded rows have stride Lrow, the first L columns are considered). */
 int re2nn_flatten_i64(const int64_t* padded, const int64_t* lengths, const int64_t* offsets, int B, int Lrow,

@@ -137,6 +137,8 @@ SYMBOLS = {
     're2nn_label_scores': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, sz,
                                      vp]),
     're2nn_argmax_decode': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, i64, vp, vp, vp]),
+    're2nn_length_order_supported': (C.c_int, [C.c_int, C.c_int]),
+    're2nn_length_order': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     're2nn_flatten_i64': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
     're2nn_crf_viterbi': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, i64, vp, vp, vp, vp]),
     're2nn_crf_nll': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),

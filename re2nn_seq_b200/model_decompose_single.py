@@ -158,16 +158,23 @@ class _DecomposeBase(nn.Module):
         return flat
 
     # ---- loss + decode tail shared by forward_local / forward (model_decompose_single.py:271-304) ---
-    def _length_order(self, lengths, re_tags):
+    def _length_order(self, lengths, re_tags, L=None):
         """Process sequences longest-first so 128-row tiles finish together and are skipped once all their rows
         are done (the reference computes every pad position; only valid positions are observable).  Outputs keep
-        the caller's order: flat predictions are scattered through the original offsets."""
+        the caller's order: flat predictions are scattered through the original offsets.
+        -> (order, offsets_sorted, lengths_sorted, offsets) or (None, None, None, None)."""
         if not getattr(self, 'sort_by_length', True) or re_tags is not None or lengths.shape[0] <= 128:
-            return None, None
+            return None, None, None, None
+        if L is not None and lengths.is_cuda:
+            fast = ops.length_order(lengths, L)          # one launch: counting sort + offsets + gathers
+            if fast is not None:
+                order, ls, offs, offs_sorted = fast
+                return order, offs_sorted, ls, offs
         # 16-bit keys: the radix sort needs 2 passes instead of 8.  The order is only a scheduling heuristic (any
         # permutation gives the same outputs), so lengths beyond int16 merely sort less usefully.
         _, order = torch.sort(lengths.to(torch.int16), descending=True, stable=True)
-        return order, exclusive_offsets(lengths).index_select(0, order)
+        offs = exclusive_offsets(lengths)
+        return order, offs.index_select(0, order), lengths.index_select(0, order), offs
 
     # ---- CUDA-graph replay of the inference path --------------------------------------------------------
     # One forward_local is ~80-110 small dependent launches; on the host that is 10+ us per launch, more than
@@ -182,11 +189,12 @@ class _DecomposeBase(nn.Module):
         """Sync-free inference body: every shape is a function of (B, Lpad, L) only."""
         B = lengths.shape[0]
         nmax = B * L
-        offs0 = exclusive_offsets(lengths)
+        order, offsets, ls, offs0 = self._length_order(lengths, None, L)
+        if order is None:
+            offs0 = exclusive_offsets(lengths)
         true = ops.flatten_i64(label.contiguous(), lengths, offs0, L, nmax)
-        order, offsets = self._length_order(lengths, None)
         if order is not None:
-            lengths = lengths.index_select(0, order)
+            lengths = ls
             inp = inp.index_select(0, order)
         else:
             offsets = offs0
@@ -461,11 +469,10 @@ class FARNN_S_D_W_I_S(_DecomposeBase):
         shape = self._host_shape(lengths)
         if self._can_graph(train, re_tags):
             return self._infer_graphed(input.to(dev).contiguous(), label.to(dev), lengths, shape, 'tok')
-        order, offsets = self._length_order(lengths, re_tags)
+        order, offsets, ls, _ = self._length_order(lengths, re_tags, shape[0])
         if order is None:
             all_scores = self.forward_scores(input, lengths, shape)
             return self._finish(all_scores, label, lengths, train, re_tags, shape)
-        ls = lengths.index_select(0, order)
         all_scores = self.forward_scores(input.to(dev).index_select(0, order), ls, shape)
         return self._finish(all_scores, label, ls, train, re_tags, shape, order, offsets, lengths)
 
@@ -538,10 +545,9 @@ class FARNN_S_SF(_DecomposeBase):
         shape = self._host_shape(lengths)
         if self._can_graph(train, re_tags):
             return self._infer_graphed(input.to(dev).float().contiguous(), label.to(dev), lengths, shape, 'sf')
-        order, offsets = self._length_order(lengths, re_tags)
+        order, offsets, ls, _ = self._length_order(lengths, re_tags, shape[0])
         if order is None:
             all_scores = self.forward_scores(input, lengths, shape)
             return self._finish(all_scores, label, lengths, train, re_tags, shape)
-        ls = lengths.index_select(0, order)
         all_scores = self.forward_scores(input.to(dev).index_select(0, order), ls, shape)
         return self._finish(all_scores, label, ls, train, re_tags, shape, order, offsets, lengths)

@@ -482,6 +482,19 @@ def onehot_backward(x, lengths, L, language, W, o, h0, hT, alpha, beta, dscores,
     return dlang
 
 
+def length_order(lengths, L):
+    """Longest-first schedule in one launch -> (order, lengths_sorted, offsets, offsets_sorted) (all int64[B]), or None
+    when the batch is outside the single-CTA kernel's range (the caller then uses torch.sort / cumsum / gathers)."""
+    B = lengths.shape[0]
+    if not fn['re2nn_length_order_supported'](B, int(L)):
+        return None
+    out = torch.empty((4, B), dtype=torch.int64, device=lengths.device)
+    check(fn['re2nn_length_order'](_i64(lengths), B, int(L), _i64(out[0]), _i64(out[1]), _i64(out[2]), _i64(out[3]),
+                                   _stream()), 'length_order')
+    _count(1)
+    return out[0], out[1], out[2], out[3]
+
+
 def flatten_i64(padded, lengths, offsets, L, n_flat):
     """Valid prefixes of an int64 B x Lrow tensor, batch-major (no host sync)."""
     B, Lrow = padded.shape

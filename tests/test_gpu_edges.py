@@ -170,3 +170,28 @@ def test_crf_backward_three_warps_per_sequence_matches_one(ntag):
     assert torch.equal(out[1][1], out[0][1])
     scale = out[0][2].abs().max().item() + 1e-30
     assert (out[1][2] - out[0][2]).abs().max().item() / scale < 2e-6
+
+
+@pytest.mark.parametrize('B,L', [(129, 7), (1024, 35), (4096, 35), (5000, 128), (16384, 255), (300, 0)])
+def test_length_order_kernel_matches_torch_sort(B, L):
+    """One-launch longest-first schedule (counting sort + offsets + gathers) == torch.sort(stable, descending) +
+    cumsum + index_select, incl. ties everywhere, empty sequences, batches that are no multiple of the 1024-row tile."""
+    from re2nn_seq_b200 import ops
+    rs = np.random.RandomState(B + L)
+    lens = torch.from_numpy(rs.randint(0, L + 1, size=B).astype(np.int64)).cuda()
+    got = ops.length_order(lens, L)
+    assert got is not None
+    order, ls, offs, offs_sorted = got
+    _, want_order = torch.sort(lens.to(torch.int16), descending=True, stable=True)
+    want_offs = torch.cumsum(lens, 0) - lens
+    assert torch.equal(order, want_order)
+    assert torch.equal(offs, want_offs)
+    assert torch.equal(ls, lens.index_select(0, want_order))
+    assert torch.equal(offs_sorted, want_offs.index_select(0, want_order))
+
+
+def test_length_order_kernel_range():
+    from re2nn_seq_b200 import ops
+    lens = torch.ones(20000, dtype=torch.int64, device='cuda')
+    assert ops.length_order(lens, 5) is None                      # beyond the single-CTA batch limit: torch path
+    assert ops.length_order(lens[:100], 300) is None              # more length bins than the kernel keeps
