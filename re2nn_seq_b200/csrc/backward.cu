@@ -312,7 +312,14 @@ __global__ void bwd_e1_kernel(const BwdCtx c) {
   }
 }
 
+// bwd_e2 / bwd_e31 sit between two tcgen05 step GEMMs 35 times per sweep: they are launched with programmatic stream
+// serialization like the GEMMs, let the next GEMM begin its prologue (barrier init, TMEM allocation, descriptor
+// prefetch) right away and wait for the previous GEMM's results themselves.
 __global__ void bwd_e2_kernel(const BwdCtx c) {
+#ifdef RE2NN_HAVE_TC
+  griddep_launch_dependents();
+  griddep_wait();
+#endif
   const size_t total = (size_t)2 * c.B * c.R;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(i % c.R);
@@ -389,6 +396,10 @@ __global__ void bwd_e3_kernel(const BwdCtx c) {
 // farnn = 0: E3 of step k and E1 of step k-1 touch the same element and nothing runs between them (no gate GEMM), so
 // they are one launch: the carry g stays in a register, the GA / g round trip disappears.  Same arithmetic, same order.
 __global__ void bwd_e31_kernel(const BwdCtx c) {
+#ifdef RE2NN_HAVE_TC
+  griddep_launch_dependents();
+  griddep_wait();
+#endif
   const size_t total = (size_t)2 * c.B * c.S;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int s = (int)(i % c.S);
@@ -761,6 +772,21 @@ static size_t bwd_carve(const re2nn_backward_args& a, char* base, BwdCtx* c, flo
   return off;
 }
 
+// launch with programmatic stream serialization (the kernel calls griddepcontrol itself)
+static cudaError_t launch_pdl(void (*kernel)(BwdCtx), int grid, cudaStream_t st, const BwdCtx& c) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, c);
+}
+
 static int grid_for(size_t total) { return (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 16); }
 
 static int run_backward(const re2nn_backward_args& a, cudaStream_t st) {
@@ -923,8 +949,7 @@ static int run_backward(const re2nn_backward_args& a, cudaStream_t st) {
       RE2NN_CUDA((launch_tc_gemm<RE2NN_PREC_TF32X3>(g, EpiStore2{{c.DQ, c.DQ + (size_t)B * R}, R, 0}, tq.get(), st)));
     else
       RE2NN_CUDA(launch_simt_gemm(g, EpiStore2{{c.DQ, c.DQ + (size_t)B * R}, R, 0}, ALoadPlain{}, st));
-    bwd_e2_kernel<<<grid_for((size_t)2 * B * R), 256, 0, st>>>(c);
-    RE2NN_LAUNCH_CHECK();
+    RE2NN_CUDA(launch_pdl(bwd_e2_kernel, grid_for((size_t)2 * B * R), st, c));
     // dhb = DU[k] @ S1^T + DA[k] @ W^T (fwd) | DU[k] @ S2^T + DA[k] @ W (bwd)
     memset(&g, 0, sizeof(g));
     g.M = B; g.N = S; g.nseg = 2; g.ndir = 2;
@@ -936,9 +961,11 @@ static int run_backward(const re2nn_backward_args& a, cudaStream_t st) {
       RE2NN_CUDA((launch_tc_gemm<RE2NN_PREC_TF32X3>(g, EpiStore2{{c.DHb, c.DHb + (size_t)B * S}, S, 0}, th.get(), st)));
     else
       RE2NN_CUDA(launch_simt_gemm(g, EpiStore2{{c.DHb, c.DHb + (size_t)B * S}, S, 0}, ALoadPlain{}, st));
-    if (a.farnn == 0) bwd_e31_kernel<<<grid_for((size_t)2 * B * S), 256, 0, st>>>(c);
-    else bwd_e3_kernel<<<grid_for((size_t)2 * B * S), 256, 0, st>>>(c);
-    RE2NN_LAUNCH_CHECK();
+    if (a.farnn == 0) RE2NN_CUDA(launch_pdl(bwd_e31_kernel, grid_for((size_t)2 * B * S), st, c));
+    else {
+      bwd_e3_kernel<<<grid_for((size_t)2 * B * S), 256, 0, st>>>(c);
+      RE2NN_LAUNCH_CHECK();
+    }
     if (a.farnn >= 1) {
       // g += [dz | dr] @ [Wss1 | Wss2]^T
       memset(&g, 0, sizeof(g));
