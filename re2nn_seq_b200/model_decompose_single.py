@@ -343,6 +343,19 @@ class _DecomposeBase(nn.Module):
             flattened_true_labels = ops.flatten_i64(label.contiguous(), orig, exclusive_offsets(orig), L, N)
             label = label.index_select(0, order)
         loss = None
+        # Training: the decoder (Viterbi: one latency-bound chain per sequence, a few warps per SM) and the loss (the CRF
+        # partition sweep: the same shape of work) are independent readers of the scores -> the decoder runs on a side
+        # stream next to the loss and is joined before returning (cfg3: 0.13 ms of the step).
+        pred = None
+        side = None
+        if train and all_scores.is_cuda and self.use_crf and getattr(self, 'overlap_decode', True):
+            main = torch.cuda.current_stream()
+            side = getattr(self, '_decode_stream', None)
+            if side is None or side.device != all_scores.device:
+                side = self._decode_stream = torch.cuda.Stream(device=all_scores.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                pred = self.decode(all_scores.detach(), None, None, lengths, _shape=shape, _offsets=offsets)
         if train:
             lab = label.contiguous()
             if self.use_crf:
@@ -366,7 +379,11 @@ class _DecomposeBase(nn.Module):
                     kl = PR_loss(all_scores, re_tags[:, :L, :], self.args)
                     pi = max(self.args.c2_kdpr, self.args.c3_pr ** self.t)
                     loss = pi * loss + (1 - pi) * kl
-        pred = self.decode(all_scores, None, None, lengths, _shape=shape, _offsets=offsets)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+            pred.record_stream(torch.cuda.current_stream())
+        else:
+            pred = self.decode(all_scores, None, None, lengths, _shape=shape, _offsets=offsets)
         return loss, pred, flattened_true_labels
 
     def _recurrence_consts(self):

@@ -195,3 +195,23 @@ def test_length_order_kernel_range():
     lens = torch.ones(20000, dtype=torch.int64, device='cuda')
     assert ops.length_order(lens, 5) is None                      # beyond the single-CTA batch limit: torch path
     assert ops.length_order(lens[:100], 300) is None              # more length bins than the kernel keeps
+
+
+def test_training_decode_on_side_stream_is_the_same_decode():
+    """forward_local(train=True) decodes on a side stream next to the CRF loss: same loss, predictions and gradients as
+    the single-stream order."""
+    from test_gpu_parity import _random_decompose
+    m, args, x, lens, lab = _random_decompose(41, 300, 64, 40, 12, 30, 200, 9, farnn=0, use_crf=1, update_nonlinear='tanh',
+                                              beta=0.1)
+    xt, lt, yt = (torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (x, lens, lab))
+    out = {}
+    for on in (True, False):
+        m.overlap_decode = on
+        m.zero_grad(set_to_none=True)
+        loss, pred, true = m.forward_local(xt, yt, lt, train=True)
+        loss.backward()
+        torch.cuda.synchronize()
+        out[on] = (loss.item(), pred.clone(), true.clone(), m.S1.grad.clone())
+    assert out[True][0] == out[False][0]
+    for i in (1, 2, 3):
+        assert torch.equal(out[True][i], out[False][i])
