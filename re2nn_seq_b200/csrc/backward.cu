@@ -10,9 +10,13 @@
 //   GEMM dhb = DU[k] @ S1^T|S2^T + DA[k] @ W^T|W
 //   E3   reset-gate grads ; g <- carry + dh~ ; o / h_init products                      (elementwise)
 //   GEMM g  += [dz|dr] @ [Wss1|Wss2]^T                                                  (farnn >= 1)
+// Without gates E3 of step k and E1 of step k-1 are one launch (bwd_e31_kernel), the step GEMMs run on tcgen05 in
+// 3xTF32, and the elementwise kernels between them are launched with programmatic stream serialization like the GEMMs.
 // After the sweep every weight gradient is ONE large transposed GEMM over all (step, sequence) rows
-// (K = 2*L*B), reduced deterministically (split-K partials + ordered sum); bias / vector gradients are
-// deterministic column sums of the per-step slabs.
+// (K = 2*L*B) -- on tcgen05 with the operands transposed on the fly (gemm_tn_tc.cuh), CUDA cores for short reductions --
+// reduced deterministically (split-K partials + ordered sum); bias / vector gradients are deterministic column sums
+// of the per-step slabs.  The whole sweep also exists as ONE resident launch (ResidentBackward below): parity-
+// identical, slower at the benchmarked batch, off by default.
 #include <algorithm>
 #include <memory>
 
