@@ -509,12 +509,12 @@ def leg_train(ctx, cfg, farnn, steps, warmup):
                                   '(V=%d,C=%d,S=%d,R=%d,len<=%d,B=%d per GPU)' % (cfg, c['V'], c['C'], S, R, c['Lmax'], c['B']),
                       'forward_precision': prec, 'tokens_per_step_per_gpu': n_tok, 'grad_bucket_bytes': bucket.total * 4,
                       'collective': 'all-reduce(SUM) of one flat fp32 gradient bucket inside the timed step' if ctx.world > 1 else
-                                    'none at N=1 (bucket pack/unpack still runs)',
+                                    'none at N=1 (the gradients are written into the flat bucket all the same)',
                       'whole_step_tflops': value / ctx.world * fl / 1e12,
                       'whole_step_frac_of_peak': value / ctx.world * fl / 1e12 / peak_tf},
            'e2e': {'value': all_tok / (total2 / steps / 1e3), 'unit': UNIT,
                    'h2d_bytes_per_step': int(xh.numel() * 8 + lh.numel() * 8 + yh.numel() * 8), 'd2h_bytes_per_step': 4},
-           'gpu_launches_per_step': int(launches_total // steps), 'clocks': clocks}
+           'gpu_launches': int(launches_total), 'gpu_launches_per_step': int(launches_total // steps), 'clocks': clocks}
     del m, bucket
     torch.cuda.empty_cache()
     return out
@@ -586,7 +586,7 @@ def leg_onehot(ctx, name, V, S, C, B, Lmax, fixed, steps, warmup, note):
                         'peak_source': 'MEASURED_PEAKS.json hbm_gbs, of measured' if ctx.peaks else 'fallback 6.65 TB/s, of fallback'},
            'e2e': {'value': all_tok / (total2 / steps / 1e3), 'unit': UNIT,
                    'h2d_bytes_per_step': int(xh.numel() * 8 + lh.numel() * 8 + yh.numel() * 8), 'd2h_bytes_per_step': int(n_tok * 8)},
-           'gpu_launches_per_step': int(launches_total // steps), 'clocks': clocks}
+           'gpu_launches': int(launches_total), 'gpu_launches_per_step': int(launches_total // steps), 'clocks': clocks}
     del m
     torch.cuda.empty_cache()
     return out

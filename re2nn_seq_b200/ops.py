@@ -429,7 +429,10 @@ def decompose_backward(consts, p, x, dense_v, lengths, L, vtab, o, alpha, beta, 
     ws = torch.empty((need,), dtype=torch.uint8, device=dev)
     a.ws, a.ws_bytes = C.c_void_p(ws.data_ptr()), need
     check(fn['re2nn_decompose_backward'](C.byref(a), _stream()), 'decompose_backward')
-    _count(4 + L * (5 + (2 if farnn else 0)) + 12)
+    # launches of the default path: without gates E1 once + (GEMM, E2, GEMM, E3+E1) per step; with gates
+    # (E1, GEMM, E2, GEMM, E3, gate GEMM, scatter) per step; around the sweep: weight copies 6, label-score backward 3,
+    # four to eight weight-gradient GEMMs + their ordered reductions, column sums
+    _count((L * 4 + 1 if farnn == 0 else L * 7) + 22 + (12 if farnn else 0))
     return out
 
 
