@@ -783,10 +783,10 @@ __global__ void crf_nll_backward_exp3_kernel(
   extern __shared__ float smem[];
   const int nseq = (blockDim.x >> 5) / 3;
   const int Tp = (T + 31) & ~31;
-  const int Tq = T | 1;
-  float* tr = smem;
-  float* te = tr + T * T;
-  float* rmax = te + T * T;
+  const int Tq = (T + 3) & ~3;         // row pitch of the table and of the accumulators: 16-byte rows, LDS.128 / STS.128
+  float* tr = smem;                    // (a quarter-warp of consecutive rows at pitch 76 hits 32 distinct banks)
+  float* te = tr + ((T * T + 3) & ~3);
+  float* rmax = te + T * Tq;
   float* s_dtr = rmax + Tp;
   float* s_vec = s_dtr + (size_t)nseq * T * Tq;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -800,7 +800,11 @@ __global__ void crf_nll_backward_exp3_kernel(
     rmax[i] = m;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < T * T; i += blockDim.x) te[i] = expf(tr[i] - rmax[i / T]);
+  for (int i = threadIdx.x; i < T * Tq; i += blockDim.x) {
+    const int r = i / Tq, c = i - r * Tq;
+    te[i] = c < T ? expf(tr[r * T + c] - rmax[r]) : 0.f;      // pad columns contribute exact zeros
+  }
+  for (int i = threadIdx.x; i < nseq * 3 * Tp; i += blockDim.x) s_vec[i] = 0.f;   // W pad entries stay 0
   __syncthreads();
   const float gs = gscale ? *gscale : 1.f;
   const int seq = warp / 3, part = warp - seq * 3;
@@ -834,7 +838,7 @@ __global__ void crf_nll_backward_exp3_kernel(
     const float logZ = m + logf(s);
     if (has) ba[own] = tr[own * T + (T - 1)];
     seq_sync();
-    const float* tei = te + (has ? own : 0) * T;
+    const float4* tei4 = reinterpret_cast<const float4*>(te + (has ? own : 0) * Tq);
     float* dwi = dw + (has ? own : 0) * Tq;
     for (int t = n - 1; t >= 0; --t) {
       // rows of the NEXT step into L1 while this step's loops run (see crf_nll_backward_exp_kernel)
@@ -878,20 +882,40 @@ __global__ void crf_nll_backward_exp3_kernel(
       if (has) W[own] = expf((ftv + ba[own]) - Mw);
       seq_sync();
       if (has) {
+        // four tag pairs per shared-memory instruction (the sweep issues ~2.5 loads per FMA otherwise); the row sum keeps
+        // its left-to-right order, the pad columns add exact zeros
+        const float4* W4 = reinterpret_cast<const float4*>(W);
+        float4* dwi4 = reinterpret_cast<float4*>(dwi);
+        const int n4 = Tq >> 2;
         float S = 0.f;
 #pragma unroll 4
-        for (int j = 0; j < T; ++j) S = fmaf(tei[j], W[j], S);
+        for (int j = 0; j < n4; ++j) {
+          const float4 t = tei4[j], w = W4[j];
+          S = fmaf(t.x, w.x, S);
+          S = fmaf(t.y, w.y, S);
+          S = fmaf(t.z, w.z, S);
+          S = fmaf(t.w, w.w, S);
+        }
         if (S > 1e-30f) {
           const float A = gs * expf(((ppv - logZ) + rmax[own]) + Mw);
           int j = 0;
-          for (; j + 8 <= T; j += 8) {     // all loads of a batch before its stores
-            float v[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = fmaf(A * tei[j + q], W[j + q], dwi[j + q]);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) dwi[j + q] = v[q];
+          for (; j + 2 <= n4; j += 2) {     // all loads of a batch before its stores
+            const float4 t0 = tei4[j], w0 = W4[j], t1 = tei4[j + 1], w1 = W4[j + 1];
+            float4 d0 = dwi4[j], d1 = dwi4[j + 1];
+            d0.x = fmaf(A * t0.x, w0.x, d0.x); d0.y = fmaf(A * t0.y, w0.y, d0.y);
+            d0.z = fmaf(A * t0.z, w0.z, d0.z); d0.w = fmaf(A * t0.w, w0.w, d0.w);
+            d1.x = fmaf(A * t1.x, w1.x, d1.x); d1.y = fmaf(A * t1.y, w1.y, d1.y);
+            d1.z = fmaf(A * t1.z, w1.z, d1.z); d1.w = fmaf(A * t1.w, w1.w, d1.w);
+            dwi4[j] = d0;
+            dwi4[j + 1] = d1;
           }
-          for (; j < T; ++j) dwi[j] = fmaf(A * tei[j], W[j], dwi[j]);
+          for (; j < n4; ++j) {
+            const float4 t0 = tei4[j], w0 = W4[j];
+            float4 d0 = dwi4[j];
+            d0.x = fmaf(A * t0.x, w0.x, d0.x); d0.y = fmaf(A * t0.y, w0.y, d0.y);
+            d0.z = fmaf(A * t0.z, w0.z, d0.z); d0.w = fmaf(A * t0.w, w0.w, d0.w);
+            dwi4[j] = d0;
+          }
           bb[own] = (rmax[own] + Mw) + logf(S);
         } else {                           // underflow: exact log-domain evaluation of this row
           float mx = -INFINITY;
@@ -1261,9 +1285,13 @@ int re2nn_crf_nll_backward(const float* feats, const float* transitions, const i
       const size_t smem_all = 226 * 1024;
       const int nwe = (int)std::min<size_t>(kCrfWarps, (smem_all - fixed) / pw);
       if (T <= 96 && g_crf_bwd_split) {      // three warps per sequence: a third of the per-step latency
-        const size_t smem_3 = fixed + nwe * pw;
+        const int Tv = (T + 3) & ~3;           // 16-byte rows of the table and the accumulators
+        const size_t fixed3 = ((((size_t)T * T + 3) & ~(size_t)3) + (size_t)T * Tv + Tp) * 4;
+        const size_t pw3 = ((size_t)T * Tv + 3 * Tp) * 4;
+        const int nwe3 = (int)std::min<size_t>(kCrfWarps, (smem_all - fixed3) / pw3);
+        const size_t smem_3 = fixed3 + nwe3 * pw3;
         RE2NN_CUDA(cudaFuncSetAttribute(crf_nll_backward_exp3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_3));
-        crf_nll_backward_exp3_kernel<<<cdiv(B, nwe), nwe * 96, smem_3, st>>>(feats, transitions, lengths, tags, part_save,
+        crf_nll_backward_exp3_kernel<<<cdiv(B, nwe3), nwe3 * 96, smem_3, st>>>(feats, transitions, lengths, tags, part_save,
                                                                              gscale, B, L, Ltags, T, dfeats, dtrans);
         RE2NN_LAUNCH_CHECK();
         return 0;
